@@ -1,0 +1,29 @@
+# Builds the C-ABI shared library (sm_100a only) in-tree so it travels to the GPU box.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+CSRC      := spectral_petsc_b200/csrc
+OBJDIR    := build
+LIB       := spectral_petsc_b200/libspectral_b200.so
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
+HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	g++ -O2 -std=c++17 -fPIC -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+clean:
+	rm -rf $(OBJDIR) $(LIB)
+
+.PHONY: all clean

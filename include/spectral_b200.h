@@ -1,0 +1,96 @@
+/* spectral_b200.h - C ABI of the B200-native matrix-free Chebyshev collocation operator.
+ *
+ * This is the drop-in boundary for ONE path of jedbrown/spectral-petsc: the per-axis
+ * Chebyshev-Gauss-Lobatto derivative (chebyshev.c) and the MatShell / SNES callbacks built on
+ * it (elliptic.C, stokes.C).  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions (mirroring the reference's PETSc conventions):
+ *   - every function returns an int error code, 0 = success (PetscErrorCode convention,
+ *     chebyshev.c:98 SETERRQ / CHKERRQ); sb200_last_error() gives the message.
+ *   - contexts are opaque and NOT re-entrant (shared scratch, like ChebCtx.work / MatElliptic.w).
+ *   - all arithmetic is IEEE fp64; vectors are contiguous doubles with the reference's Vec layout.
+ *   - pointers named d_* are DEVICE pointers (the "VECCUDA-backed Vec"); h_* are HOST pointers.
+ *     x must not alias y; x is preserved, y fully overwritten (chebyshev.c:127 PRESERVE_INPUT).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry points
+ *     are asynchronous on that stream; *_host entry points copy in, run, copy out and synchronise.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with SB200_ERR_CUDA.
+ */
+#ifndef SPECTRAL_B200_H
+#define SPECTRAL_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_OK 0
+#define SB200_ERR_USER 83     /* PETSC_ERR_USER: bad sizes / options (chebyshev.c:98,106,122) */
+#define SB200_ERR_SUP 56      /* PETSC_ERR_SUP: not implemented (stokes.C:452, elliptic.C:406) */
+#define SB200_ERR_CUDA 97     /* CUDA runtime failure or no device */
+#define SB200_ERR_ARG 62      /* PETSC_ERR_ARG_*: null / aliased pointers */
+
+typedef struct sb200_cheb sb200_cheb;         /* replaces ChebCtx      (chebyshev.h:18-24) */
+typedef struct sb200_elliptic sb200_elliptic; /* replaces MatElliptic  (elliptic.C:78-86)  */
+typedef struct sb200_stokes sb200_stokes;     /* replaces StokesCtx    (stokes.C:40-65)    */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int sb200_version(void);
+const char* sb200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+long long sb200_launch_count(void);
+int sb200_device_count(int* n);
+int sb200_set_device(int ordinal);
+/* Device memory helpers so a non-torch host (the C++ PETSc shim) can own VECCUDA-like arrays. */
+int sb200_malloc(void** d_ptr, size_t bytes);
+int sb200_free(void* d_ptr);
+int sb200_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int sb200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int sb200_memset0(void* d_dst, size_t bytes, void* stream);
+int sb200_stream_sync(void* stream);
+
+/* ---- Chebyshev derivative: MatCreateCheb / ChebMult / ChebDestroy (chebyshev.h:31-34) ----- */
+/* MatCreateCheb(comm, rank, tr, dims, flag, vx, vy, &A) (chebyshev.c:89-138).  dims is row-major,
+ * last axis fastest; n_total is the Vec length and must equal prod(dims) (chebyshev.c:122).
+ * Errors like the reference: n_total < 2, tr out of range, size mismatch -> SB200_ERR_USER. */
+int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb200_cheb** out);
+/* ChebMult(A, vx, vy) (chebyshev.c:142-199): y = d x / d xi_tr on the CGL nodes cos(i pi/n). */
+int sb200_cheb_apply(sb200_cheb* c, const double* d_x, double* d_y, void* stream);
+int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y);
+/* ChebDestroy(A) (chebyshev.c:223-235). */
+int sb200_cheb_destroy(sb200_cheb* c);
+/* The P x P differentiation matrix the kernels apply (row-major, host buffer of P*P doubles). */
+int sb200_cheb_matrix(int P, double* h_D);
+
+/* ---- elliptic.C: MatCreate_Elliptic / MatMult_Elliptic / FormFunction ---------------------- */
+/* MatCreate_Elliptic(comm, d, dim, flag, bf, &vG, &A) (elliptic.C:250-293) with the all-Dirichlet
+ * boundary function the reference uses (DirichletBdy, elliptic.C:470-477). */
+int sb200_elliptic_create(int d, const int* dim, sb200_elliptic** out);
+/* DOF distribution printed at elliptic.C:424: local (m), global (g), dirichlet (nd). */
+int sb200_elliptic_sizes(const sb200_elliptic* e, long long* m, long long* g, long long* nd);
+/* -gamma / -exponent (elliptic.C:147-148): eta = 1 + gamma*u^exponent. */
+int sb200_elliptic_set_params(sb200_elliptic* e, double gamma, double exponent);
+/* c->dirichlet (nd doubles, lexicographic boundary order; elliptic.C:672) and ac->b (g doubles, :674). */
+int sb200_elliptic_set_dirichlet(sb200_elliptic* e, const double* d_values, void* stream);
+int sb200_elliptic_set_rhs(sb200_elliptic* e, const double* d_b, void* stream);
+/* MatMult_Elliptic(A, U, V) (elliptic.C:297-339): Jacobian action, U and V of g doubles. */
+int sb200_elliptic_matmult(sb200_elliptic* e, const double* d_U, double* d_V, void* stream);
+int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V);
+/* FormFunction(snes, U, rhs, ctx) (elliptic.C:481-533): residual; refreshes eta/deta/gradu caches. */
+int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream);
+int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F);
+/* Cached state read by FormJacobian (elliptic.C:550-553): which = 0 eta, 1 deta, 2+k gradu[k];
+ * copies m doubles device->device into d_out. */
+int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* d_out, void* stream);
+/* Scatter helpers with the semantics of scatterGL+scatterDL / scatterLG (elliptic.C:426-434). */
+int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream);
+int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, void* stream);
+/* Select kernel path: 0 = auto, 1 = generic per-axis kernels, 2 = fused plane kernels (3-D only). */
+int sb200_elliptic_set_path(sb200_elliptic* e, int path);
+/* MatDestroy_Elliptic (elliptic.C:343-368). */
+int sb200_elliptic_destroy(sb200_elliptic* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRAL_B200_H */

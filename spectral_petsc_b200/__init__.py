@@ -1,0 +1,19 @@
+"""spectral_petsc_b200 - B200-native matrix-free Chebyshev collocation operators.
+
+Host-side mirror of the reference's operator interface (chebyshev.h, elliptic.C, stokes.C) over the
+C-ABI library ``libspectral_b200.so`` (include/spectral_b200.h).  PyTorch is used only for device
+memory, streams and torch.distributed plumbing.  There is no CPU fallback: importing works without
+a GPU (so the ABI can be inspected), but every compute call raises if the CUDA library or a CUDA
+device is missing.
+"""
+from .capi import (  # noqa: F401
+    SB200Error,
+    lib,
+    lib_path,
+    launch_count,
+    Cheb,
+    Elliptic,
+    cheb_matrix,
+)
+
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "cheb_matrix"]

@@ -1,0 +1,203 @@
+"""ctypes binding of include/spectral_b200.h plus thin operator classes.
+
+The classes keep the reference's names and argument meaning:
+  Cheb      <-> MatCreateCheb / ChebMult / ChebDestroy       (chebyshev.c:89-235)
+  Elliptic  <-> MatCreate_Elliptic / MatMult_Elliptic / FormFunction (elliptic.C:250-533)
+Vectors are torch fp64 CUDA tensors (the VECCUDA-backed Vec); only their data_ptr() crosses the ABI.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libspectral_b200.so")
+
+
+class SB200Error(RuntimeError):
+    """Non-zero PetscErrorCode-style return from the C ABI."""
+
+    def __init__(self, code, msg):
+        super().__init__("sb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it was not built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise SB200Error(-1, "CUDA library %s is missing: run `make` or __graft_entry__.build()" % lib_path)
+        L = ctypes.CDLL(lib_path)
+        L.sb200_last_error.restype = ctypes.c_char_p
+        L.sb200_launch_count.restype = ctypes.c_longlong
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise SB200Error(rc, lib().sb200_last_error().decode())
+
+
+def launch_count():
+    return int(lib().sb200_launch_count())
+
+
+def _ptr(t):
+    import torch
+
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise TypeError("expected a contiguous fp64 CUDA tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _hptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def cheb_matrix(P):
+    """The P x P CGL differentiation matrix the kernels apply (host, numpy)."""
+    D = np.empty((P, P))
+    _ck(lib().sb200_cheb_matrix(ctypes.c_int(P), _hptr(D)))
+    return D
+
+
+class Cheb:
+    """MatCreateCheb(comm, rank, tr, dims, flag, vx, vy, &A): y = ChebMult(A, x)."""
+
+    def __init__(self, rank, tr, dims, n_total=None):
+        dims = [int(v) for v in dims]
+        arr = (ctypes.c_int * len(dims))(*dims)
+        n = int(np.prod(dims[:rank])) if n_total is None else int(n_total)
+        self._h = ctypes.c_void_p()
+        _ck(lib().sb200_cheb_create(ctypes.c_int(rank), ctypes.c_int(tr), arr, ctypes.c_longlong(n), ctypes.byref(self._h)))
+        self.N = n
+
+    def mult(self, x, y=None):
+        import torch
+
+        if y is None:
+            y = torch.empty_like(x)
+        if x.numel() != self.N or y.numel() != self.N:
+            raise SB200Error(83, "vector length does not match the operator")
+        _ck(lib().sb200_cheb_apply(self._h, _ptr(x), _ptr(y), _stream()))
+        return y
+
+    def mult_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        _ck(lib().sb200_cheb_apply_host(self._h, _hptr(x), _hptr(y)))
+        return y
+
+    def destroy(self):
+        if self._h:
+            _ck(lib().sb200_cheb_destroy(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Elliptic:
+    """MatCreate_Elliptic + the MatMult_Elliptic / FormFunction callbacks (elliptic.C)."""
+
+    def __init__(self, dim, gamma=0.0, exponent=2.0):
+        dim = [int(v) for v in dim]
+        arr = (ctypes.c_int * len(dim))(*dim)
+        self._h = ctypes.c_void_p()
+        _ck(lib().sb200_elliptic_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        m, g, nd = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        _ck(lib().sb200_elliptic_sizes(self._h, ctypes.byref(m), ctypes.byref(g), ctypes.byref(nd)))
+        self.dim, self.d = dim, len(dim)
+        self.m, self.g, self.nd = m.value, g.value, nd.value
+        self.set_params(gamma, exponent)
+
+    def set_params(self, gamma, exponent):
+        _ck(lib().sb200_elliptic_set_params(self._h, ctypes.c_double(gamma), ctypes.c_double(exponent)))
+
+    def set_path(self, path):
+        _ck(lib().sb200_elliptic_set_path(self._h, ctypes.c_int(path)))
+
+    def set_dirichlet(self, values):
+        assert values.numel() == self.nd
+        _ck(lib().sb200_elliptic_set_dirichlet(self._h, _ptr(values), _stream()))
+
+    def set_rhs(self, b):
+        assert b.numel() == self.g
+        _ck(lib().sb200_elliptic_set_rhs(self._h, _ptr(b), _stream()))
+
+    def mat_mult(self, U, V=None):
+        import torch
+
+        if V is None:
+            V = torch.empty_like(U)
+        assert U.numel() == self.g and V.numel() == self.g
+        _ck(lib().sb200_elliptic_matmult(self._h, _ptr(U), _ptr(V), _stream()))
+        return V
+
+    def form_function(self, U, F=None):
+        import torch
+
+        if F is None:
+            F = torch.empty_like(U)
+        assert U.numel() == self.g and F.numel() == self.g
+        _ck(lib().sb200_elliptic_function(self._h, _ptr(U), _ptr(F), _stream()))
+        return F
+
+    def mat_mult_host(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        V = np.empty_like(U)
+        _ck(lib().sb200_elliptic_matmult_host(self._h, _hptr(U), _hptr(V)))
+        return V
+
+    def form_function_host(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        F = np.empty_like(U)
+        _ck(lib().sb200_elliptic_function_host(self._h, _hptr(U), _hptr(F)))
+        return F
+
+    def get_state(self, which):
+        import torch
+
+        out = torch.empty(self.m, dtype=torch.float64, device="cuda")
+        _ck(lib().sb200_elliptic_get_state(self._h, ctypes.c_int(which), _ptr(out), _stream()))
+        return out
+
+    def pad(self, U, with_dirichlet=False):
+        import torch
+
+        out = torch.empty(self.m, dtype=torch.float64, device="cuda")
+        _ck(lib().sb200_elliptic_pad(self._h, _ptr(U), ctypes.c_int(int(with_dirichlet)), _ptr(out), _stream()))
+        return out
+
+    def crop(self, local):
+        import torch
+
+        out = torch.empty(self.g, dtype=torch.float64, device="cuda")
+        _ck(lib().sb200_elliptic_crop(self._h, _ptr(local), _ptr(out), _stream()))
+        return out
+
+    def destroy(self):
+        if self._h:
+            _ck(lib().sb200_elliptic_destroy(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

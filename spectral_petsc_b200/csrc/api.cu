@@ -1,0 +1,300 @@
+// C ABI (include/spectral_b200.h): thin extern "C" layer over the device contexts.
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/spectral_b200.h"
+#include "cheb_matrix.h"
+#include "common.cuh"
+#include "deriv.h"
+#include "elliptic.h"
+
+namespace sb200 {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace sb200
+
+using namespace sb200;
+
+// ChebCtx replacement: (rank, tr, dims) -> (O, P, R) factorisation + the matrix.
+struct sb200_cheb {
+  int rank, tr;
+  std::vector<int> dims;
+  long long N, O, R;
+  DiffMatrix D;
+  double* d_x = nullptr;  // staging for *_host
+  double* d_y = nullptr;
+};
+
+struct sb200_elliptic {
+  EllipticCtx* c = nullptr;
+  double* d_in = nullptr;  // staging for *_host
+  double* d_out = nullptr;
+  double* h_pin_in = nullptr;
+  double* h_pin_out = nullptr;
+};
+
+extern "C" {
+
+int sb200_version(void) { return 100; }
+
+const char* sb200_last_error(void) { return g_last_error.c_str(); }
+
+long long sb200_launch_count(void) { return g_launches.load(); }
+
+int sb200_device_count(int* n) {
+  SB_CHECK(n, SB200_ERR_ARG, "null pointer");
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    set_last_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return SB200_ERR_CUDA;
+  }
+  return 0;
+}
+
+int sb200_set_device(int ordinal) {
+  SB_CUDA(cudaSetDevice(ordinal));
+  return 0;
+}
+
+int sb200_malloc(void** d_ptr, size_t bytes) {
+  SB_CHECK(d_ptr, SB200_ERR_ARG, "null pointer");
+  SB_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 8));
+  return 0;
+}
+
+int sb200_free(void* d_ptr) {
+  if (d_ptr) SB_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+
+int sb200_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+  SB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+  SB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_memset0(void* d_dst, size_t bytes, void* stream) {
+  SB_CUDA(cudaMemsetAsync(d_dst, 0, bytes, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_stream_sync(void* stream) {
+  SB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+// ---- Chebyshev ---------------------------------------------------------------------------
+int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb200_cheb** out) {
+  SB_CHECK(out && dims, SB200_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (n_total < 2) {  // chebyshev.c:98
+    set_last_error("n = " + std::to_string(n_total) + " but must be >= 2");
+    return SB200_ERR_USER;
+  }
+  SB_CHECK(rank >= 1, SB200_ERR_USER, "rank must be >= 1");
+  SB_CHECK(0 <= tr && tr < rank, SB200_ERR_USER, "tdim out of range");  // chebyshev.c:106
+  long long stride = 1;
+  for (int r = 0; r < rank; r++) {
+    SB_CHECK(dims[r] >= 1, SB200_ERR_USER, "extents must be positive");
+    stride *= dims[r];
+  }
+  if (n_total != stride) {  // chebyshev.c:122
+    set_last_error("dimensions do not agree: n = " + std::to_string(n_total) + " but stride = " + std::to_string(stride));
+    return SB200_ERR_USER;
+  }
+  SB_CHECK(dims[tr] >= 2, SB200_ERR_USER, "transformed extent must be >= 2");
+  sb200_cheb* c = new sb200_cheb();
+  c->rank = rank;
+  c->tr = tr;
+  c->dims.assign(dims, dims + rank);
+  c->N = n_total;
+  c->R = 1;
+  for (int r = tr + 1; r < rank; r++) c->R *= dims[r];
+  c->O = n_total / (c->R * dims[tr]);
+  int rc = DiffMatrix::create(dims[tr], &c->D);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+int sb200_cheb_apply(sb200_cheb* c, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(c && d_x && d_y, SB200_ERR_ARG, "null pointer");
+  DerivParams p;
+  p.D = c->D.d_D;
+  p.P = c->D.P;
+  p.Pp = c->D.Pp;
+  p.x = d_x;
+  p.y = d_y;
+  p.yin = nullptr;
+  p.O = c->O;
+  p.R = c->R;
+  p.xs = p.ys = 1;
+  p.xoff = p.yoff = 0;
+  p.mode = DERIV_STORE;
+  return deriv_apply(p, (cudaStream_t)stream);
+}
+
+int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y) {
+  SB_CHECK(c && h_x && h_y, SB200_ERR_ARG, "null pointer");
+  const size_t bytes = (size_t)c->N * sizeof(double);
+  if (!c->d_x) {
+    SB_CUDA(cudaMalloc((void**)&c->d_x, bytes));
+    SB_CUDA(cudaMalloc((void**)&c->d_y, bytes));
+  }
+  SB_CUDA(cudaMemcpyAsync(c->d_x, h_x, bytes, cudaMemcpyHostToDevice, 0));
+  SB_TRY(sb200_cheb_apply(c, c->d_x, c->d_y, nullptr));
+  SB_CUDA(cudaMemcpyAsync(h_y, c->d_y, bytes, cudaMemcpyDeviceToHost, 0));
+  SB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int sb200_cheb_destroy(sb200_cheb* c) {
+  if (!c) return 0;
+  c->D.destroy();
+  if (c->d_x) cudaFree(c->d_x);
+  if (c->d_y) cudaFree(c->d_y);
+  delete c;
+  return 0;
+}
+
+int sb200_cheb_matrix(int P, double* h_D) {
+  SB_CHECK(P >= 2 && h_D, SB200_ERR_ARG, "bad arguments");
+  std::vector<double> D = cgl_diff_matrix(P);
+  std::memcpy(h_D, D.data(), D.size() * sizeof(double));
+  return 0;
+}
+
+// ---- elliptic ----------------------------------------------------------------------------
+int sb200_elliptic_create(int d, const int* dim, sb200_elliptic** out) {
+  SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
+  *out = nullptr;
+  EllipticCtx* c = nullptr;
+  SB_TRY(EllipticCtx::create(d, dim, &c));
+  sb200_elliptic* e = new sb200_elliptic();
+  e->c = c;
+  *out = e;
+  return 0;
+}
+
+int sb200_elliptic_sizes(const sb200_elliptic* e, long long* m, long long* g, long long* nd) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  if (m) *m = e->c->gd.m;
+  if (g) *g = e->c->gd.g;
+  if (nd) *nd = e->c->gd.m - e->c->gd.g;
+  return 0;
+}
+
+int sb200_elliptic_set_params(sb200_elliptic* e, double gamma, double exponent) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  e->c->gamma = gamma;
+  e->c->exponent = exponent;
+  return 0;
+}
+
+int sb200_elliptic_set_dirichlet(sb200_elliptic* e, const double* d_values, void* stream) {
+  SB_CHECK(e && d_values, SB200_ERR_ARG, "null pointer");
+  const size_t bytes = (size_t)(e->c->gd.m - e->c->gd.g) * sizeof(double);
+  SB_CUDA(cudaMemcpyAsync(e->c->dirichlet, d_values, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_elliptic_set_rhs(sb200_elliptic* e, const double* d_b, void* stream) {
+  SB_CHECK(e && d_b, SB200_ERR_ARG, "null pointer");
+  SB_CUDA(cudaMemcpyAsync(e->c->b, d_b, (size_t)e->c->gd.g * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_elliptic_matmult(sb200_elliptic* e, const double* d_U, double* d_V, void* stream) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  return e->c->matmult(d_U, d_V, (cudaStream_t)stream);
+}
+
+int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  return e->c->function(d_U, d_F, (cudaStream_t)stream);
+}
+
+static int elliptic_host_staging(sb200_elliptic* e) {
+  if (e->d_in) return 0;
+  const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  SB_CUDA(cudaMalloc((void**)&e->d_in, bytes));
+  SB_CUDA(cudaMalloc((void**)&e->d_out, bytes));
+  return 0;
+}
+
+int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V) {
+  SB_CHECK(e && h_U && h_V, SB200_ERR_ARG, "null pointer");
+  SB_TRY(elliptic_host_staging(e));
+  const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  SB_CUDA(cudaMemcpyAsync(e->d_in, h_U, bytes, cudaMemcpyHostToDevice, 0));
+  SB_TRY(e->c->matmult(e->d_in, e->d_out, 0));
+  SB_CUDA(cudaMemcpyAsync(h_V, e->d_out, bytes, cudaMemcpyDeviceToHost, 0));
+  SB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F) {
+  SB_CHECK(e && h_U && h_F, SB200_ERR_ARG, "null pointer");
+  SB_TRY(elliptic_host_staging(e));
+  const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  SB_CUDA(cudaMemcpyAsync(e->d_in, h_U, bytes, cudaMemcpyHostToDevice, 0));
+  SB_TRY(e->c->function(e->d_in, e->d_out, 0));
+  SB_CUDA(cudaMemcpyAsync(h_F, e->d_out, bytes, cudaMemcpyDeviceToHost, 0));
+  SB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* d_out, void* stream) {
+  SB_CHECK(e && d_out, SB200_ERR_ARG, "null pointer");
+  const double* src = nullptr;
+  if (which == 0) src = e->c->eta;
+  else if (which == 1) src = e->c->deta;
+  else if (which >= 2 && which < 2 + e->c->gd.d) src = e->c->gradu[which - 2];
+  SB_CHECK(src, SB200_ERR_USER, "state selector out of range");
+  SB_CUDA(cudaMemcpyAsync(d_out, src, (size_t)e->c->gd.m * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream) {
+  SB_CHECK(e && d_U && d_local, SB200_ERR_ARG, "null pointer");
+  return e->c->pad(d_U, with_dirichlet != 0, d_local, (cudaStream_t)stream);
+}
+
+int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, void* stream) {
+  SB_CHECK(e && d_U && d_local, SB200_ERR_ARG, "null pointer");
+  return e->c->crop(d_local, nullptr, d_U, (cudaStream_t)stream);
+}
+
+int sb200_elliptic_set_path(sb200_elliptic* e, int path) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  SB_CHECK(path >= 0 && path <= 2, SB200_ERR_USER, "path must be 0, 1 or 2");
+  e->c->path = path;
+  return 0;
+}
+
+int sb200_elliptic_destroy(sb200_elliptic* e) {
+  if (!e) return 0;
+  delete e->c;
+  if (e->d_in) cudaFree(e->d_in);
+  if (e->d_out) cudaFree(e->d_out);
+  delete e;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// Internal interface of the generic per-axis derivative kernel (deriv_generic.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sb200 {
+
+enum DerivMode { DERIV_STORE = 0, DERIV_SUB = 1, DERIV_ADD = 2 };
+
+struct DerivParams {
+  const double* D;    // device, Pp x Pp row-major, zero padded
+  int P, Pp;          // extent of the differentiated axis, padded extent (multiple of 32)
+  const double* x;    // input field
+  double* y;          // output field (must not alias x)
+  const double* yin;  // accumulation input for SUB/ADD (may alias y, may be null = 0)
+  long long O, R;     // array factored as (O, P, R), row-major
+  int xs, xoff;       // element e of x lives at x[e*xs + xoff]  (AoS component access)
+  int ys, yoff;       // same for y / yin
+  int mode;           // DerivMode: y = acc | yin - acc | yin + acc
+};
+
+int deriv_apply(const DerivParams& p, cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+}  // namespace sb200

@@ -1,0 +1,277 @@
+// Elliptic operator shells: MatMult_Elliptic (elliptic.C:297-339) and FormFunction
+// (elliptic.C:481-533) on device-resident fp64 vectors, arbitrary dimension.
+//
+// Generic path (any rank / extents): structured pad (scatterGL + scatterDL as index arithmetic,
+// no index arrays), one DMMA derivative launch per axis, one pointwise flux kernel, one
+// derivative launch per axis with the "-=" accumulation fused in its epilogue, structured crop.
+// The 3-D fused plane kernels (elliptic_fused.cu) replace the middle of this when enabled.
+#include "elliptic.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/spectral_b200.h"
+#include "cheb_matrix.h"
+#include "common.cuh"
+#include "deriv.h"
+
+namespace sb200 {
+
+namespace {
+
+__device__ __forceinline__ bool decode_node(const GridDesc& gd, long long idx, long long& gid, long long& did) {
+  // Lexicographic walk semantics of SetupBC (elliptic.C:386-415): a node is on the boundary iff any
+  // index is 0 or dim-1; interior nodes get consecutive global ids, boundary nodes consecutive
+  // dirichlet ids, both in walk (row-major) order.
+  long long rem = idx;
+  long long cnt = 0;       // interior nodes strictly before idx in walk order
+  bool prefix_int = true;  // all more-significant indices interior so far
+  bool bdy = false;
+#pragma unroll 1
+  for (int j = 0; j < gd.d; j++) {
+    const long long s = gd.stride[j];
+    const int i = (int)(rem / s);
+    rem -= (long long)i * s;
+    const bool b = (i == 0) || (i == gd.dim[j] - 1);
+    if (prefix_int) {
+      int c = i - 1;
+      c = c < 0 ? 0 : (c > gd.dim[j] - 2 ? gd.dim[j] - 2 : c);
+      cnt += (long long)c * gd.istride[j];
+      if (b) prefix_int = false;
+    }
+    bdy |= b;
+  }
+  gid = cnt;
+  did = idx - cnt;
+  return !bdy;
+}
+
+__global__ void pad_kernel(GridDesc gd, const double* __restrict__ U, const double* __restrict__ dir,
+                           double* __restrict__ w0) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    long long gid, did;
+    if (decode_node(gd, idx, gid, did))
+      w0[idx] = U[gid];
+    else
+      w0[idx] = dir ? dir[did] : 0.0;
+  }
+}
+
+__global__ void crop_kernel(GridDesc gd, const double* __restrict__ w0, const double* __restrict__ b,
+                            double* __restrict__ V) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    long long gid, did;
+    if (decode_node(gd, idx, gid, did)) {
+      double v = w0[idx];
+      if (b) v = v + (-1.0) * b[gid];  // VecAXPY(rhs, -1.0, ac->b) elliptic.C:530
+      V[gid] = v;
+    }
+  }
+}
+
+struct FluxPtrs {
+  double* w[SB200_MAX_DIM];
+  const double* g0[SB200_MAX_DIM];
+};
+
+// elliptic.C:319-323: w[d] = eta*w[d] + deta*u*gradu[d]
+__global__ void flux_kernel(long long m, int d, const double* __restrict__ u, const double* __restrict__ eta,
+                            const double* __restrict__ deta, FluxPtrs fp) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double e = eta[i], de = deta[i], ui = u[i];
+    for (int k = 0; k < d; k++) {
+      fp.w[k][i] = __dadd_rn(__dmul_rn(e, fp.w[k][i]), __dmul_rn(__dmul_rn(de, ui), fp.g0[k][i]));
+    }
+  }
+}
+
+// elliptic.C:507-513: eta = 1 + gamma*pow(u,p); deta = p*gamma*pow(u,p-1); w[d] = eta*gradu[d]
+__global__ void coef_flux_kernel(long long m, int d, double gamma, double expo, const double* __restrict__ u,
+                                 double* __restrict__ eta, double* __restrict__ deta, FluxPtrs fp) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double ui = u[i];
+    const double e = __dadd_rn(1.0, __dmul_rn(gamma, pow(ui, expo)));
+    const double de = __dmul_rn(__dmul_rn(expo, gamma), pow(ui, expo - 1.0));
+    eta[i] = e;
+    deta[i] = de;
+    for (int k = 0; k < d; k++) fp.w[k][i] = __dmul_rn(e, fp.g0[k][i]);
+  }
+}
+
+int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  return (int)std::min<long long>(b, 148 * 16);
+}
+
+}  // namespace
+
+// ---- derivative-matrix cache -------------------------------------------------------------
+int DiffMatrix::create(int P, DiffMatrix* out) {
+  out->P = P;
+  out->Pp = (P + 31) / 32 * 32;
+  std::vector<double> D = cgl_diff_matrix(P);
+  std::vector<double> Dp((size_t)out->Pp * out->Pp, 0.0);
+  for (int i = 0; i < P; i++)
+    for (int j = 0; j < P; j++) Dp[(size_t)i * out->Pp + j] = D[(size_t)i * P + j];
+  SB_CUDA(cudaMalloc((void**)&out->d_D, Dp.size() * sizeof(double)));
+  SB_CUDA(cudaMemcpy(out->d_D, Dp.data(), Dp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void DiffMatrix::destroy() {
+  if (d_D) cudaFree(d_D);
+  d_D = nullptr;
+}
+
+int GridDesc::init(int d_, const int* dim_) {
+  SB_CHECK(d_ >= 1 && d_ <= SB200_MAX_DIM, SB200_ERR_USER, "dimension count must be in [1,10] (elliptic.C:138)");
+  d = d_;
+  m = 1;
+  g = 1;
+  for (int j = 0; j < d; j++) {
+    SB_CHECK(dim_[j] >= 3, SB200_ERR_USER, "each extent must be >= 3 (needs an interior node)");
+    dim[j] = dim_[j];
+  }
+  for (int j = d - 1; j >= 0; j--) {
+    stride[j] = m;
+    istride[j] = g;
+    m *= dim[j];
+    g *= dim[j] - 2;
+  }
+  return 0;
+}
+
+// ---- EllipticCtx ---------------------------------------------------------------------------
+int EllipticCtx::create(int d, const int* dim, EllipticCtx** out) {
+  EllipticCtx* e = new EllipticCtx();
+  int rc = e->init(d, dim);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+int EllipticCtx::init(int d, const int* dim) {
+  SB_TRY(gd.init(d, dim));
+  nw = 2 + d;  // elliptic.C:259
+  const size_t mb = (size_t)gd.m * sizeof(double);
+  for (int k = 0; k < nw; k++) SB_CUDA(cudaMalloc((void**)&w[k], mb));
+  for (int k = 0; k < d; k++) {
+    SB_CUDA(cudaMalloc((void**)&gradu[k], mb));
+    SB_CUDA(cudaMemset(gradu[k], 0, mb));
+  }
+  SB_CUDA(cudaMalloc((void**)&eta, mb));
+  SB_CUDA(cudaMalloc((void**)&deta, mb));
+  SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
+  SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
+  SB_CUDA(cudaMalloc((void**)&b, (size_t)gd.g * sizeof(double)));
+  SB_CUDA(cudaMemset(b, 0, (size_t)gd.g * sizeof(double)));
+  {  // VecSet(eta, 1.0); VecSet(deta, 0.0) elliptic.C:266-267
+    std::vector<double> ones((size_t)gd.m, 1.0);
+    SB_CUDA(cudaMemcpy(eta, ones.data(), mb, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemset(deta, 0, mb));
+  }
+  for (int k = 0; k < d; k++) {
+    Dax[k] = nullptr;
+    for (int q = 0; q < k; q++)
+      if (gd.dim[q] == gd.dim[k]) Dax[k] = Dax[q];
+    if (!Dax[k]) {
+      DiffMatrix* dm = new DiffMatrix();
+      SB_TRY(DiffMatrix::create(gd.dim[k], dm));
+      owned.push_back(dm);
+      Dax[k] = dm;
+    }
+  }
+  return 0;
+}
+
+EllipticCtx::~EllipticCtx() {
+  for (int k = 0; k < SB200_MAX_DIM + 2; k++)
+    if (w[k]) cudaFree(w[k]);
+  for (int k = 0; k < SB200_MAX_DIM; k++)
+    if (gradu[k]) cudaFree(gradu[k]);
+  if (eta) cudaFree(eta);
+  if (deta) cudaFree(deta);
+  if (dirichlet) cudaFree(dirichlet);
+  if (b) cudaFree(b);
+  for (DiffMatrix* dm : owned) {
+    dm->destroy();
+    delete dm;
+  }
+}
+
+int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
+  DerivParams p;
+  p.D = Dax[axis]->d_D;
+  p.P = Dax[axis]->P;
+  p.Pp = Dax[axis]->Pp;
+  p.x = x;
+  p.y = y;
+  p.yin = yin;
+  p.O = gd.m / (gd.stride[axis] * gd.dim[axis]);
+  p.R = gd.stride[axis];
+  p.xs = p.ys = 1;
+  p.xoff = p.yoff = 0;
+  p.mode = mode;
+  return deriv_apply(p, s);
+}
+
+int EllipticCtx::pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s) {
+  pad_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, U, with_dirichlet ? dirichlet : nullptr, local);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStream_t s) {
+  crop_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, local, rhs, V);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
+  SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
+  const int d = gd.d;
+  SB_TRY(pad(U, false, w[0], s));                                              // :305-308
+  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], w[1 + k], nullptr, DERIV_STORE, s));  // :309-311
+  FluxPtrs fp;
+  for (int k = 0; k < d; k++) {
+    fp.w[k] = w[1 + k];
+    fp.g0[k] = gradu[k];
+  }
+  flux_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd.m, d, w[0], eta, deta, fp);  // :319-323
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  // :329-334  w0 = 0; w0 -= D_k w[1+k] in axis order (the AXPY is the derivative's epilogue)
+  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[1 + k], w[0], k == 0 ? nullptr : w[0], DERIV_SUB, s));
+  SB_TRY(crop(w[0], nullptr, V, s));  // :336-337
+  return 0;
+}
+
+int EllipticCtx::function(const double* U, double* F, cudaStream_t s) {
+  SB_CHECK(U && F && U != F, SB200_ERR_ARG, "FormFunction: U and F must be distinct non-null vectors");
+  const int d = gd.d;
+  SB_TRY(pad(U, true, w[0], s));                                                   // :489-492
+  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], gradu[k], nullptr, DERIV_STORE, s));  // :497-499
+  FluxPtrs fp;
+  for (int k = 0; k < d; k++) {
+    fp.w[k] = w[1 + k];
+    fp.g0[k] = gradu[k];
+  }
+  coef_flux_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd.m, d, gamma, exponent, w[0], eta, deta, fp);  // :506-513
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[1 + k], w[0], k == 0 ? nullptr : w[0], DERIV_SUB, s));  // :520-524
+  SB_TRY(crop(w[0], b, F, s));  // :528-531
+  return 0;
+}
+
+}  // namespace sb200
