@@ -1,0 +1,120 @@
+// Warp-private even-odd DMMA machinery for the fused "chain" kernels.
+//
+// A chain along one axis is  out (-)= D * flux(D * w)  for every grid line of that axis
+// (MatMult_Elliptic's  w[1+d] = D_d w0 ; pointwise ; w0 -= D_d w[1+d],  elliptic.C:309-334).
+// One warp owns a block of 8 lines (all P points of each) in shared memory and runs the whole
+// chain on it with no CTA-level synchronisation:
+//     GEMM1 (DMMA)  ->  flux in registers  ->  overwrite the block in place  ->  GEMM2 (DMMA)  ->  epilogue.
+//
+// Even-odd split: the CGL matrix is centro-antisymmetric, D[n-i][n-j] = -D[i][j] (n = P-1), so with
+//   s_j = u_j + u_{n-j},  d_j = u_j - u_{n-j},  Ae = (D[i][j] + D[i][n-j])/2,  Bo = (D[i][j] - D[i][n-j])/2
+//   a = Ae s,  b = Bo d   (two h x h products, h = P/2)      y_i = a_i + b_i,   y_{n-i} = b_i - a_i
+// which halves the executed flops of the dense P x P product.  s and d are formed on the fly from the
+// two shared-memory loads that feed the B fragments; Ae/Bo stay resident in shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace sb200 {
+
+template <int P>
+struct EO {
+  static constexpr int H = P / 2;        // pair count
+  static constexpr int MT = H / 8;       // m-tiles of pair rows
+  static constexpr int KS = H / 4;       // k4 steps
+  static constexpr int LDM = H + 4;      // matrix leading dim in smem: (4g+t) mod 16 distinct
+  static constexpr int LDR = P + 4;      // RIGHT block leading dim
+  static constexpr int MAT_ELEMS = 2 * H * LDM;
+  static constexpr int BLOCK_ELEMS_LEFT = P * 8;
+  static constexpr int BLOCK_ELEMS_RIGHT = 8 * LDR;
+  static_assert(P % 16 == 0, "even-odd DMMA path needs P % 16 == 0");
+};
+
+// Shared-memory address of element (row m along the axis, line c in 0..7) of a warp's block.
+template <int P, bool RIGHT>
+__device__ __forceinline__ int xaddr(int m, int c) {
+  if (RIGHT) return c * EO<P>::LDR + m;
+  return m * 8 + (c ^ (((m >> 1) & 1) << 2));  // XOR swizzle keeps the B-fragment loads conflict free
+}
+
+// a[mt], b[mt] (+)= Ae * s, Bo * d  for the warp's 8 lines.  acc layout: row = mt*8+g, cols 2t, 2t+1.
+template <int P, bool RIGHT>
+__device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const double* __restrict__ Bo,
+                                        const double* __restrict__ Xw, double (&a)[EO<P>::MT][2],
+                                        double (&b)[EO<P>::MT][2], int g, int t) {
+  using E = EO<P>;
+#pragma unroll
+  for (int i = 0; i < E::MT; i++) a[i][0] = a[i][1] = b[i][0] = b[i][1] = 0.0;
+#pragma unroll 4
+  for (int ks = 0; ks < E::KS; ks++) {
+    const int kk = ks * 4 + t;
+    const double p = Xw[xaddr<P, RIGHT>(kk, g)];
+    const double q = Xw[xaddr<P, RIGHT>(P - 1 - kk, g)];
+    const double s = p + q, d = p - q;
+    double fa[E::MT], fb[E::MT];
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) {
+      fa[i] = Ae[(i * 8 + g) * E::LDM + kk];
+      fb[i] = Bo[(i * 8 + g) * E::LDM + kk];
+    }
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) {
+      dmma884(a[i][0], a[i][1], fa[i], s);
+      dmma884(b[i][0], b[i][1], fb[i], d);
+    }
+  }
+}
+
+// Cooperative (whole CTA) load of Ae, Bo ([H][H] row-major in global) into padded smem.
+template <int P>
+__device__ __forceinline__ void load_matrices(double* sm, const double* __restrict__ gAe, const double* __restrict__ gBo) {
+  using E = EO<P>;
+  for (int idx = threadIdx.x; idx < E::H * E::H / 2; idx += blockDim.x) {
+    const int r = idx / (E::H / 2), c2 = (idx % (E::H / 2)) * 2;
+    cp_async16(sm + r * E::LDM + c2, gAe + r * E::H + c2, true);
+    cp_async16(sm + E::H * E::LDM + r * E::LDM + c2, gBo + r * E::H + c2, true);
+  }
+  cp_async_commit();
+}
+
+// Line addressing for an array factored as (O, P, R): line n = o*R + r starts at o*P*R + r, stride R.
+struct LineGeom {
+  long long R, PR, nlines;
+  __device__ __forceinline__ long long base(long long n) const {
+    const long long o = n / R, r = n - o * R;
+    return o * PR + r;
+  }
+};
+
+// Warp-level load of one 8-line block of field x into Xw (zero fill beyond nlines).
+template <int P, bool RIGHT>
+__device__ __forceinline__ void load_block(double* Xw, const double* __restrict__ x, const LineGeom& lg,
+                                           long long n0, int lane) {
+  using E = EO<P>;
+  if (RIGHT) {
+    // R == 1: each line is P contiguous doubles
+#pragma unroll 4
+    for (int idx = lane; idx < 8 * (P / 2); idx += 32) {
+      const int c = idx / (P / 2), m2 = (idx % (P / 2)) * 2;
+      const bool ok = (n0 + c) < lg.nlines;
+      cp_async16(Xw + c * E::LDR + m2, x + (ok ? (n0 + c) * P + m2 : 0), ok);
+    }
+  } else {
+    const bool fast = (lg.R % 8 == 0) && (n0 + 8 <= lg.nlines);
+    if (fast) {
+      const long long b0 = lg.base(n0);
+#pragma unroll 4
+      for (int idx = lane; idx < P * 4; idx += 32) {
+        const int m = idx >> 2, c2 = (idx & 3) * 2;
+        cp_async16(Xw + xaddr<P, false>(m, c2), x + b0 + (long long)m * lg.R + c2, true);
+      }
+    } else {
+      const int c = lane & 7;
+      const bool ok = (n0 + c) < lg.nlines;
+      const long long bc = ok ? lg.base(n0 + c) : 0;
+      for (int m = lane >> 3; m < P; m += 4) cp_async8(Xw + xaddr<P, false>(m, c), x + bc + (long long)m * lg.R, ok);
+    }
+  }
+  cp_async_commit();
+}
+
+}  // namespace sb200

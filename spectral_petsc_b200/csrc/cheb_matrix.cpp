@@ -4,9 +4,9 @@
 
 namespace sb200 {
 
-std::vector<double> cgl_diff_matrix(int P) {
+static std::vector<long double> cgl_diff_matrix_ld(int P) {
   const int n = P - 1;
-  std::vector<double> D((size_t)P * P, 0.0);
+  std::vector<long double> D((size_t)P * P, 0.0L);
   if (n < 1) return D;
   const long double pi = 3.14159265358979323846264338327950288L;
   auto cbar = [n](int i) { return (i == 0 || i == n) ? 2.0L : 1.0L; };
@@ -29,10 +29,30 @@ std::vector<double> cgl_diff_matrix(int P) {
         long double c = cosl(pi * (long double)i / n);
         v = -c / (2.0L * s * s);
       }
-      D[(size_t)i * P + j] = (double)v;
+      D[(size_t)i * P + j] = v;
     }
   }
   return D;
+}
+
+std::vector<double> cgl_diff_matrix(int P) {
+  std::vector<long double> L = cgl_diff_matrix_ld(P);
+  std::vector<double> D(L.size());
+  for (size_t k = 0; k < L.size(); k++) D[k] = (double)L[k];
+  return D;
+}
+
+void cgl_even_odd(int P, std::vector<double>& Ae, std::vector<double>& Bo) {
+  const int n = P - 1, h = P / 2;
+  std::vector<long double> L = cgl_diff_matrix_ld(P);
+  Ae.assign((size_t)h * h, 0.0);
+  Bo.assign((size_t)h * h, 0.0);
+  for (int i = 0; i < h; i++)
+    for (int j = 0; j < h; j++) {
+      const long double p = L[(size_t)i * P + j], q = L[(size_t)i * P + (n - j)];
+      Ae[(size_t)i * h + j] = (double)(0.5L * (p + q));
+      Bo[(size_t)i * h + j] = (double)(0.5L * (p - q));
+    }
 }
 
 }  // namespace sb200

@@ -8,4 +8,7 @@ namespace sb200 {
 // (chebyshev.c:142-199) applies through DCT-I -> *k -> DST-I -> 1/(2n sin); entries are formed in
 // 80-bit long double with the product-to-sum form of x_i - x_j and rounded once to fp64.
 std::vector<double> cgl_diff_matrix(int P);
+// Even-odd halves for even P (h = P/2, row-major h x h), formed in long double and rounded once:
+//   Ae[i][j] = (D[i][j] + D[i][P-1-j])/2,  Bo[i][j] = (D[i][j] - D[i][P-1-j])/2   (see chain.cuh).
+void cgl_even_odd(int P, std::vector<double>& Ae, std::vector<double>& Bo);
 }  // namespace sb200

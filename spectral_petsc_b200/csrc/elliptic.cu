@@ -120,12 +120,22 @@ int DiffMatrix::create(int P, DiffMatrix* out) {
     for (int j = 0; j < P; j++) Dp[(size_t)i * out->Pp + j] = D[(size_t)i * P + j];
   SB_CUDA(cudaMalloc((void**)&out->d_D, Dp.size() * sizeof(double)));
   SB_CUDA(cudaMemcpy(out->d_D, Dp.data(), Dp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (P % 2 == 0) {
+    std::vector<double> Ae, Bo;
+    cgl_even_odd(P, Ae, Bo);
+    SB_CUDA(cudaMalloc((void**)&out->d_Ae, Ae.size() * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&out->d_Bo, Bo.size() * sizeof(double)));
+    SB_CUDA(cudaMemcpy(out->d_Ae, Ae.data(), Ae.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(out->d_Bo, Bo.data(), Bo.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
 void DiffMatrix::destroy() {
   if (d_D) cudaFree(d_D);
-  d_D = nullptr;
+  if (d_Ae) cudaFree(d_Ae);
+  if (d_Bo) cudaFree(d_Bo);
+  d_D = d_Ae = d_Bo = nullptr;
 }
 
 int GridDesc::init(int d_, const int* dim_) {
@@ -240,6 +250,10 @@ int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStr
 int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
   SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
   const int d = gd.d;
+  if (path == 2 || (path == 0 && elliptic_fused_supported(*this))) {
+    SB_CHECK(elliptic_fused_supported(*this), SB200_ERR_SUP, "fused path needs equal extents P in {32,64,128}");
+    return elliptic_matmult_fused(*this, U, V, s);
+  }
   SB_TRY(pad(U, false, w[0], s));                                              // :305-308
   for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], w[1 + k], nullptr, DERIV_STORE, s));  // :309-311
   FluxPtrs fp;

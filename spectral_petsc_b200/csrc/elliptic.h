@@ -12,6 +12,8 @@ namespace sb200 {
 struct DiffMatrix {
   int P = 0, Pp = 0;
   double* d_D = nullptr;
+  double* d_Ae = nullptr;  // even-odd halves (P even), [P/2][P/2] row-major
+  double* d_Bo = nullptr;
   static int create(int P, DiffMatrix* out);
   void destroy();
 };
@@ -49,5 +51,8 @@ struct EllipticCtx {
   int matmult(const double* U, double* V, cudaStream_t s);
   int function(const double* U, double* F, cudaStream_t s);
 };
+
+bool elliptic_fused_supported(const EllipticCtx& e);
+int elliptic_matmult_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
 
 }  // namespace sb200

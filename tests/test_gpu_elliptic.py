@@ -87,3 +87,31 @@ def test_full_size_128(cuda):
     lhs = G.mat_mult(3.0 * a - b)
     rhs = 3.0 * G.mat_mult(a) - G.mat_mult(b)
     assert ((lhs - rhs).abs().max() / rhs.abs().max()).item() < 1e-12
+
+
+@pytest.mark.parametrize("dim", [[32, 32], [32, 32, 32], [64, 64, 64], [32, 32, 32, 32], [128, 128]], ids=lambda v: str(v))
+def test_fused_chain_path_matches_generic_and_oracle(cuda, dim):
+    # path 2 = persistent even-odd chain kernels, path 1 = generic per-axis kernels
+    O, G, u, u2 = make_pair(dim, 4.0, 2.0, cuda)
+    Us = 0.1 * np.random.default_rng(1).standard_normal(O.g)
+    O.form_function(Us)
+    G.form_function(torch.from_numpy(Us).to(cuda))
+    U = np.random.default_rng(0).standard_normal(O.g)
+    Vo = O.mat_mult(U)
+    Ud = torch.from_numpy(U).to(cuda)
+    G.set_path(1)
+    V1 = G.mat_mult(Ud).cpu().numpy()
+    G.set_path(2)
+    V2 = G.mat_mult(Ud).cpu().numpy()
+    assert rel_max(V1, Vo) < TOL
+    assert rel_max(V2, Vo) < TOL
+    assert rel_max(V2, V1) < 1e-13
+
+
+def test_fused_path_rejects_unsupported_extents(cuda):
+    G = sp.Elliptic([16, 16, 16])
+    G.set_path(2)
+    U = torch.zeros(G.g, dtype=torch.float64, device=cuda)
+    with pytest.raises(sp.SB200Error) as ei:
+        G.mat_mult(U)
+    assert ei.value.code == 56
