@@ -36,7 +36,10 @@ __device__ __forceinline__ int xaddr(int m, int c) {
   return m * 8 + (c ^ (((m >> 1) & 1) << 2));  // XOR swizzle keeps the B-fragment loads conflict free
 }
 
-// a[mt], b[mt] (+)= Ae * s, Bo * d  for the warp's 8 lines.  acc layout: row = mt*8+g, cols 2t, 2t+1.
+// a[i], b[i] = Ae * s, Bo * d  for the warp's 8 lines (i = tile of 8 pair indices).
+// LEFT  (!RIGHT): matrices are the A operand.  acc[i][h] <-> pair index i*8+g, line 2t+h.
+// RIGHT:          the field is the A operand.   acc[i][h] <-> line g, pair index i*8+2t+h.
+// Either way a thread's two values are adjacent in global memory (16-byte accesses).
 template <int P, bool RIGHT>
 __device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const double* __restrict__ Bo,
                                         const double* __restrict__ Xw, double (&a)[EO<P>::MT][2],
@@ -58,9 +61,57 @@ __device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const dou
     }
 #pragma unroll
     for (int i = 0; i < E::MT; i++) {
-      dmma884(a[i][0], a[i][1], fa[i], s);
-      dmma884(b[i][0], b[i][1], fb[i], d);
+      if (RIGHT) {
+        dmma884(a[i][0], a[i][1], s, fa[i]);
+        dmma884(b[i][0], b[i][1], d, fb[i]);
+      } else {
+        dmma884(a[i][0], a[i][1], fa[i], s);
+        dmma884(b[i][0], b[i][1], fb[i], d);
+      }
     }
+  }
+}
+
+// Thread-owned element geometry shared by every epilogue.  For tile i the thread owns a "top" pair
+// of adjacent elements and the mirrored "bottom" pair (also adjacent, in reversed order):
+//   LEFT : rows mt = i*8+g / mb = P-1-mt, lines 2t,2t+1        -> global offset base0 + m*R + 2t
+//   RIGHT: line g, rows i*8+2t,+1 / mirrors P-2-i*8-2t,+1      -> global offset (n0+g)*P + row
+// top[h]  <-> acc (a+b)[i][h];   LEFT: bot[h] <-> (b-a)[i][h];   RIGHT: bot[h] <-> (b-a)[i][1-h].
+template <int P, bool RIGHT>
+struct Own {
+  long long base;  // LEFT: base0 + 2t ; RIGHT: (n0+g)*P
+  long long R;
+  int g, t;
+  __device__ __forceinline__ long long top(int i) const {
+    return RIGHT ? base + i * 8 + 2 * t : base + (long long)(i * 8 + g) * R;
+  }
+  __device__ __forceinline__ long long bot(int i) const {
+    return RIGHT ? base + (P - 2 - i * 8 - 2 * t) : base + (long long)(P - 1 - i * 8 - g) * R;
+  }
+  // shared-memory addresses of the same pairs inside the warp's block (both 16-byte aligned)
+  __device__ __forceinline__ int stop(int i) const {
+    return RIGHT ? xaddr<P, true>(i * 8 + 2 * t, g) : xaddr<P, false>(i * 8 + g, 2 * t);
+  }
+  __device__ __forceinline__ int sbot(int i) const {
+    return RIGHT ? xaddr<P, true>(P - 2 - i * 8 - 2 * t, g) : xaddr<P, false>(P - 1 - i * 8 - g, 2 * t);
+  }
+};
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Warp-level L2 prefetch of the block's footprint in array x (issued long before the epilogue reads it).
+template <int P, bool RIGHT>
+__device__ __forceinline__ void prefetch_block(const double* __restrict__ x, long long base0, long long R, int lane) {
+  if (RIGHT) {
+    // 8 lines x P contiguous doubles starting at base0 = n0*P : 8*P*8 bytes = P/2 lines of 128 B
+#pragma unroll
+    for (int l = lane; l < P / 2; l += 32) prefetch_l2(x + base0 + l * 16);
+  } else {
+#pragma unroll
+    for (int m = lane; m < P; m += 32) prefetch_l2(x + base0 + (long long)m * R);
   }
 }
 

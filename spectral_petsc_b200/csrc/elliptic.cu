@@ -20,17 +20,21 @@ namespace sb200 {
 
 namespace {
 
-__device__ __forceinline__ bool decode_node(const GridDesc& gd, long long idx, long long& gid, long long& did) {
-  // Lexicographic walk semantics of SetupBC (elliptic.C:386-415): a node is on the boundary iff any
-  // index is 0 or dim-1; interior nodes get consecutive global ids, boundary nodes consecutive
-  // dirichlet ids, both in walk (row-major) order.
-  long long rem = idx;
-  long long cnt = 0;       // interior nodes strictly before idx in walk order
-  bool prefix_int = true;  // all more-significant indices interior so far
-  bool bdy = false;
-#pragma unroll 1
-  for (int j = 0; j < gd.d; j++) {
-    const long long s = gd.stride[j];
+// Line-based pad / crop: one (ty) thread row per grid line of the LAST axis, so the d-1 leading
+// indices are decoded once per line and the walk along the line is contiguous in both vectors.
+struct LineInfo {
+  bool interior;   // all leading indices interior
+  long long gid0;  // global id of the line's first interior node (k = 1)
+  long long did0;  // dirichlet id of the line's first node (k = 0)
+};
+
+__device__ __forceinline__ LineInfo decode_line(const GridDesc& gd, long long line) {
+  // Same walk-order semantics as SetupBC (elliptic.C:386-415), specialised to whole last-axis lines.
+  const int d = gd.d, PL = gd.dim[d - 1];
+  long long rem = line, cnt = 0;
+  bool prefix_int = true;
+  for (int j = 0; j < d - 1; j++) {
+    const long long s = gd.stride[j] / PL;
     const int i = (int)(rem / s);
     rem -= (long long)i * s;
     const bool b = (i == 0) || (i == gd.dim[j] - 1);
@@ -40,35 +44,44 @@ __device__ __forceinline__ bool decode_node(const GridDesc& gd, long long idx, l
       cnt += (long long)c * gd.istride[j];
       if (b) prefix_int = false;
     }
-    bdy |= b;
   }
-  gid = cnt;
-  did = idx - cnt;
-  return !bdy;
+  LineInfo li;
+  li.interior = prefix_int;
+  li.gid0 = cnt;                 // interior nodes before this line
+  li.did0 = line * PL - cnt;     // boundary nodes before this line
+  return li;
 }
 
-__global__ void pad_kernel(GridDesc gd, const double* __restrict__ U, const double* __restrict__ dir,
-                           double* __restrict__ w0) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
-    long long gid, did;
-    if (decode_node(gd, idx, gid, did))
-      w0[idx] = U[gid];
-    else
-      w0[idx] = dir ? dir[did] : 0.0;
+__global__ void pad_kernel(GridDesc gd, long long nlines, const double* __restrict__ U,
+                           const double* __restrict__ dir, double* __restrict__ w0) {
+  const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (line >= nlines) return;
+  const int PL = gd.dim[gd.d - 1];
+  const LineInfo li = decode_line(gd, line);
+  double* wl = w0 + line * PL;
+  for (int k = threadIdx.x; k < PL; k += blockDim.x) {
+    double v;
+    if (li.interior && k > 0 && k < PL - 1) v = U[li.gid0 + k - 1];
+    else if (!dir) v = 0.0;
+    else if (!li.interior) v = dir[li.did0 + k];
+    else v = dir[li.did0 + (k == 0 ? 0 : 1)];
+    wl[k] = v;
   }
 }
 
-__global__ void crop_kernel(GridDesc gd, const double* __restrict__ w0, const double* __restrict__ b,
-                            double* __restrict__ V) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
-    long long gid, did;
-    if (decode_node(gd, idx, gid, did)) {
-      double v = w0[idx];
-      if (b) v = v + (-1.0) * b[gid];  // VecAXPY(rhs, -1.0, ac->b) elliptic.C:530
-      V[gid] = v;
-    }
+__global__ void crop_kernel(GridDesc gd, long long nlines, const double* __restrict__ w0,
+                            const double* __restrict__ b, double* __restrict__ V) {
+  const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (line >= nlines) return;
+  const int PL = gd.dim[gd.d - 1];
+  const LineInfo li = decode_line(gd, line);
+  if (!li.interior) return;
+  const double* wl = w0 + line * PL;
+  for (int k = 1 + threadIdx.x; k < PL - 1; k += blockDim.x) {
+    double v = wl[k];
+    const long long gid = li.gid0 + k - 1;
+    if (b) v = v + (-1.0) * b[gid];  // VecAXPY(rhs, -1.0, ac->b) elliptic.C:530
+    V[gid] = v;
   }
 }
 
@@ -234,14 +247,22 @@ int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, 
 }
 
 int EllipticCtx::pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s) {
-  pad_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, U, with_dirichlet ? dirichlet : nullptr, local);
+  const int PL = gd.dim[gd.d - 1];
+  const long long nlines = gd.m / PL;
+  const int tx = PL >= 128 ? 128 : (PL > 32 ? 64 : 32);
+  dim3 blk(tx, 256 / tx);
+  pad_kernel<<<(unsigned)((nlines + blk.y - 1) / blk.y), blk, 0, s>>>(gd, nlines, U, with_dirichlet ? dirichlet : nullptr, local);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;
 }
 
 int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStream_t s) {
-  crop_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, local, rhs, V);
+  const int PL = gd.dim[gd.d - 1];
+  const long long nlines = gd.m / PL;
+  const int tx = PL >= 128 ? 128 : (PL > 32 ? 64 : 32);
+  dim3 blk(tx, 256 / tx);
+  crop_kernel<<<(unsigned)((nlines + blk.y - 1) / blk.y), blk, 0, s>>>(gd, nlines, local, rhs, V);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;

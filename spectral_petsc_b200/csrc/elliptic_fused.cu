@@ -11,6 +11,8 @@
 #include "deriv.h"
 #include "elliptic.h"
 
+#include <cstdlib>
+
 namespace sb200 {
 
 namespace {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) chain_kernel(ChainParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   double* Xw = sm + E::MAT_ELEMS + warp * BE;
 
-  const long long nblocks = (p.lg.nlines + 7) / 8;
+  const long long nblocks = p.lg.nlines / 8;  // host guarantees nlines % 8 == 0
   const long long per = (nblocks + gridDim.x - 1) / gridDim.x;
   const long long b_begin = (long long)blockIdx.x * per;
   const long long b_end = b_begin + per < nblocks ? b_begin + per : nblocks;
@@ -57,38 +59,49 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) chain_kernel(ChainParams p) {
 
   for (; blk < b_end; blk += NWARPS) {
     const long long n0 = blk * 8;
-    // per-thread global bases of its two C-fragment columns (lines n0+2t, n0+2t+1)
-    long long base[2];
-    bool lok[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const long long n = n0 + 2 * t + h;
-      lok[h] = n < p.lg.nlines;
-      base[h] = lok[h] ? p.lg.base(n) : 0;
-    }
+    const long long base0 = RIGHT ? n0 * P : p.lg.base(n0);
+    Own<P, RIGHT> own;
+    own.base = RIGHT ? (n0 + g) * P : base0 + 2 * t;
+    own.R = p.lg.R;
+    own.g = g;
+    own.t = t;
+    // pull the epilogue operands of this block towards L2 while the tensor pipe works
+    prefetch_block<P, RIGHT>(p.eta, base0, p.lg.R, lane);
+    prefetch_block<P, RIGHT>(p.deta, base0, p.lg.R, lane);
+    prefetch_block<P, RIGHT>(p.g0, base0, p.lg.R, lane);
+    if (POS != POS_FIRST) prefetch_block<P, RIGHT>(p.out, base0, p.lg.R, lane);
+
     double a[E::MT][2], b[E::MT][2];
     eo_gemm<P, RIGHT>(Ae, Bo, Xw, a, b, g, t);
     __syncwarp();
-    // flux (elliptic.C:319-323), written back in place: f = eta*y + (deta*w)*g0
+    // flux (elliptic.C:319-323) written back in place: f = eta*y + (deta*w)*g0 ; loads batched 2 tiles deep
 #pragma unroll
-    for (int i = 0; i < E::MT; i++) {
-      const int r = i * 8 + g;
+    for (int ib = 0; ib < E::MT; ib += 2) {
+      double2 e[2][2], de[2][2], gg[2][2];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int c = 2 * t + h;
-        const double ytop = a[i][h] + b[i][h];
-        const double ybot = b[i][h] - a[i][h];
-        const int mt = r, mb = P - 1 - r;
-        double ft = 0.0, fb = 0.0;
-        if (lok[h]) {
-          const long long et = base[h] + (long long)mt * p.lg.R;
-          const long long eb = base[h] + (long long)mb * p.lg.R;
-          const double wt = Xw[xaddr<P, RIGHT>(mt, c)], wb = Xw[xaddr<P, RIGHT>(mb, c)];
-          ft = __dadd_rn(__dmul_rn(__ldg(p.eta + et), ytop), __dmul_rn(__dmul_rn(__ldg(p.deta + et), wt), __ldg(p.g0 + et)));
-          fb = __dadd_rn(__dmul_rn(__ldg(p.eta + eb), ybot), __dmul_rn(__dmul_rn(__ldg(p.deta + eb), wb), __ldg(p.g0 + eb)));
-        }
-        Xw[xaddr<P, RIGHT>(mt, c)] = ft;
-        Xw[xaddr<P, RIGHT>(mb, c)] = fb;
+      for (int ii = 0; ii < 2; ii++) {
+        const long long ot = own.top(ib + ii), ob = own.bot(ib + ii);
+        e[ii][0] = ldg2(p.eta + ot);
+        e[ii][1] = ldg2(p.eta + ob);
+        de[ii][0] = ldg2(p.deta + ot);
+        de[ii][1] = ldg2(p.deta + ob);
+        gg[ii][0] = ldg2(p.g0 + ot);
+        gg[ii][1] = ldg2(p.g0 + ob);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 2; ii++) {
+        const int i = ib + ii;
+        const int st = own.stop(i), sb = own.sbot(i);
+        const double2 wt = ld2(Xw + st), wb = ld2(Xw + sb);
+        const double yt0 = a[i][0] + b[i][0], yt1 = a[i][1] + b[i][1];
+        const double yb0 = RIGHT ? b[i][1] - a[i][1] : b[i][0] - a[i][0];
+        const double yb1 = RIGHT ? b[i][0] - a[i][0] : b[i][1] - a[i][1];
+        const double ft0 = __dadd_rn(__dmul_rn(e[ii][0].x, yt0), __dmul_rn(__dmul_rn(de[ii][0].x, wt.x), gg[ii][0].x));
+        const double ft1 = __dadd_rn(__dmul_rn(e[ii][0].y, yt1), __dmul_rn(__dmul_rn(de[ii][0].y, wt.y), gg[ii][0].y));
+        const double fb0 = __dadd_rn(__dmul_rn(e[ii][1].x, yb0), __dmul_rn(__dmul_rn(de[ii][1].x, wb.x), gg[ii][1].x));
+        const double fb1 = __dadd_rn(__dmul_rn(e[ii][1].y, yb1), __dmul_rn(__dmul_rn(de[ii][1].y, wb.y), gg[ii][1].y));
+        st2(Xw + st, ft0, ft1);
+        st2(Xw + sb, fb0, fb1);
       }
     }
     __syncwarp();
@@ -97,48 +110,52 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) chain_kernel(ChainParams p) {
     const long long nblk = blk + NWARPS;
     if (nblk < b_end) load_block<P, RIGHT>(Xw, p.w, p.lg, nblk * 8, lane);  // overlaps the epilogue
 
-    // epilogue: out = (FIRST ? 0 : out) - D f ; LAST crops into V
-    long long vrow[2] = {0, 0};
-    bool vint[2] = {false, false};
+    // epilogue: out = (FIRST ? 0 : out) - D f ; LAST crops into V (LAST is always the R == 1 axis)
+    long long vrow = 0;
+    bool vint = false;
     if (POS == POS_LAST) {
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        // line index = lexicographic index over the leading d-1 axes; interior id of the line
-        long long n = n0 + 2 * t + h, gid = 0, mul = 1;
-        bool interior = lok[h];
-        for (int j = p.d - 2; j >= 0; j--) {
-          const int ij = (int)(n % p.dim[j]);
-          n /= p.dim[j];
-          interior = interior && ij > 0 && ij < p.dim[j] - 1;
-          gid += (long long)(ij - 1) * mul;
-          mul *= p.dim[j] - 2;
-        }
-        vint[h] = interior;
-        vrow[h] = gid * (P - 2);
+      // line index = lexicographic index over the leading d-1 axes; interior id of the line
+      long long n = n0 + g, gid = 0, mul = 1;
+      vint = true;
+      for (int j = p.d - 2; j >= 0; j--) {
+        const int ij = (int)(n % p.dim[j]);
+        n /= p.dim[j];
+        vint = vint && ij > 0 && ij < p.dim[j] - 1;
+        gid += (long long)(ij - 1) * mul;
+        mul *= p.dim[j] - 2;
       }
+      vrow = gid * (P - 2) - 1;  // V index of row m is vrow + m
     }
 #pragma unroll
-    for (int i = 0; i < E::MT; i++) {
-      const int r = i * 8 + g;
+    for (int ib = 0; ib < E::MT; ib += 4) {
+      double2 ot[4], ob[4];
+      if (POS != POS_FIRST) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        if (!lok[h]) continue;
-        const double ytop = a[i][h] + b[i][h];
-        const double ybot = b[i][h] - a[i][h];
-        const int mt = r, mb = P - 1 - r;
-        const long long et = base[h] + (long long)mt * p.lg.R;
-        const long long eb = base[h] + (long long)mb * p.lg.R;
-        if (POS == POS_FIRST) {
-          p.out[et] = 0.0 - ytop;
-          p.out[eb] = 0.0 - ybot;
-        } else if (POS == POS_MID) {
-          p.out[et] = p.out[et] - ytop;
-          p.out[eb] = p.out[eb] - ybot;
-        } else {
-          if (vint[h]) {
-            if (mt > 0) p.V[vrow[h] + mt - 1] = p.out[et] - ytop;  // mt < P/2 so never the far end
-            if (mb < P - 1) p.V[vrow[h] + mb - 1] = p.out[eb] - ybot;
-          }
+        for (int ii = 0; ii < 4; ii++) {
+          ot[ii] = ld2(p.out + own.top(ib + ii));
+          ob[ii] = ld2(p.out + own.bot(ib + ii));
+        }
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) ot[ii] = ob[ii] = make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++) {
+        const int i = ib + ii;
+        const double yt0 = a[i][0] + b[i][0], yt1 = a[i][1] + b[i][1];
+        const double yb0 = RIGHT ? b[i][1] - a[i][1] : b[i][0] - a[i][0];
+        const double yb1 = RIGHT ? b[i][0] - a[i][0] : b[i][1] - a[i][1];
+        const double rt0 = ot[ii].x - yt0, rt1 = ot[ii].y - yt1;
+        const double rb0 = ob[ii].x - yb0, rb1 = ob[ii].y - yb1;
+        if (POS != POS_LAST) {
+          st2(p.out + own.top(i), rt0, rt1);
+          st2(p.out + own.bot(i), rb0, rb1);
+        } else if (vint) {
+          const int mt = i * 8 + 2 * t, mb = P - 2 - i * 8 - 2 * t;  // first row of each pair
+          if (mt > 0) p.V[vrow + mt] = rt0;
+          p.V[vrow + mt + 1] = rt1;  // mt+1 <= P/2 - 1
+          p.V[vrow + mb] = rb0;      // mb >= P/2
+          if (mb + 1 < P - 1) p.V[vrow + mb + 1] = rb1;
         }
       }
     }
@@ -161,10 +178,11 @@ int launch_chain(const ChainParams& p, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long nblocks = (p.lg.nlines + 7) / 8;
+  const long long nblocks = p.lg.nlines / 8;
   // one persistent CTA per SM; fewer when there is not a block per warp to hand out
   long long grid = (nblocks + NWARPS - 1) / NWARPS;
   if (grid > sms) grid = sms;
+  if (const char* gs = getenv("SB200_CHAIN_GRID")) grid = atoi(gs);  // experiment knob
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>(p);
   count_launch();
@@ -207,7 +225,7 @@ bool elliptic_fused_supported(const EllipticCtx& e) {
   const int P = e.gd.dim[0];
   for (int j = 1; j < d; j++)
     if (e.gd.dim[j] != P) return false;
-  return P == 32 || P == 64 || P == 128;
+  return (P == 32 || P == 64 || P == 128) && (e.gd.m / P) % 8 == 0;
 }
 
 int elliptic_matmult_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
