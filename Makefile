@@ -1,7 +1,7 @@
 # Builds the C-ABI shared library (sm_100a only) in-tree so it travels to the GPU box.
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v $(EXTRA)
 CSRC      := spectral_petsc_b200/csrc
 OBJDIR    := build
 LIB       := spectral_petsc_b200/libspectral_b200.so

@@ -85,8 +85,11 @@ int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* d_out, void* 
 /* Scatter helpers with the semantics of scatterGL+scatterDL / scatterLG (elliptic.C:426-434). */
 int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream);
 int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, void* stream);
-/* Select kernel path: 0 = auto, 1 = generic per-axis kernels, 2 = fused plane kernels (3-D only). */
+/* Select kernel path: 0 = auto, 1 = generic per-axis kernels, 2 = one fused chain kernel per axis,
+ * 3 = single persistent chain kernel (2 and 3 need equal extents P in {32, 64, 128}). */
 int sb200_elliptic_set_path(sb200_elliptic* e, int path);
+/* Debug hook (only active in SB200_TRACE builds): device buffer receiving per-item phase clocks. */
+int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf);
 /* MatDestroy_Elliptic (elliptic.C:343-368). */
 int sb200_elliptic_destroy(sb200_elliptic* e);
 

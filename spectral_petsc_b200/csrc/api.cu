@@ -283,8 +283,14 @@ int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, v
 
 int sb200_elliptic_set_path(sb200_elliptic* e, int path) {
   SB_CHECK(e, SB200_ERR_ARG, "null context");
-  SB_CHECK(path >= 0 && path <= 2, SB200_ERR_USER, "path must be 0, 1 or 2");
+  SB_CHECK(path >= 0 && path <= 3, SB200_ERR_USER, "path must be 0..3");
   e->c->path = path;
+  return 0;
+}
+
+int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  e->c->trace = d_buf;
   return 0;
 }
 

@@ -72,6 +72,50 @@ __device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const dou
   }
 }
 
+// NT-block variant: one set of matrix fragments feeds NT line-blocks (block j at Xw + j*BE).
+template <int P, int NT, bool RIGHT>
+__device__ __forceinline__ void eo_gemm_nt(const double* __restrict__ Ae, const double* __restrict__ Bo,
+                                           const double* __restrict__ Xw, double (&a)[NT][EO<P>::MT][2],
+                                           double (&b)[NT][EO<P>::MT][2], int g, int t) {
+  using E = EO<P>;
+  constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
+#pragma unroll
+  for (int j = 0; j < NT; j++)
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) a[j][i][0] = a[j][i][1] = b[j][i][0] = b[j][i][1] = 0.0;
+#pragma unroll 2
+  for (int ks = 0; ks < E::KS; ks++) {
+    const int kk = ks * 4 + t;
+    double s[NT], d[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const double p = Xw[j * BE + xaddr<P, RIGHT>(kk, g)];
+      const double q = Xw[j * BE + xaddr<P, RIGHT>(P - 1 - kk, g)];
+      s[j] = p + q;
+      d[j] = p - q;
+    }
+    double fa[E::MT], fb[E::MT];
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) {
+      fa[i] = Ae[(i * 8 + g) * E::LDM + kk];
+      fb[i] = Bo[(i * 8 + g) * E::LDM + kk];
+    }
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) {
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        if (RIGHT) {
+          dmma884(a[j][i][0], a[j][i][1], s[j], fa[i]);
+          dmma884(b[j][i][0], b[j][i][1], d[j], fb[i]);
+        } else {
+          dmma884(a[j][i][0], a[j][i][1], fa[i], s[j]);
+          dmma884(b[j][i][0], b[j][i][1], fb[i], d[j]);
+        }
+      }
+    }
+  }
+}
+
 // Thread-owned element geometry shared by every epilogue.  For tile i the thread owns a "top" pair
 // of adjacent elements and the mirrored "bottom" pair (also adjacent, in reversed order):
 //   LEFT : rows mt = i*8+g / mb = P-1-mt, lines 2t,2t+1        -> global offset base0 + m*R + 2t

@@ -54,10 +54,15 @@ __device__ __forceinline__ LineInfo decode_line(const GridDesc& gd, long long li
 
 __global__ void pad_kernel(GridDesc gd, long long nlines, const double* __restrict__ U,
                            const double* __restrict__ dir, double* __restrict__ w0) {
+  // one thread row (threadIdx.y) per line; the line decode is done once per row by lane 0
   const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (line >= nlines) return;
+  const bool live = line < nlines;
   const int PL = gd.dim[gd.d - 1];
-  const LineInfo li = decode_line(gd, line);
+  __shared__ LineInfo sli[32];
+  if (threadIdx.x == 0 && live) sli[threadIdx.y] = decode_line(gd, line);
+  __syncthreads();
+  if (!live) return;
+  const LineInfo li = sli[threadIdx.y];
   double* wl = w0 + line * PL;
   for (int k = threadIdx.x; k < PL; k += blockDim.x) {
     double v;
@@ -224,6 +229,7 @@ EllipticCtx::~EllipticCtx() {
   if (deta) cudaFree(deta);
   if (dirichlet) cudaFree(dirichlet);
   if (b) cudaFree(b);
+  if (sync) cudaFree(sync);
   for (DiffMatrix* dm : owned) {
     dm->destroy();
     delete dm;
@@ -249,7 +255,7 @@ int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, 
 int EllipticCtx::pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s) {
   const int PL = gd.dim[gd.d - 1];
   const long long nlines = gd.m / PL;
-  const int tx = PL >= 128 ? 128 : (PL > 32 ? 64 : 32);
+  const int tx = 32;
   dim3 blk(tx, 256 / tx);
   pad_kernel<<<(unsigned)((nlines + blk.y - 1) / blk.y), blk, 0, s>>>(gd, nlines, U, with_dirichlet ? dirichlet : nullptr, local);
   count_launch();
@@ -271,7 +277,11 @@ int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStr
 int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
   SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
   const int d = gd.d;
-  if (path == 2 || (path == 0 && elliptic_fused_supported(*this))) {
+  if (path == 3 || (path == 0 && elliptic_persist_supported(*this))) {
+    SB_CHECK(elliptic_persist_supported(*this), SB200_ERR_SUP, "persistent path needs equal extents P in {32,64,128}");
+    return elliptic_matmult_persist(*this, U, V, s);
+  }
+  if (path == 2) {
     SB_CHECK(elliptic_fused_supported(*this), SB200_ERR_SUP, "fused path needs equal extents P in {32,64,128}");
     return elliptic_matmult_fused(*this, U, V, s);
   }

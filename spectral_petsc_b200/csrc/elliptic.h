@@ -39,6 +39,8 @@ struct EllipticCtx {
   double* b = nullptr;          // ac->b
   double gamma = 0.0, exponent = 2.0;
   int path = 0;
+  long long* trace = nullptr;  // debug: phase time stamps (SB200_TRACE builds)
+  unsigned* sync = nullptr;  // ticket / completion counters of the persistent kernel
   DiffMatrix* Dax[SB200_MAX_DIM] = {};
   std::vector<DiffMatrix*> owned;
 
@@ -54,5 +56,7 @@ struct EllipticCtx {
 
 bool elliptic_fused_supported(const EllipticCtx& e);
 int elliptic_matmult_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
+bool elliptic_persist_supported(const EllipticCtx& e);
+int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
 
 }  // namespace sb200

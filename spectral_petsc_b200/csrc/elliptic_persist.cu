@@ -1,0 +1,439 @@
+// Single-launch persistent MatMult_Elliptic (elliptic.C:297-339) for grids with all extents equal to
+// P (P % 16 == 0):  ONE kernel runs the chains of every axis.
+//
+// Work item = (axis k, block of 8*NT grid lines of that axis); items are handed out in order through a
+// global ticket counter, all axes but the last first.  A warp owns its item end to end (chain.cuh):
+//     load w block -> GEMM1 (even-odd DMMA) -> flux in registers -> in-place -> GEMM2 -> epilogue.
+// Non-last axes store their term  D_k f_k  into a partial field (phase A launch); the last axis
+// (R == 1, phase B launch) finishes   V = crop(((0 - p_0) - p_1 ...) - D_l f_l),  i.e. exactly the
+// reference's accumulation order (elliptic.C:331-334).  Phase B is a programmatic dependent launch:
+// its CTAs start on SMs as phase A drains, run GEMM1/flux/GEMM2 of their first items, and only block
+// (griddepcontrol.wait) right before they read the partials.  Because every warp pulls several items
+// of different phase, the global-memory phases of some warps overlap the tensor phases of the others.
+#include <cstdlib>
+
+#include "../../include/spectral_b200.h"
+#include "chain.cuh"
+#include "deriv.h"
+#include "elliptic.h"
+
+#ifdef SB200_TRACE
+#define STAMP(k) do { if (lane == 0 && p.trace) tr[k] = clock64(); } while (0)
+#else
+#define STAMP(k) do { } while (0)
+#endif
+
+namespace sb200 {
+
+namespace {
+
+struct PersistParams {
+  const double* Ae;
+  const double* Bo;
+  const double* w;     // padded local field (m)
+  const double* eta;   // m
+  const double* deta;  // m
+  const double* g0[SB200_MAX_DIM];   // gradu[k]
+  double* part[SB200_MAX_DIM];       // partial fields of the non-last axes
+  double* V;                         // g: cropped result
+  long long R[SB200_MAX_DIM];        // stride of axis k
+  long long nlines;                  // m / P (same for every axis)
+  int d;
+  int dim[SB200_MAX_DIM];
+  unsigned* sync;  // phase A: [0] ticket, [1] exited warps; phase B: [4], [5]
+  int stagger;       // start delay per warp group, in clocks
+  int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
+  long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
+};
+
+template <int P, int NT, bool RIGHT>
+__device__ __forceinline__ void load_item(double* Xw, const double* __restrict__ w, const LineGeom& lg,
+                                          long long n0, int lane) {
+  constexpr int BE = RIGHT ? EO<P>::BLOCK_ELEMS_RIGHT : EO<P>::BLOCK_ELEMS_LEFT;
+#pragma unroll
+  for (int j = 0; j < NT; j++) load_block<P, RIGHT>(Xw + j * BE, w, lg, n0 + 8 * j, lane);
+}
+
+// Flux operands of two tiles (top and bottom pair each): eta, deta, gradu.
+struct FluxBuf {
+  double2 e[2][2], de[2][2], gg[2][2];
+};
+
+template <int P, bool RIGHT>
+__device__ __forceinline__ void flux_load(FluxBuf& f, const Own<P, RIGHT>& own, int ib, const double* __restrict__ eta,
+                                          const double* __restrict__ deta, const double* __restrict__ g0) {
+#pragma unroll
+  for (int ii = 0; ii < 2; ii++) {
+    if (eta == nullptr) {
+      f.e[ii][0] = f.e[ii][1] = make_double2(1.5, 1.5);
+      f.de[ii][0] = f.de[ii][1] = f.gg[ii][0] = f.gg[ii][1] = make_double2(0.25, 0.25);
+      continue;
+    }
+    const long long ot = own.top(ib + ii), ob = own.bot(ib + ii);
+    f.e[ii][0] = ldg2(eta + ot);
+    f.e[ii][1] = ldg2(eta + ob);
+    f.de[ii][0] = ldg2(deta + ot);
+    f.de[ii][1] = ldg2(deta + ob);
+    f.gg[ii][0] = ldg2(g0 + ot);
+    f.gg[ii][1] = ldg2(g0 + ob);
+  }
+}
+
+// elliptic.C:319-323 for tiles ib, ib+1:  f = eta*y + (deta*w)*g0, written over w in the block.
+template <int P, bool RIGHT>
+__device__ __forceinline__ void flux_apply(const FluxBuf& f, const Own<P, RIGHT>& own, int ib, double* Xj,
+                                           const double (&a)[EO<P>::MT][2], const double (&b)[EO<P>::MT][2]) {
+#pragma unroll
+  for (int ii = 0; ii < 2; ii++) {
+    const int i = ib + ii;
+    const int st = own.stop(i), sb = own.sbot(i);
+    const double2 wt = ld2(Xj + st), wb = ld2(Xj + sb);
+    const double yt0 = a[i][0] + b[i][0], yt1 = a[i][1] + b[i][1];
+    const double yb0 = RIGHT ? b[i][1] - a[i][1] : b[i][0] - a[i][0];
+    const double yb1 = RIGHT ? b[i][0] - a[i][0] : b[i][1] - a[i][1];
+    const double ft0 = __dadd_rn(__dmul_rn(f.e[ii][0].x, yt0), __dmul_rn(__dmul_rn(f.de[ii][0].x, wt.x), f.gg[ii][0].x));
+    const double ft1 = __dadd_rn(__dmul_rn(f.e[ii][0].y, yt1), __dmul_rn(__dmul_rn(f.de[ii][0].y, wt.y), f.gg[ii][0].y));
+    const double fb0 = __dadd_rn(__dmul_rn(f.e[ii][1].x, yb0), __dmul_rn(__dmul_rn(f.de[ii][1].x, wb.x), f.gg[ii][1].x));
+    const double fb1 = __dadd_rn(__dmul_rn(f.e[ii][1].y, yb1), __dmul_rn(__dmul_rn(f.de[ii][1].y, wb.y), f.gg[ii][1].y));
+    st2(Xj + st, ft0, ft1);
+    st2(Xj + sb, fb0, fb1);
+  }
+}
+
+// The whole chain for one item.  Returns after the epilogue stores are issued.
+// DEEP: keep one flux batch in flight across GEMM1 and double-buffer the batches (needs registers).
+template <int P, int NT, bool RIGHT, bool DEEP>
+__device__ __forceinline__ void run_item(const PersistParams& p, int axis, long long n0, const double* Ae,
+                                         const double* Bo, double* Xw, int lane) {
+  using E = EO<P>;
+  constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
+  const int g = lane >> 2, t = lane & 3;
+  LineGeom lg;
+  lg.R = p.R[axis];
+  lg.PR = (long long)P * lg.R;
+  lg.nlines = p.nlines;
+  Own<P, RIGHT> own[NT];
+  long long base0[NT];
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    const long long nj = n0 + 8 * j;
+    base0[j] = RIGHT ? nj * P : lg.base(nj);
+    own[j].base = RIGHT ? (nj + g) * P : base0[j] + 2 * t;
+    own[j].R = lg.R;
+    own[j].g = g;
+    own[j].t = t;
+  }
+  const double* __restrict__ g0 = p.g0[axis];
+  const double* __restrict__ etap = (p.xflags & 1) ? nullptr : p.eta;
+#ifdef SB200_TRACE
+  long long* tr = p.trace ? p.trace + ((long long)axis * (p.nlines / (8 * NT)) + n0 / (8 * NT)) * 8 : nullptr;
+  if (lane == 0 && p.trace) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); tr[6] = smid; tr[7] = threadIdx.x >> 5; }
+#endif
+  STAMP(0);
+  FluxBuf f0, f1;
+  if (DEEP) flux_load<P, RIGHT>(f0, own[0], 0, etap, p.deta, g0);
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    prefetch_block<P, RIGHT>(p.eta, base0[j], lg.R, lane);
+    prefetch_block<P, RIGHT>(p.deta, base0[j], lg.R, lane);
+    prefetch_block<P, RIGHT>(g0, base0[j], lg.R, lane);
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  STAMP(1);
+
+  double a[NT][E::MT][2], b[NT][E::MT][2];
+  eo_gemm_nt<P, NT, RIGHT>(Ae, Bo, Xw, a, b, g, t);
+  __syncwarp();
+  STAMP(2);
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    double* Xj = Xw + j * BE;
+    if (DEEP) {
+      // software pipeline: batch k+1 is in flight while batch k is applied
+      if (j > 0) flux_load<P, RIGHT>(f0, own[j], 0, etap, p.deta, g0);
+#pragma unroll
+      for (int ib = 0; ib < E::MT; ib += 4) {
+        flux_load<P, RIGHT>(f1, own[j], ib + 2, etap, p.deta, g0);
+        flux_apply<P, RIGHT>(f0, own[j], ib, Xj, a[j], b[j]);
+        if (ib + 4 < E::MT) flux_load<P, RIGHT>(f0, own[j], ib + 4, etap, p.deta, g0);
+        flux_apply<P, RIGHT>(f1, own[j], ib + 2, Xj, a[j], b[j]);
+      }
+    } else {
+#pragma unroll
+      for (int ib = 0; ib < E::MT; ib += 2) {
+        flux_load<P, RIGHT>(f0, own[j], ib, etap, p.deta, g0);
+        flux_apply<P, RIGHT>(f0, own[j], ib, Xj, a[j], b[j]);
+      }
+    }
+  }
+  __syncwarp();
+  STAMP(3);
+  eo_gemm_nt<P, NT, RIGHT>(Ae, Bo, Xw, a, b, g, t);
+  __syncwarp();  // block free again (the caller refills it while the epilogue drains)
+  STAMP(4);
+
+  if (p.xflags & 2) {
+    // experiment: no epilogue traffic (keep one dependent store so the GEMM is not dead code)
+    if (a[0][0][0] + b[0][0][0] == 12345.678) p.V[0] = 1.0;
+  } else if (!RIGHT) {
+    // non-last axis: partial_k = D f
+    double* __restrict__ part = p.part[axis];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int i = 0; i < E::MT; i++) {
+        st2(part + own[j].top(i), a[j][i][0] + b[j][i][0], a[j][i][1] + b[j][i][1]);
+        st2(part + own[j].bot(i), b[j][i][0] - a[j][i][0], b[j][i][1] - a[j][i][1]);
+      }
+    }
+  } else {
+    // last axis: phase A (all partials) must be complete and visible, then
+    // V = crop(((0 - p_0) - p_1 ...) - D f)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      long long n = n0 + 8 * j + g, gid = 0, mul = 1;
+      bool vint = true;
+      for (int q = p.d - 2; q >= 0; q--) {
+        const int iq = (int)(n % p.dim[q]);
+        n /= p.dim[q];
+        vint = vint && iq > 0 && iq < p.dim[q] - 1;
+        gid += (long long)(iq - 1) * mul;
+        mul *= p.dim[q] - 2;
+      }
+      const long long vrow = gid * (P - 2) - 1;  // V index of row m is vrow + m
+#pragma unroll
+      for (int ib = 0; ib < E::MT; ib += 4) {
+        double2 ot[4], ob[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) ot[ii] = ob[ii] = make_double2(0.0, 0.0);
+        if (p.d == 3) {
+          // common case: both partials of the batch in flight at once
+          double2 lt[2][4], lb[2][4];
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const double* __restrict__ pk = p.part[k];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              lt[k][ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].top(ib + ii)));
+              lb[k][ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].bot(ib + ii)));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              ot[ii].x -= lt[k][ii].x;
+              ot[ii].y -= lt[k][ii].y;
+              ob[ii].x -= lb[k][ii].x;
+              ob[ii].y -= lb[k][ii].y;
+            }
+          }
+        } else {
+          for (int k = 0; k < p.d - 1; k++) {
+            const double* __restrict__ pk = p.part[k];
+            double2 lt[4], lb[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              lt[ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].top(ib + ii)));
+              lb[ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].bot(ib + ii)));
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              ot[ii].x -= lt[ii].x;
+              ot[ii].y -= lt[ii].y;
+              ob[ii].x -= lb[ii].x;
+              ob[ii].y -= lb[ii].y;
+            }
+          }
+        }
+        if (vint) {
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) {
+            const int i = ib + ii;
+            const double yt0 = a[j][i][0] + b[j][i][0], yt1 = a[j][i][1] + b[j][i][1];
+            const double yb0 = b[j][i][1] - a[j][i][1], yb1 = b[j][i][0] - a[j][i][0];
+            const int mt = i * 8 + 2 * t, mb = P - 2 - i * 8 - 2 * t;  // first row of each pair
+            if (mt > 0) p.V[vrow + mt] = ot[ii].x - yt0;
+            p.V[vrow + mt + 1] = ot[ii].y - yt1;
+            p.V[vrow + mb] = ob[ii].x - yb0;
+            if (mb + 1 < P - 1) p.V[vrow + mb + 1] = ob[ii].y - yb1;
+          }
+        }
+      }
+    }
+  }
+  STAMP(5);
+}
+
+template <int P, int NWARPS, int NT, bool LASTPHASE>
+__global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p) {
+  using E = EO<P>;
+  extern __shared__ double sm[];
+  double* Ae = sm;
+  double* Bo = sm + E::H * E::LDM;
+  constexpr int BEMAX = E::BLOCK_ELEMS_RIGHT > E::BLOCK_ELEMS_LEFT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Xw = sm + E::MAT_ELEMS + warp * (NT * BEMAX);
+  unsigned* sync = p.sync + (LASTPHASE ? 4 : 0);  // [0] ticket, [1] exited warps
+
+  const unsigned items_per_axis = (unsigned)(p.nlines / (8 * NT));
+  const unsigned total = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1);
+  if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  load_matrices<P>(sm, p.Ae, p.Bo);
+
+  auto grab = [&]() -> unsigned {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(sync, 1u);
+    return __shfl_sync(0xffffffffu, tk, 0);
+  };
+  auto issue_load = [&](unsigned tk) {
+    if (tk >= total) return;
+    const int axis = LASTPHASE ? p.d - 1 : tk / items_per_axis;
+    const long long n0 = (long long)(tk - (LASTPHASE ? 0 : axis * items_per_axis)) * (8 * NT);
+    LineGeom lg;
+    lg.R = p.R[axis];
+    lg.PR = (long long)P * lg.R;
+    lg.nlines = p.nlines;
+    load_item<P, NT, LASTPHASE>(Xw, p.w, lg, n0, lane);
+  };
+
+  constexpr bool DEEP = (NWARPS * NT <= 8);  // 255 registers available
+  // De-phase the warps of each SM sub-partition (warp w runs on SMSP w % 4): identical items started
+  // together stay in lockstep, which serialises the tensor phases against the memory phases.
+  unsigned tk = grab();
+  issue_load(tk);
+  cp_async_wait<0>();
+  __syncthreads();  // matrices visible to all warps (the only CTA-wide barrier)
+  if (p.stagger > 0) {
+    const long long until = clock64() + (long long)(warp / 4) * p.stagger;
+    while (clock64() < until) {
+    }
+  }
+
+  while (tk < total) {
+    const int axis = LASTPHASE ? p.d - 1 : tk / items_per_axis;
+    const long long n0 = (long long)(tk - (LASTPHASE ? 0 : axis * items_per_axis)) * (8 * NT);
+    run_item<P, NT, LASTPHASE, DEEP>(p, axis, n0, Ae, Bo, Xw, lane);
+    tk = grab();
+    issue_load(tk);  // run_item waits for it at its top
+  }
+  cp_async_wait<0>();
+  // the last warp to leave re-arms the counters for the next launch
+  if (lane == 0) {
+    const unsigned gone = atomicAdd(sync + 1, 1u);
+    if (gone == gridDim.x * NWARPS - 1) {
+      sync[0] = 0;
+      sync[1] = 0;
+    }
+  }
+}
+
+template <int P, int NWARPS, int NT, bool LASTPHASE>
+int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
+  auto kern = persist_kernel<P, NWARPS, NT, LASTPHASE>;
+  static bool attr = false;
+  if (!attr) {
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1);
+  long long grid = (items + NWARPS - 1) / NWARPS;
+  if (grid > sms) grid = sms;  // one persistent CTA per SM
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NWARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = LASTPHASE ? 1 : 0;  // phase B may start while phase A drains
+  SB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+  return 0;
+}
+
+template <int P, int NWARPS, int NT>
+int launch_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
+  using E = EO<P>;
+  constexpr int BEMAX = E::BLOCK_ELEMS_RIGHT > E::BLOCK_ELEMS_LEFT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
+  const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * NT * BEMAX) * sizeof(double);
+  if (!e.sync) {
+    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
+    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
+  }
+  const int d = e.gd.d;
+  SB_TRY(e.pad(U, false, e.w[0], s));
+  PersistParams p;
+  p.Ae = e.Dax[0]->d_Ae;
+  p.Bo = e.Dax[0]->d_Bo;
+  p.w = e.w[0];
+  p.eta = e.eta;
+  p.deta = e.deta;
+  p.V = V;
+  p.nlines = e.gd.m / P;
+  p.d = d;
+  for (int k = 0; k < d; k++) {
+    p.g0[k] = e.gradu[k];
+    p.part[k] = e.w[1 + k];
+    p.R[k] = e.gd.stride[k];
+    p.dim[k] = e.gd.dim[k];
+  }
+  p.sync = e.sync;
+  p.trace = e.trace;
+  {
+    static int stg = -1;
+    if (stg < 0) {
+      const char* c = getenv("SB200_STAGGER");
+      stg = c ? atoi(c) : 6000;  // measured best on B200 (profiles/r01_notes.md)
+    }
+    p.stagger = stg;
+    const char* xf = getenv("SB200_XFLAGS");
+    p.xflags = xf ? atoi(xf) : 0;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  SB_TRY((launch_phase<P, NWARPS, NT, false>(p, smem, sms, s)));
+  SB_TRY((launch_phase<P, NWARPS, NT, true>(p, smem, sms, s)));
+  return 0;
+}
+
+}  // namespace
+
+bool elliptic_persist_supported(const EllipticCtx& e) {
+  const int d = e.gd.d;
+  if (d < 2) return false;
+  const int P = e.gd.dim[0];
+  for (int j = 1; j < d; j++)
+    if (e.gd.dim[j] != P) return false;
+  return (P == 32 || P == 64 || P == 128) && (e.gd.m / P) % 16 == 0;
+}
+
+int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* c = getenv("SB200_PERSIST_CFG");
+    cfg = c ? atoi(c) : 2;  // 8 warps x 255 registers measured best on B200
+  }
+  switch (e.gd.dim[0]) {
+    case 32: return launch_persist<32, 16, 1>(e, U, V, s);
+    case 64: return launch_persist<64, 16, 1>(e, U, V, s);
+    case 128:
+      switch (cfg) {
+        case 1: return launch_persist<128, 12, 1>(e, U, V, s);
+        case 2: return launch_persist<128, 8, 1>(e, U, V, s);
+        case 3: return launch_persist<128, 8, 2>(e, U, V, s);
+        default: return launch_persist<128, 16, 1>(e, U, V, s);
+      }
+  }
+  set_last_error("persistent path: unsupported extent");
+  return SB200_ERR_SUP;
+}
+
+}  // namespace sb200

@@ -91,7 +91,7 @@ def test_full_size_128(cuda):
 
 @pytest.mark.parametrize("dim", [[32, 32], [32, 32, 32], [64, 64, 64], [32, 32, 32, 32], [128, 128]], ids=lambda v: str(v))
 def test_fused_chain_path_matches_generic_and_oracle(cuda, dim):
-    # path 2 = persistent even-odd chain kernels, path 1 = generic per-axis kernels
+    # path 1 = generic per-axis kernels, 2 = one chain kernel per axis, 3 = single persistent chain kernel
     O, G, u, u2 = make_pair(dim, 4.0, 2.0, cuda)
     Us = 0.1 * np.random.default_rng(1).standard_normal(O.g)
     O.form_function(Us)
@@ -103,9 +103,15 @@ def test_fused_chain_path_matches_generic_and_oracle(cuda, dim):
     V1 = G.mat_mult(Ud).cpu().numpy()
     G.set_path(2)
     V2 = G.mat_mult(Ud).cpu().numpy()
+    G.set_path(3)
+    V3 = G.mat_mult(Ud).cpu().numpy()
+    V3b = G.mat_mult(Ud).cpu().numpy()  # counters re-armed by the previous launch
     assert rel_max(V1, Vo) < TOL
     assert rel_max(V2, Vo) < TOL
+    assert rel_max(V3, Vo) < TOL
     assert rel_max(V2, V1) < 1e-13
+    assert np.array_equal(V3, V2)  # same arithmetic, same order
+    assert np.array_equal(V3, V3b)
 
 
 def test_fused_path_rejects_unsupported_extents(cuda):
