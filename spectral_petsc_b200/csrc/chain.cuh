@@ -212,4 +212,58 @@ __device__ __forceinline__ void load_block(double* Xw, const double* __restrict_
   cp_async_commit();
 }
 
+
+// Warp-level load of one 8-line block straight from the GLOBAL vector U (interior nodes only,
+// lexicographic; elliptic.C:408-409) with the homogeneous-Dirichlet pad of MatMult_Elliptic
+// (elliptic.C:305-308) applied on the fly: boundary nodes are zero-filled, so no padded copy of the
+// field is ever materialised.  All extents equal P; `axis` is the chain axis, n0 the first line.
+template <int P, bool RIGHT>
+__device__ __forceinline__ void load_block_from_U(double* Xw, const double* __restrict__ U, int d, int axis,
+                                                  unsigned n0, int lane) {
+  using E = EO<P>;
+  // decode the d-1 digits (base P) of line n0 over the axes other than `axis`, fastest axis first
+  unsigned rem = n0;
+  long long gb = 0;      // global id of (line, m = 1) for c = 0
+  long long ist = 1;     // interior stride of the axis being visited
+  long long ist_a = 1, ist_fast = 1;
+  int dig_fast = 0;
+  bool inter = true;
+  const int fast = RIGHT ? d - 2 : d - 1;
+  for (int j = d - 1; j >= 0; j--) {
+    if (j == axis) {
+      ist_a = ist;
+    } else {
+      const int dig = (int)(rem % P);
+      rem /= P;
+      if (j == fast) {
+        dig_fast = dig;
+        ist_fast = ist;
+      } else {
+        inter = inter && dig >= 1 && dig <= P - 2;
+      }
+      gb += (long long)(dig - 1) * ist;
+    }
+    ist *= (P - 2);
+  }
+  if (RIGHT) {
+    // lanes run along the line (contiguous in U); 8 lines, P/32 passes each
+#pragma unroll 4
+    for (int i = 0; i < 8 * (P / 32); i++) {
+      const int c = i / (P / 32), m = lane + 32 * (i % (P / 32));
+      const bool ok = inter && (dig_fast + c >= 1) && (dig_fast + c <= P - 2) && m >= 1 && m <= P - 2;
+      cp_async8(Xw + c * E::LDR + m, U + (ok ? gb + c * ist_fast + (m - 1) : 0), ok);
+    }
+  } else {
+    const int c = lane & 7;
+    const bool okc = inter && (dig_fast + c >= 1) && (dig_fast + c <= P - 2);
+    const double* src = U + gb + c - ist_a;  // + m * ist_a  (ist_fast == 1 for the last axis)
+#pragma unroll 4
+    for (int m = lane >> 3; m < P; m += 4) {
+      const bool ok = okc && m >= 1 && m <= P - 2;
+      cp_async8(Xw + xaddr<P, false>(m, c), ok ? src + (long long)m * ist_a : U, ok);
+    }
+  }
+  cp_async_commit();
+}
+
 }  // namespace sb200

@@ -30,7 +30,7 @@ namespace {
 struct PersistParams {
   const double* Ae;
   const double* Bo;
-  const double* w;     // padded local field (m)
+  const double* U;     // global vector (g): the pad is applied by the block loader
   const double* eta;   // m
   const double* deta;  // m
   const double* g0[SB200_MAX_DIM];   // gradu[k]
@@ -47,11 +47,11 @@ struct PersistParams {
 };
 
 template <int P, int NT, bool RIGHT>
-__device__ __forceinline__ void load_item(double* Xw, const double* __restrict__ w, const LineGeom& lg,
+__device__ __forceinline__ void load_item(double* Xw, const double* __restrict__ U, int d, int axis,
                                           long long n0, int lane) {
   constexpr int BE = RIGHT ? EO<P>::BLOCK_ELEMS_RIGHT : EO<P>::BLOCK_ELEMS_LEFT;
 #pragma unroll
-  for (int j = 0; j < NT; j++) load_block<P, RIGHT>(Xw + j * BE, w, lg, n0 + 8 * j, lane);
+  for (int j = 0; j < NT; j++) load_block_from_U<P, RIGHT>(Xw + j * BE, U, d, axis, (unsigned)(n0 + 8 * j), lane);
 }
 
 // Flux operands of two tiles (top and bottom pair each): eta, deta, gradu.
@@ -293,11 +293,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     if (tk >= total) return;
     const int axis = LASTPHASE ? p.d - 1 : tk / items_per_axis;
     const long long n0 = (long long)(tk - (LASTPHASE ? 0 : axis * items_per_axis)) * (8 * NT);
-    LineGeom lg;
-    lg.R = p.R[axis];
-    lg.PR = (long long)P * lg.R;
-    lg.nlines = p.nlines;
-    load_item<P, NT, LASTPHASE>(Xw, p.w, lg, n0, lane);
+    load_item<P, NT, LASTPHASE>(Xw, p.U, p.d, axis, n0, lane);
   };
 
   constexpr bool DEEP = (NWARPS * NT <= 8);  // 255 registers available
@@ -368,11 +364,10 @@ int launch_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
     SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
   }
   const int d = e.gd.d;
-  SB_TRY(e.pad(U, false, e.w[0], s));
   PersistParams p;
   p.Ae = e.Dax[0]->d_Ae;
   p.Bo = e.Dax[0]->d_Bo;
-  p.w = e.w[0];
+  p.U = U;
   p.eta = e.eta;
   p.deta = e.deta;
   p.V = V;
