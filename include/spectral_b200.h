@@ -93,6 +93,45 @@ int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf);
 /* MatDestroy_Elliptic (elliptic.C:343-368). */
 int sb200_elliptic_destroy(sb200_elliptic* e);
 
+/* ---- stokes.C: the five MatShells, the SNES residual, the rheology ---------------------------- */
+/* StokesCreate(comm, &A, &x, &ctx) (stokes.C:257-345) for -boundary 0 (all Dirichlet, stokes.C:463-468);
+ * d must be 2 or 3 (StokesPressureReduceOrder, stokes.C:1036). */
+int sb200_stokes_create(int d, const int* dim, sb200_stokes** out);
+/* DOF distribution printed at stokes.C:891: local nodes m, global g, pressure gp, velocity gv, dirichlet dv. */
+int sb200_stokes_sizes(const sb200_stokes* s, long long* m, long long* g, long long* gp, long long* gv, long long* dv);
+/* -rheology / -hardness / -exponent / -eps / -gamma0 (stokes.C:404-410); type 0 linear, 1 power law.
+ * The continuation loop (stokes.C:217-221) calls this with the per-step exponent / regularisation. */
+int sb200_stokes_set_rheology(sb200_stokes* s, int type, double hardness, double exponent, double regularization, double gamma0);
+/* c->dirichlet (dv doubles: boundary nodes in walk order x d components, stokes.C:796-801) and c->force (g doubles). */
+int sb200_stokes_set_dirichlet(sb200_stokes* s, const double* d_values, void* stream);
+int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream);
+/* StokesMatMult(A, x, y) (stokes.C:499-519): x, y of g doubles, AoS [v_0..v_{d-1}, p] per interior node. */
+int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y);
+/* StokesMatMultVV (stokes.C:623-676): gv -> gv. */
+int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+/* StokesMatMultPV (stokes.C:557-566): divergence, gv -> gp. */
+int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+/* StokesMatMultVP (stokes.C:599-619): pressure gradient with P_N - P_{N-2} extrapolation, gp -> gv. */
+int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+/* StokesMatGetDiagonalSchur (stokes.C:542-553): y = 1/eta at pressure nodes (gp doubles). */
+int sb200_stokes_get_diagonal_schur(sb200_stokes* s, double* d_y, void* stream);
+/* StokesMatMultSchur (stokes.C:523-535): y = -PV * solve(VP * x); `solve` stands for
+ * KSPSolve(KSPSchurVelocity, rhs, sol) on device vectors of gv doubles and returns 0 on success. */
+typedef int (*sb200_velocity_solve_fn)(void* ctx, const double* d_rhs, double* d_sol, void* stream);
+int sb200_stokes_matmult_schur(sb200_stokes* s, const double* d_x, double* d_y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream);
+/* StokesFunction(snes, x, y, ctx) (stokes.C:680-758): residual; refreshes strain / eta / deta caches. */
+int sb200_stokes_function(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+int sb200_stokes_function_host(sb200_stokes* s, const double* h_x, double* h_y);
+/* "Minimum eta / Maximum eta" of the last residual evaluation (stokes.C:731-734); synchronises the stream. */
+int sb200_stokes_eta_minmax(sb200_stokes* s, double* h_min, double* h_max, void* stream);
+/* Cached state (stokes.C:766): which = 0 eta (m), 1 deta (m), 2+j strain[j] (m*d); device->device copy. */
+int sb200_stokes_get_state(sb200_stokes* s, int which, double* d_out, void* stream);
+/* StokesPressureReduceOrder (stokes.C:1029-1080) applied in place to a local pressure array of m doubles. */
+int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stream);
+/* StokesDestroy (stokes.C:348-388). */
+int sb200_stokes_destroy(sb200_stokes* s);
+
 #ifdef __cplusplus
 }
 #endif

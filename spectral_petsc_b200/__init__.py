@@ -13,7 +13,8 @@ from .capi import (  # noqa: F401
     launch_count,
     Cheb,
     Elliptic,
+    Stokes,
     cheb_matrix,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "cheb_matrix"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "cheb_matrix"]

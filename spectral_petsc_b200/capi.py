@@ -201,3 +201,137 @@ class Elliptic:
             self.destroy()
         except Exception:
             pass
+
+
+_VSOLVE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+
+class Stokes:
+    """StokesCreate + the StokesMatMult{,VV,PV,VP,Schur} shells and StokesFunction (stokes.C), -boundary 0."""
+
+    def __init__(self, dim, rheology=0, hardness=1.0, exponent=1.0, regularization=1.0, gamma0=1.0):
+        dim = [int(v) for v in dim]
+        arr = (ctypes.c_int * len(dim))(*dim)
+        self._h = ctypes.c_void_p()
+        _ck(lib().sb200_stokes_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        v = [ctypes.c_longlong() for _ in range(5)]
+        _ck(lib().sb200_stokes_sizes(self._h, *[ctypes.byref(x) for x in v]))
+        self.m, self.g, self.gp, self.gv, self.dv = [x.value for x in v]
+        self.dim, self.d = dim, len(dim)
+        self.set_rheology(rheology, hardness, exponent, regularization, gamma0)
+
+    def set_rheology(self, rheology, hardness=1.0, exponent=1.0, regularization=1.0, gamma0=1.0):
+        _ck(lib().sb200_stokes_set_rheology(self._h, ctypes.c_int(rheology), ctypes.c_double(hardness), ctypes.c_double(exponent),
+                                            ctypes.c_double(regularization), ctypes.c_double(gamma0)))
+
+    def set_dirichlet(self, values):
+        assert values.numel() == self.dv
+        _ck(lib().sb200_stokes_set_dirichlet(self._h, _ptr(values), _stream()))
+
+    def set_force(self, force):
+        assert force.numel() == self.g
+        _ck(lib().sb200_stokes_set_force(self._h, _ptr(force), _stream()))
+
+    def _apply(self, fn, x, nin, nout, y=None):
+        import torch
+
+        assert x.numel() == nin
+        if y is None:
+            y = torch.empty(nout, dtype=torch.float64, device=x.device)
+        _ck(fn(self._h, _ptr(x), _ptr(y), _stream()))
+        return y
+
+    def mat_mult(self, x, y=None):
+        return self._apply(lib().sb200_stokes_matmult, x, self.g, self.g, y)
+
+    def mat_mult_vv(self, x, y=None):
+        return self._apply(lib().sb200_stokes_matmult_vv, x, self.gv, self.gv, y)
+
+    def mat_mult_pv(self, x, y=None):
+        return self._apply(lib().sb200_stokes_matmult_pv, x, self.gv, self.gp, y)
+
+    def mat_mult_vp(self, x, y=None):
+        return self._apply(lib().sb200_stokes_matmult_vp, x, self.gp, self.gv, y)
+
+    def function(self, x, y=None):
+        return self._apply(lib().sb200_stokes_function, x, self.g, self.g, y)
+
+    def mat_mult_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        _ck(lib().sb200_stokes_matmult_host(self._h, _hptr(x), _hptr(y)))
+        return y
+
+    def function_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        _ck(lib().sb200_stokes_function_host(self._h, _hptr(x), _hptr(y)))
+        return y
+
+    def get_diagonal_schur(self):
+        import torch
+
+        y = torch.empty(self.gp, dtype=torch.float64, device="cuda")
+        _ck(lib().sb200_stokes_get_diagonal_schur(self._h, _ptr(y), _stream()))
+        return y
+
+    def mat_mult_schur(self, x, velocity_solve):
+        """velocity_solve(rhs_tensor) -> sol_tensor stands for KSPSolve(KSPSchurVelocity) (stokes.C:531)."""
+        import torch
+
+        y = torch.empty(self.gp, dtype=torch.float64, device=x.device)
+        gv = self.gv
+
+        def cb(_ctx, d_rhs, d_sol, _stream_):
+            try:
+                rhs = _wrap(d_rhs, gv)
+                sol = _wrap(d_sol, gv)
+                sol.copy_(velocity_solve(rhs))
+                return 0
+            except Exception:  # pragma: no cover
+                return 1
+
+        cfn = _VSOLVE(cb)
+        _ck(lib().sb200_stokes_matmult_schur(self._h, _ptr(x), _ptr(y), cfn, None, _stream()))
+        return y
+
+    def eta_minmax(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _ck(lib().sb200_stokes_eta_minmax(self._h, ctypes.byref(a), ctypes.byref(b), _stream()))
+        return a.value, b.value
+
+    def get_state(self, which):
+        import torch
+
+        n = self.m if which < 2 else self.m * self.d
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        _ck(lib().sb200_stokes_get_state(self._h, ctypes.c_int(which), _ptr(out), _stream()))
+        return out
+
+    def pressure_reduce_order(self, pL):
+        assert pL.numel() == self.m
+        _ck(lib().sb200_stokes_pressure_reduce_order(self._h, _ptr(pL), _stream()))
+        return pL
+
+    def destroy(self):
+        if self._h:
+            _ck(lib().sb200_stokes_destroy(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _wrap(ptr, n):
+    """View n doubles of device memory owned by the library as a torch tensor (no copy)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device="cuda")

@@ -1,0 +1,168 @@
+// C ABI for the stokes.C shells (include/spectral_b200.h).
+#include <string>
+
+#include "../../include/spectral_b200.h"
+#include "common.cuh"
+#include "stokes.h"
+
+using namespace sb200;
+
+struct sb200_stokes {
+  StokesCtx* c = nullptr;
+  double* d_in = nullptr;  // staging for *_host
+  double* d_out = nullptr;
+};
+
+extern "C" {
+
+int sb200_stokes_create(int d, const int* dim, sb200_stokes** out) {
+  SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
+  *out = nullptr;
+  StokesCtx* c = nullptr;
+  SB_TRY(StokesCtx::create(d, dim, &c));
+  sb200_stokes* s = new sb200_stokes();
+  s->c = c;
+  *out = s;
+  return 0;
+}
+
+int sb200_stokes_sizes(const sb200_stokes* s, long long* m, long long* g, long long* gp, long long* gv, long long* dv) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  if (m) *m = s->c->gd.m;
+  if (g) *g = s->c->g;
+  if (gp) *gp = s->c->gp;
+  if (gv) *gv = s->c->gv;
+  if (dv) *dv = s->c->dvn;
+  return 0;
+}
+
+int sb200_stokes_set_rheology(sb200_stokes* s, int type, double hardness, double exponent, double regularization, double gamma0) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  if (type != 0 && type != 1) {  // stokes.C:491
+    set_last_error("Rheology type " + std::to_string(type) + " not implemented");
+    return SB200_ERR_SUP;
+  }
+  s->c->rheology = type;
+  s->c->hardness = hardness;
+  s->c->exponent = exponent;
+  s->c->regularization = regularization;
+  s->c->gamma0 = gamma0;
+  return 0;
+}
+
+int sb200_stokes_set_dirichlet(sb200_stokes* s, const double* d_values, void* stream) {
+  SB_CHECK(s && d_values, SB200_ERR_ARG, "null pointer");
+  SB_CUDA(cudaMemcpyAsync(s->c->dirichlet, d_values, (size_t)s->c->dvn * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream) {
+  SB_CHECK(s && d_force, SB200_ERR_ARG, "null pointer");
+  SB_CUDA(cudaMemcpyAsync(s->c->force, d_force, (size_t)s->c->g * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  return s->c->matmult(d_x, d_y, (cudaStream_t)stream);
+}
+
+int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVV: bad vectors");
+  return s->c->matmult_vv_into(d_x, s->c->gd.d, 0, d_y, s->c->gd.d, 0, (cudaStream_t)stream);
+}
+
+int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultPV: bad vectors");
+  return s->c->divergence_into(d_x, s->c->gd.d, 0, false, d_y, 1, 0, (cudaStream_t)stream);
+}
+
+int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVP: bad vectors");
+  return s->c->matmult_vp_into(d_x, 1, 0, d_y, s->c->gd.d, 0, false, nullptr, (cudaStream_t)stream);
+}
+
+int sb200_stokes_get_diagonal_schur(sb200_stokes* s, double* d_y, void* stream) {
+  SB_CHECK(s && d_y, SB200_ERR_ARG, "null pointer");
+  return s->c->get_diagonal_schur(d_y, (cudaStream_t)stream);
+}
+
+int sb200_stokes_matmult_schur(sb200_stokes* s, const double* d_x, double* d_y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream) {
+  SB_CHECK(s && d_x && d_y, SB200_ERR_ARG, "null pointer");
+  return s->c->matmult_schur(d_x, d_y, solve, solve_ctx, (cudaStream_t)stream);
+}
+
+int sb200_stokes_function(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  return s->c->function(d_x, d_y, (cudaStream_t)stream);
+}
+
+static int stokes_host_staging(sb200_stokes* s) {
+  if (s->d_in) return 0;
+  SB_CUDA(cudaMalloc((void**)&s->d_in, (size_t)s->c->g * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&s->d_out, (size_t)s->c->g * sizeof(double)));
+  return 0;
+}
+
+int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y) {
+  SB_CHECK(s && h_x && h_y, SB200_ERR_ARG, "null pointer");
+  SB_TRY(stokes_host_staging(s));
+  const size_t bytes = (size_t)s->c->g * sizeof(double);
+  SB_CUDA(cudaMemcpyAsync(s->d_in, h_x, bytes, cudaMemcpyHostToDevice, 0));
+  SB_TRY(s->c->matmult(s->d_in, s->d_out, 0));
+  SB_CUDA(cudaMemcpyAsync(h_y, s->d_out, bytes, cudaMemcpyDeviceToHost, 0));
+  SB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int sb200_stokes_function_host(sb200_stokes* s, const double* h_x, double* h_y) {
+  SB_CHECK(s && h_x && h_y, SB200_ERR_ARG, "null pointer");
+  SB_TRY(stokes_host_staging(s));
+  const size_t bytes = (size_t)s->c->g * sizeof(double);
+  SB_CUDA(cudaMemcpyAsync(s->d_in, h_x, bytes, cudaMemcpyHostToDevice, 0));
+  SB_TRY(s->c->function(s->d_in, s->d_out, 0));
+  SB_CUDA(cudaMemcpyAsync(h_y, s->d_out, bytes, cudaMemcpyDeviceToHost, 0));
+  SB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int sb200_stokes_eta_minmax(sb200_stokes* s, double* h_min, double* h_max, void* stream) {
+  SB_CHECK(s && h_min && h_max, SB200_ERR_ARG, "null pointer");
+  double mm[2];
+  SB_CUDA(cudaMemcpyAsync(mm, s->c->minmax, sizeof(mm), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *h_min = mm[0];
+  *h_max = mm[1];
+  return 0;
+}
+
+int sb200_stokes_get_state(sb200_stokes* s, int which, double* d_out, void* stream) {
+  SB_CHECK(s && d_out, SB200_ERR_ARG, "null pointer");
+  const double* src = nullptr;
+  size_t n = (size_t)s->c->gd.m;
+  if (which == 0) src = s->c->eta;
+  else if (which == 1) src = s->c->deta;
+  else if (which >= 2 && which < 2 + s->c->gd.d) {
+    src = s->c->strain[which - 2];
+    n *= s->c->gd.d;
+  }
+  SB_CHECK(src, SB200_ERR_USER, "state selector out of range");
+  SB_CUDA(cudaMemcpyAsync(d_out, src, n * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stream) {
+  SB_CHECK(s && d_pL, SB200_ERR_ARG, "null pointer");
+  return s->c->pressure_reduce_order(d_pL, (cudaStream_t)stream);
+}
+
+int sb200_stokes_destroy(sb200_stokes* s) {
+  if (!s) return 0;
+  delete s->c;
+  if (s->d_in) cudaFree(s->d_in);
+  if (s->d_out) cudaFree(s->d_out);
+  delete s;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,585 @@
+// Stokes operator shells (stokes.C:499-758) on device-resident fp64 vectors, Dirichlet boundary
+// (-boundary 0, the only configuration the reference documents as working, README:64-68).
+//
+// Layouts follow the reference: local velocity AoS [node][k] (stokes.C:651), local pressure [node],
+// global vector AoS per interior node [v_0..v_{d-1}, p] (stokes.C:867-877).  The VecScatters are
+// structured pad/crop index arithmetic; VecStrideGather/Scatter (stokes.C:585,613) are folded into
+// the derivative kernel's element stride/offset; the VecAXPY accumulations are its epilogue.
+#include "stokes.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "../../include/spectral_b200.h"
+#include "common.cuh"
+#include "deriv.h"
+
+namespace sb200 {
+
+namespace {
+
+struct NodeInfo {
+  bool interior;
+  long long gid;  // interior ordinal (walk order)
+  long long did;  // boundary ordinal (walk order)
+};
+
+__device__ __forceinline__ NodeInfo decode_node(const GridDesc& gd, long long idx) {
+  // walk-order semantics of StokesSetupDomain (stokes.C:791-879) / BlockIt::normal (util.C:70-82)
+  long long rem = idx, cnt = 0;
+  bool prefix_int = true, bdy = false;
+  for (int j = 0; j < gd.d; j++) {
+    const long long s = gd.stride[j];
+    const int i = (int)(rem / s);
+    rem -= (long long)i * s;
+    const bool b = (i == 0) || (i == gd.dim[j] - 1);
+    if (prefix_int) {
+      int c = i - 1;
+      c = c < 0 ? 0 : (c > gd.dim[j] - 2 ? gd.dim[j] - 2 : c);
+      cnt += (long long)c * gd.istride[j];
+      if (b) prefix_int = false;
+    }
+    bdy |= b;
+  }
+  NodeInfo n;
+  n.interior = !bdy;
+  n.gid = cnt;
+  n.did = idx - cnt;
+  return n;
+}
+
+// local[node*nc + k] = interior ? src[gid*sstride + soff + k] : (dir ? dir[did*nc + k] : 0)
+__global__ void pad_nodes_kernel(GridDesc gd, int nc, const double* __restrict__ src, int sstride, int soff,
+                                 const double* __restrict__ dir, double* __restrict__ local) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    const NodeInfo n = decode_node(gd, idx);
+    for (int k = 0; k < nc; k++) {
+      double v;
+      if (n.interior) v = src[n.gid * sstride + soff + k];
+      else v = dir ? dir[n.did * nc + k] : 0.0;
+      local[idx * nc + k] = v;
+    }
+  }
+}
+
+// dst[gid*dstride + doff + k] (=|+=) local[node*nc + k] (- sub[gid*dstride + doff + k]) at interior nodes
+__global__ void crop_nodes_kernel(GridDesc gd, int nc, const double* __restrict__ local, double* __restrict__ dst,
+                                  int dstride, int doff, int add, const double* __restrict__ sub) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    const NodeInfo n = decode_node(gd, idx);
+    if (!n.interior) continue;
+    for (int k = 0; k < nc; k++) {
+      const long long e = n.gid * dstride + doff + k;
+      double v = local[idx * nc + k];
+      if (add) v = dst[e] + v;             // VecAXPY(vG1, 1.0, vG0) stokes.C:513,750
+      if (sub) v = v + (-1.0) * sub[e];    // VecAXPY(yG, -1.0, force) stokes.C:756
+      dst[e] = v;
+    }
+  }
+}
+
+template <int D>
+struct VPtrs {
+  double* v[D];
+  const double* s[D];
+};
+
+// stokes.C:647-662: symmetrise, z = eps:E0, v = eta*eps + deta*E0*z
+template <int D>
+__global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, const double* __restrict__ deta, VPtrs<D> p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    double g[D][D], st[D][D], S0[D][D];
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        g[j][k] = p.v[j][i * D + k];
+        S0[j][k] = p.s[j][i * D + k];
+      }
+    double z = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        st[j][k] = __dmul_rn(0.5, __dadd_rn(g[j][k], g[k][j]));
+        z = __dadd_rn(z, __dmul_rn(st[j][k], S0[j][k]));
+      }
+    const double e = eta[i], de = deta[i];
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const double s = __dmul_rn(e, st[j][k]);
+        p.v[j][i * D + k] = __dadd_rn(s, __dmul_rn(__dmul_rn(de, S0[j][k]), z));
+      }
+  }
+}
+
+struct Rheo {
+  int type;
+  double hardness, exponent, regularization, gamma0;
+};
+
+__device__ __forceinline__ double atomicMinD(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) <= v) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while (assumed != old);
+  return __longlong_as_double(old);
+}
+__device__ __forceinline__ double atomicMaxD(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) >= v) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while (assumed != old);
+  return __longlong_as_double(old);
+}
+
+// stokes.C:708-725 + rheology (stokes.C:1920-1944): s = sym(grad v), gamma = 1/2 s:s, eta/deta, V = eta*s, strain = s
+template <int D>
+__global__ void rheology_kernel(long long m, Rheo r, double* __restrict__ eta, double* __restrict__ deta, VPtrs<D> p,
+                                double* __restrict__ minmax) {
+  // p.s[j] (const view) and the written strain are the same arrays: strain is read raw and overwritten
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double lmin = DBL_MAX, lmax = -DBL_MAX;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    double g[D][D], s[D][D];
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) g[j][k] = p.s[j][i * D + k];
+    double gamma = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        s[j][k] = __dmul_rn(0.5, __dadd_rn(g[j][k], g[k][j]));
+        gamma = __dadd_rn(gamma, __dmul_rn(0.5, __dmul_rn(s[j][k], s[j][k])));
+      }
+    double e, de;
+    if (r.type == 0) {
+      e = 1.0;
+      de = 0.0;
+    } else {
+      const double n = r.exponent;
+      const double pw = (1.0 - n) / (2.0 * n);
+      const double base = __dadd_rn(r.regularization, gamma / r.gamma0);
+      e = __dmul_rn(r.hardness, pow(base, pw));
+      de = (fabs(n) > 1.0e-5) ? __dmul_rn(r.hardness * pw / r.gamma0, pow(base, pw - 1.0)) : 0.0;
+    }
+    eta[i] = e;
+    deta[i] = de;
+    lmin = fmin(lmin, e);
+    lmax = fmax(lmax, e);
+    double* sw[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) sw[j] = const_cast<double*>(p.s[j]);
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        p.v[j][i * D + k] = __dmul_rn(e, s[j][k]);
+        sw[j][i * D + k] = s[j][k];
+      }
+  }
+  // block reduce min/max (VecMin / VecMax, stokes.C:731-734) without a host sync
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lmin <= lmax) {
+    atomicMinD(minmax, lmin);
+    atomicMaxD(minmax + 1, lmax);
+  }
+}
+
+__global__ void init_minmax_kernel(double* mm) {
+  mm[0] = DBL_MAX;
+  mm[1] = -DBL_MAX;
+}
+
+__global__ void recip_crop_kernel(GridDesc gd, const double* __restrict__ eta, double* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    const NodeInfo n = decode_node(gd, idx);
+    if (n.interior) y[n.gid] = 1.0 / eta[idx];  // scatterLP + VecReciprocal, stokes.C:549-551
+  }
+}
+
+__global__ void scale_kernel(long long n, double a, double* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * y[i];
+}
+
+// One pass of StokesPressureReduceOrder (stokes.C:1042-1074): along `axis`, set both end nodes of every
+// selected line to the degree-(P-3) extrapolation of its interior values.  Lines are enumerated over
+// the other axes; lo[j]/hi[j] bound the other indices (inclusive) so the three ordered passes touch
+// exactly the nodes the reference's loops leave in the final array.
+struct ReduceArgs {
+  int axis;
+  int lo[3], hi[3];
+  long long stride[3];
+  int P;
+  int nother;       // number of other axes (d-1)
+  int oax[2];       // the other axes, slowest first
+  long long nlines;
+};
+
+__global__ void reduce_order_kernel(ReduceArgs a, const double* __restrict__ w0, const double* __restrict__ w1,
+                                    double* __restrict__ pres) {
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= a.nlines) return;
+  long long rem = line, base = 0;
+  for (int q = a.nother - 1; q >= 0; q--) {
+    const int ax = a.oax[q];
+    const int ext = a.hi[ax] - a.lo[ax] + 1;
+    const int i = a.lo[ax] + (int)(rem % ext);
+    rem /= ext;
+    base += (long long)i * a.stride[ax];
+  }
+  const long long s = a.stride[a.axis];
+  double f0 = 0.0, f1 = 0.0;
+  for (int k = 1; k < a.P - 1; k++) {
+    const double v = pres[base + k * s];
+    f0 = fma(w0[k], v, f0);
+    f1 = fma(w1[k], v, f1);
+  }
+  pres[base] = f0;
+  pres[base + (long long)(a.P - 1) * s] = f1;
+}
+
+int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  return (int)std::min<long long>(std::max<long long>(b, 1), 148 * 16);
+}
+
+// Lagrange weights l_k(x_end) on the interior CGL nodes x_1..x_{P-2}, in long double.
+void extrap_weights(int P, std::vector<double>& w0, std::vector<double>& w1) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<long double> x(P);
+  for (int i = 0; i < P; i++) x[i] = cosl(pi * i / (P - 1));
+  w0.assign(P, 0.0);
+  w1.assign(P, 0.0);
+  for (int k = 1; k < P - 1; k++) {
+    long double a = 1.0L, b = 1.0L;
+    for (int j = 1; j < P - 1; j++) {
+      if (j == k) continue;
+      a *= (x[0] - x[j]) / (x[k] - x[j]);
+      b *= (x[P - 1] - x[j]) / (x[k] - x[j]);
+    }
+    w0[k] = (double)a;
+    w1[k] = (double)b;
+  }
+}
+
+}  // namespace
+
+// ---- StokesCtx ---------------------------------------------------------------------------
+int StokesCtx::create(int d, const int* dim, StokesCtx** out) {
+  SB_CHECK(d == 2 || d == 3, SB200_ERR_SUP, "Stokes shells are implemented for dimension 2 and 3 (stokes.C:1036)");
+  StokesCtx* c = new StokesCtx();
+  int rc = c->init(d, dim);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+int StokesCtx::init(int d, const int* dim) {
+  SB_TRY(gd.init(d, dim));
+  gp = gd.g;
+  gv = gd.g * d;
+  g = gd.g * (d + 1);
+  dvn = (gd.m - gd.g) * d;
+  const size_t mb = (size_t)gd.m * sizeof(double);
+  for (int k = 0; k < 2 + d; k++) SB_CUDA(cudaMalloc((void**)&workV[k], mb * d));  // xL, yL, V[d]
+  for (int k = 0; k < 3; k++) SB_CUDA(cudaMalloc((void**)&workP[k], mb));
+  for (int k = 0; k < d; k++) {
+    SB_CUDA(cudaMalloc((void**)&strain[k], mb * d));
+    SB_CUDA(cudaMemset(strain[k], 0, mb * d));
+  }
+  SB_CUDA(cudaMalloc((void**)&eta, mb));
+  SB_CUDA(cudaMalloc((void**)&deta, mb));
+  {
+    std::vector<double> ones((size_t)gd.m, 1.0);
+    SB_CUDA(cudaMemcpy(eta, ones.data(), mb, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemset(deta, 0, mb));
+  }
+  SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)dvn * sizeof(double))));
+  SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)dvn * sizeof(double))));
+  SB_CUDA(cudaMalloc((void**)&force, (size_t)g * sizeof(double)));
+  SB_CUDA(cudaMemset(force, 0, (size_t)g * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&vG0, (size_t)gv * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&vG1, (size_t)gv * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&minmax, 2 * sizeof(double)));
+  for (int k = 0; k < d; k++) {
+    Dax[k] = nullptr;
+    for (int q = 0; q < k; q++)
+      if (gd.dim[q] == gd.dim[k]) {
+        Dax[k] = Dax[q];
+        w0[k] = w0[q];
+        w1[k] = w1[q];
+      }
+    if (!Dax[k]) {
+      DiffMatrix* dm = new DiffMatrix();
+      SB_TRY(DiffMatrix::create(gd.dim[k], dm));
+      owned.push_back(dm);
+      Dax[k] = dm;
+      std::vector<double> a, b;
+      extrap_weights(gd.dim[k], a, b);
+      SB_CUDA(cudaMalloc((void**)&w0[k], a.size() * sizeof(double)));
+      SB_CUDA(cudaMalloc((void**)&w1[k], b.size() * sizeof(double)));
+      SB_CUDA(cudaMemcpy(w0[k], a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice));
+      SB_CUDA(cudaMemcpy(w1[k], b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
+      owned_w.push_back(w0[k]);
+      owned_w.push_back(w1[k]);
+    }
+  }
+  return 0;
+}
+
+StokesCtx::~StokesCtx() {
+  for (auto& p : workV)
+    if (p) cudaFree(p);
+  for (auto& p : workP)
+    if (p) cudaFree(p);
+  for (auto& p : strain)
+    if (p) cudaFree(p);
+  if (eta) cudaFree(eta);
+  if (deta) cudaFree(deta);
+  if (dirichlet) cudaFree(dirichlet);
+  if (force) cudaFree(force);
+  if (vG0) cudaFree(vG0);
+  if (vG1) cudaFree(vG1);
+  if (minmax) cudaFree(minmax);
+  for (double* p : owned_w) cudaFree(p);
+  for (DiffMatrix* dm : owned) {
+    dm->destroy();
+    delete dm;
+  }
+}
+
+int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
+  // DV[axis]: rank d+1 with trailing component axis of extent d (stokes.C:284-289)
+  DerivParams p;
+  p.D = Dax[axis]->d_D;
+  p.P = Dax[axis]->P;
+  p.Pp = Dax[axis]->Pp;
+  p.x = x;
+  p.y = y;
+  p.yin = yin;
+  p.O = gd.m / (gd.stride[axis] * gd.dim[axis]);
+  p.R = gd.stride[axis] * gd.d;
+  p.xs = p.ys = 1;
+  p.xoff = p.yoff = 0;
+  p.mode = mode;
+  return deriv_apply(p, s);
+}
+
+int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin,
+                       int mode, cudaStream_t s) {
+  // DP[axis] on a scalar field that may live inside an AoS vector (VecStrideGather/Scatter, stokes.C:585,613)
+  DerivParams p;
+  p.D = Dax[axis]->d_D;
+  p.P = Dax[axis]->P;
+  p.Pp = Dax[axis]->Pp;
+  p.x = x;
+  p.y = y;
+  p.yin = yin;
+  p.O = gd.m / (gd.stride[axis] * gd.dim[axis]);
+  p.R = gd.stride[axis];
+  p.xs = xs;
+  p.xoff = xoff;
+  p.ys = ys;
+  p.yoff = yoff;
+  p.mode = mode;
+  return deriv_apply(p, s);
+}
+
+int StokesCtx::pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s) {
+  pad_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, gd.d, src, sstride, soff, with_dirichlet ? dirichlet : nullptr, local);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int StokesCtx::pad_pres(const double* src, int sstride, int soff, double* local, cudaStream_t s) {
+  pad_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, 1, src, sstride, soff, nullptr, local);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int StokesCtx::crop(int nc, const double* local, double* dst, int dstride, int doff, bool add, const double* sub, cudaStream_t s) {
+  crop_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, nc, local, dst, dstride, doff, add ? 1 : 0, sub);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y_vel[interior] (=|+=) -sum_j D_j V_j   with V from the pointwise step; shared tail of VV and Function
+int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) {
+  const int d = gd.d;
+  double* yL = workV[1];
+  for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, workV[2 + i], yL, i == 0 ? nullptr : yL, DERIV_SUB, s));  // :668-671
+  return crop(d, yL, dst, dstride, doff, false, nullptr, s);
+}
+
+int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s) {
+  const int d = gd.d;
+  double* xL = workV[0];
+  SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));                                             // :635-637
+  for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
+  if (d == 2) {
+    VPtrs<2> p;
+    for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
+    vv_flux_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+  } else {
+    VPtrs<3> p;
+    for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
+    vv_flux_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+  }
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return viscous_tail(dst, dstride, doff, s);
+}
+
+int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride,
+                               int doff, cudaStream_t s) {
+  const int d = gd.d;
+  double* xL = workV[0];
+  SB_TRY(pad_vel(x, xstride, xoff, with_dirichlet, xL, s));  // :574-581
+  double* acc = workP[2];
+  for (int i = 0; i < d; i++)  // :584-590  component i gathered by stride, accumulated in the epilogue
+    SB_TRY(deriv_p(i, xL, d, i, acc, 1, 0, i == 0 ? nullptr : acc, DERIV_ADD, s));
+  return crop(1, acc, dst, dstride, doff, false, nullptr, s);  // :592
+}
+
+int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s) {
+  // stokes.C:1029-1080: z lines, then y lines, then x lines; later passes consume earlier results
+  const int d = gd.d;
+  for (int pass = 0; pass < d; pass++) {
+    const int axis = d - 1 - pass;
+    ReduceArgs a;
+    a.axis = axis;
+    a.P = gd.dim[axis];
+    if (a.P < 3) continue;
+    for (int j = 0; j < 3; j++) { a.lo[j] = 0; a.hi[j] = 0; a.stride[j] = 0; }
+    for (int j = 0; j < d; j++) {
+      a.stride[j] = gd.stride[j];
+      // axes slower than `axis` were not extended yet: interior only; faster ones already were: full range
+      a.lo[j] = (j < axis) ? 1 : 0;
+      a.hi[j] = (j < axis) ? gd.dim[j] - 2 : gd.dim[j] - 1;
+    }
+    a.nother = 0;
+    a.nlines = 1;
+    for (int j = 0; j < d; j++)
+      if (j != axis) {
+        a.oax[a.nother++] = j;
+        a.nlines *= (a.hi[j] - a.lo[j] + 1);
+      }
+    if (a.nlines <= 0) continue;
+    reduce_order_kernel<<<(unsigned)((a.nlines + 127) / 128), 128, 0, s>>>(a, w0[axis], w1[axis], pL);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, bool add,
+                               const double* sub, cudaStream_t s) {
+  const int d = gd.d;
+  double* pL = workP[0];
+  SB_TRY(pad_pres(x, xstride, xoff, pL, s));  // :606-608
+  SB_TRY(pressure_reduce_order(pL, s));       // :609
+  double* vL = workV[0];
+  for (int i = 0; i < d; i++) SB_TRY(deriv_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE, s));  // :611-614
+  return crop(d, vL, dst, dstride, doff, add, sub, s);                                         // :617
+}
+
+int StokesCtx::matmult(const double* xG, double* yG, cudaStream_t s) {
+  SB_CHECK(xG && yG && xG != yG, SB200_ERR_ARG, "StokesMatMult: x and y must be distinct non-null vectors");
+  const int d = gd.d;
+  SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s));                 // :508  vG1 = VV v
+  SB_TRY(divergence_into(xG, d + 1, 0, false, yG, d + 1, d, s));          // :509  pG1 = PV v
+  SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :512-513  vG1 += VP p
+  return 0;
+}
+
+int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
+  SB_CHECK(xG && yG && xG != yG, SB200_ERR_ARG, "StokesFunction: x and y must be distinct non-null vectors");
+  const int d = gd.d;
+  double* xL = workV[0];
+  SB_TRY(pad_vel(xG, d + 1, 0, true, xL, s));                                                 // :691-699
+  for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
+  init_minmax_kernel<<<1, 1, 0, s>>>(minmax);
+  count_launch();
+  Rheo r{rheology, hardness, exponent, regularization, gamma0};
+  if (d == 2) {
+    VPtrs<2> p;
+    for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
+    rheology_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+  } else {
+    VPtrs<3> p;
+    for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
+    rheology_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+  }
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  SB_TRY(viscous_tail(yG, d + 1, 0, s));                                // :737-744 -> velocity slots
+  SB_TRY(divergence_into(xG, d + 1, 0, true, yG, d + 1, d, s));         // :746 -> pressure slots
+  SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :747-750
+  // :756 yG -= force
+  {
+    SB_TRY(axpy_launch(g, -1.0, force, yG, s));
+  }
+  return 0;
+}
+
+int StokesCtx::get_diagonal_schur(double* y, cudaStream_t s) {
+  recip_crop_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, eta, y);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int StokesCtx::matmult_schur(const double* x, double* y, sb200_velocity_solve_fn solve, void* solve_ctx, cudaStream_t s) {
+  SB_CHECK(solve, SB200_ERR_ARG, "StokesMatMultSchur needs the inner velocity solve (KSPSchurVelocity, stokes.C:531)");
+  SB_TRY(matmult_vp_into(x, 1, 0, vG0, gd.d, 0, false, nullptr, s));  // :530
+  int rc = solve(solve_ctx, vG0, vG1, (void*)s);                      // :531
+  SB_CHECK(rc == 0, rc, "inner velocity solve failed");
+  SB_TRY(divergence_into(vG1, gd.d, 0, false, y, 1, 0, s));  // :532
+  scale_kernel<<<grid_for(gp), 256, 0, s>>>(gp, -1.0, y);     // :533
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+__global__ void axpy_kernel(long long n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = y[i] + a * x[i];
+}
+}  // namespace
+
+int axpy_launch(long long n, double a, const double* x, double* y, cudaStream_t s) {
+  axpy_kernel<<<grid_for(n), 256, 0, s>>>(n, a, x, y);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sb200

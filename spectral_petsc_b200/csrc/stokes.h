@@ -1,0 +1,59 @@
+// Internal: device-side context for the stokes.C shells (replaces StokesCtx, stokes.C:40-65).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "elliptic.h"  // GridDesc, DiffMatrix
+
+extern "C" typedef int (*sb200_velocity_solve_fn)(void* ctx, const double* d_rhs, double* d_sol, void* stream);
+
+namespace sb200 {
+
+struct StokesCtx {
+  GridDesc gd;
+  long long gp = 0, gv = 0, g = 0, dvn = 0;  // DOF counts printed at stokes.C:891
+  double* workV[2 + 3] = {};  // xL, yL, V[d]   (c->workV, stokes.C:271)
+  double* workP[3] = {};      // pL, scratch, accumulator (c->workP)
+  double* strain[3] = {};     // c->strain, each m*d
+  double* eta = nullptr;
+  double* deta = nullptr;
+  double* dirichlet = nullptr;  // dv values: boundary nodes in walk order x d components
+  double* force = nullptr;      // c->force (g)
+  double* vG0 = nullptr;        // c->vG0 / vG1 (used by the Schur shell)
+  double* vG1 = nullptr;
+  double* minmax = nullptr;     // device [min eta, max eta] of the last residual evaluation
+  double* w0[3] = {};           // end-point extrapolation weights per axis (StokesPressureReduceOrder)
+  double* w1[3] = {};
+  int rheology = 0;             // 0 linear, 1 power law (stokes.C:481-492)
+  double hardness = 1.0, exponent = 1.0, regularization = 1.0, gamma0 = 1.0;
+  DiffMatrix* Dax[3] = {};
+  std::vector<DiffMatrix*> owned;
+  std::vector<double*> owned_w;
+
+  static int create(int d, const int* dim, StokesCtx** out);
+  int init(int d, const int* dim);
+  ~StokesCtx();
+
+  int deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);
+  int deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode,
+              cudaStream_t s);
+  int pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s);
+  int pad_pres(const double* src, int sstride, int soff, double* local, cudaStream_t s);
+  int crop(int nc, const double* local, double* dst, int dstride, int doff, bool add, const double* sub, cudaStream_t s);
+  int viscous_tail(double* dst, int dstride, int doff, cudaStream_t s);
+  int matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s);
+  int divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride, int doff,
+                      cudaStream_t s);
+  int pressure_reduce_order(double* pL, cudaStream_t s);
+  int matmult_vp_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, bool add,
+                      const double* sub, cudaStream_t s);
+  int matmult(const double* xG, double* yG, cudaStream_t s);
+  int function(const double* xG, double* yG, cudaStream_t s);
+  int get_diagonal_schur(double* y, cudaStream_t s);
+  int matmult_schur(const double* x, double* y, sb200_velocity_solve_fn solve, void* solve_ctx, cudaStream_t s);
+};
+
+int axpy_launch(long long n, double a, const double* x, double* y, cudaStream_t s);
+
+}  // namespace sb200
