@@ -7,10 +7,17 @@ OBJDIR    := build
 LIB       := spectral_petsc_b200/libspectral_b200.so
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
-OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
+HOST      := spectral_petsc_b200/host
+HOST_SRCS := $(wildcard $(HOST)/*.cpp)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS)) $(patsubst $(HOST)/%.cpp,$(OBJDIR)/host_%.o,$(HOST_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
-all: $(LIB)
+DRIVER    := tests/cpp/ref_api_driver
+
+all: $(LIB) $(DRIVER)
+
+$(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
+	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -20,10 +27,14 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJDIR)
 	g++ -O2 -std=c++17 -fPIC -c $< -o $@
 
+$(OBJDIR)/host_%.o: $(HOST)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	g++ -O2 -std=c++17 -fPIC -c $< -o $@
+
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf $(OBJDIR) $(LIB)
+	rm -rf $(OBJDIR) $(LIB) $(DRIVER)
 
 .PHONY: all clean

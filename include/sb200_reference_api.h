@@ -1,0 +1,65 @@
+/* sb200_reference_api.h - the reference's own operator interface, re-implemented on the B200 path.
+ * Names, argument order and error behaviour are the reference's (file:line cited per function);
+ * Vecs are device resident.  These are thin C++ wrappers over the C ABI in spectral_b200.h. */
+#ifndef SB200_REFERENCE_API_H
+#define SB200_REFERENCE_API_H
+
+#include "sb200_petsc_shim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* chebyshev.h:31-34 */
+PetscErrorCode MatCreateCheb(MPI_Comm comm, int rank, int tr, int* dims, unsigned flag, Vec vx, Vec vy, Mat* A);
+PetscErrorCode ChebMult(Mat A, Vec vx, Vec vy);
+PetscErrorCode ChebDestroy(Mat A);
+
+/* elliptic.C:88-112 */
+typedef enum { BDY_DIRICHLET, BDY_NEUMANN } BdyType;
+typedef struct {
+  BdyType type;
+  PetscScalar value;
+} BdyCond;
+typedef PetscErrorCode (*BdyFunc)(int, double*, double*, BdyCond*);
+typedef struct { /* elliptic.C:88-94 */
+  PetscInt exact, d, *dim;
+  Mat A;
+  Vec b;
+  PetscReal gamma, exponent;
+  int debug;
+} AppCtx;
+PetscErrorCode DirichletBdy(int d, double* x, double* n, BdyCond* bc);
+PetscErrorCode MatCreate_Elliptic(MPI_Comm comm, int d, int* dim, unsigned flag, BdyFunc bf, Vec* vG, Mat* A);
+PetscErrorCode MatMult_Elliptic(Mat A, Vec U, Vec V);
+PetscErrorCode MatDestroy_Elliptic(Mat A);
+PetscErrorCode FormFunction(SNES snes, Vec U, Vec rhs, void* void_ac);
+/* CreateExactSolution(snes, u, u2) (elliptic.C:594-677); -cos_scale is passed explicitly because the
+ * reference reads it from the options database without a default (elliptic.C:607-609). */
+PetscErrorCode CreateExactSolution(SNES snes, Vec u, Vec u2, PetscReal cos_scale);
+
+/* stokes.C:67-79: the context is opaque here; options that StokesProcessOptions reads from the PETSc
+ * options database (stokes.C:392-495) are passed in a plain struct. */
+typedef struct {
+  PetscInt numDims, dim[3];
+  PetscInt exact, rheology;
+  PetscReal hardness, exponent, regularization, gamma0;
+} StokesOptionsB200;
+typedef struct StokesCtxB200 StokesCtxB200;
+PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A, Vec* x, StokesCtxB200** ctx);
+PetscErrorCode StokesDestroy(StokesCtxB200* ctx);
+PetscErrorCode StokesMatMult(Mat A, Vec xG, Vec yG);
+PetscErrorCode StokesMatMultVV(Mat A, Vec xG, Vec yG);
+PetscErrorCode StokesMatMultPV(Mat A, Vec xG, Vec yG);
+PetscErrorCode StokesMatMultVP(Mat A, Vec xG, Vec yG);
+PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y);
+PetscErrorCode StokesFunction(SNES snes, Vec xG, Vec yG, void* ctx);
+PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2);
+/* the inner shells created by StokesCreate (stokes.C:308-325) */
+PetscErrorCode StokesGetShells(StokesCtxB200* ctx, Mat* MatVV, Mat* MatPV, Mat* MatVP, Mat* MatSchur);
+PetscErrorCode StokesSetContinuation(StokesCtxB200* ctx, PetscReal exponent, PetscReal regularization); /* stokes.C:218-219 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

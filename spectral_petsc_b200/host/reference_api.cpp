@@ -1,0 +1,367 @@
+// The reference's operator interface on the B200 path (include/sb200_reference_api.h): same
+// names, same argument meaning, same error behaviour; each function cites what it replaces.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/sb200_reference_api.h"
+#include "../../include/spectral_b200.h"
+
+#define CHK(expr)            \
+  do {                       \
+    PetscErrorCode _e = (expr); \
+    if (_e) return _e;       \
+  } while (0)
+
+static const double PI_ = 3.14159265358979323846;  // chebyshev.h:10
+
+extern "C" {
+
+// ---- chebyshev.c ---------------------------------------------------------------------------
+// MatCreateCheb (chebyshev.c:89-138): N x N shell with MULT and DESTROY operations (:133-135).
+PetscErrorCode MatCreateCheb(MPI_Comm comm, int rank, int tr, int* dims, unsigned, Vec vx, Vec vy, Mat* A) {
+  PetscInt n = 0;
+  CHK(VecGetSize(vx, &n));
+  (void)vy;
+  sb200_cheb* c = nullptr;
+  CHK(sb200_cheb_create(rank, tr, dims, n, &c));
+  CHK(MatCreateShell(comm, n, n, n, n, c, A));
+  CHK(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))ChebMult));
+  CHK(MatShellSetOperation(*A, MATOP_DESTROY, (void (*)(void))ChebDestroy));
+  return 0;
+}
+
+// ChebMult (chebyshev.c:142-199)
+PetscErrorCode ChebMult(Mat A, Vec vx, Vec vy) {
+  sb200_cheb* c = nullptr;
+  const PetscScalar* x;
+  PetscScalar* y;
+  CHK(MatShellGetContext(A, (void**)&c));
+  CHK(VecCUDAGetArrayRead(vx, &x));
+  CHK(VecCUDAGetArrayWrite(vy, &y));
+  CHK(sb200_cheb_apply(c, x, y, nullptr));
+  CHK(VecCUDARestoreArrayRead(vx, &x));
+  CHK(VecCUDARestoreArrayWrite(vy, &y));
+  return 0;
+}
+
+// ChebDestroy (chebyshev.c:223-235)
+PetscErrorCode ChebDestroy(Mat A) {
+  sb200_cheb* c = nullptr;
+  CHK(MatShellGetContext(A, (void**)&c));
+  return sb200_cheb_destroy(c);
+}
+
+// ---- elliptic.C ------------------------------------------------------------------------------
+struct MatEllipticB200 {  // MatElliptic (elliptic.C:78-86): the device state lives behind `e`
+  sb200_elliptic* e;
+  int d;
+  std::vector<int> dim;
+  long long m, g, nd;
+};
+
+PetscErrorCode DirichletBdy(int, double*, double*, BdyCond* bc) {  // elliptic.C:470-477
+  bc->type = BDY_DIRICHLET;
+  bc->value = 0.0;
+  return 0;
+}
+
+PetscErrorCode MatCreate_Elliptic(MPI_Comm comm, int d, int* dim, unsigned, BdyFunc bf, Vec* vG, Mat* A) {
+  // elliptic.C:250-293.  SetupBC (elliptic.C:372-466) only supports Dirichlet ("Neumann not implemented", :406)
+  if (bf) {
+    BdyCond bc;
+    double x0[10] = {0}, n0[10] = {0};
+    CHK(bf(d, x0, n0, &bc));
+    if (bc.type != BDY_DIRICHLET) return SB200_ERR_SUP;
+  }
+  MatEllipticB200* c = new MatEllipticB200();
+  PetscErrorCode rc = sb200_elliptic_create(d, dim, &c->e);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  c->d = d;
+  c->dim.assign(dim, dim + d);
+  sb200_elliptic_sizes(c->e, &c->m, &c->g, &c->nd);
+  CHK(VecCreateSeqCUDA(comm, (PetscInt)c->g, vG));
+  CHK(MatCreateShell(comm, (PetscInt)c->g, (PetscInt)c->g, (PetscInt)c->g, (PetscInt)c->g, c, A));
+  CHK(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))MatMult_Elliptic));
+  CHK(MatShellSetOperation(*A, MATOP_DESTROY, (void (*)(void))MatDestroy_Elliptic));
+  return 0;
+}
+
+PetscErrorCode MatMult_Elliptic(Mat A, Vec U, Vec V) {  // elliptic.C:297-339
+  MatEllipticB200* c = nullptr;
+  CHK(MatShellGetContext(A, (void**)&c));
+  const PetscScalar* u;
+  PetscScalar* v;
+  CHK(VecCUDAGetArrayRead(U, &u));
+  CHK(VecCUDAGetArrayWrite(V, &v));
+  CHK(sb200_elliptic_matmult(c->e, u, v, nullptr));
+  CHK(VecCUDARestoreArrayRead(U, &u));
+  CHK(VecCUDARestoreArrayWrite(V, &v));
+  return 0;
+}
+
+PetscErrorCode MatDestroy_Elliptic(Mat A) {  // elliptic.C:343-368
+  MatEllipticB200* c = nullptr;
+  CHK(MatShellGetContext(A, (void**)&c));
+  PetscErrorCode rc = sb200_elliptic_destroy(c->e);
+  delete c;
+  return rc;
+}
+
+PetscErrorCode FormFunction(SNES, Vec U, Vec rhs, void* void_ac) {  // elliptic.C:481-533
+  AppCtx* ac = (AppCtx*)void_ac;
+  MatEllipticB200* c = nullptr;
+  CHK(MatShellGetContext(ac->A, (void**)&c));
+  CHK(sb200_elliptic_set_params(c->e, ac->gamma, ac->exponent));
+  const PetscScalar *u, *b;
+  PetscScalar* r;
+  CHK(VecCUDAGetArrayRead(ac->b, &b));
+  CHK(sb200_elliptic_set_rhs(c->e, b, nullptr));
+  CHK(VecCUDAGetArrayRead(U, &u));
+  CHK(VecCUDAGetArrayWrite(rhs, &r));
+  CHK(sb200_elliptic_function(c->e, u, r, nullptr));
+  return 0;
+}
+
+PetscErrorCode CreateExactSolution(SNES snes, Vec u, Vec u2, PetscReal cos_scale) {  // elliptic.C:594-677
+  AppCtx* ac = nullptr;
+  MatEllipticB200* c = nullptr;
+  CHK(SNESGetApplicationContext(snes, (void**)&ac));
+  CHK(MatShellGetContext(ac->A, (void**)&c));
+  const int d = c->d;
+  const double gamma = ac->gamma, exponent = ac->exponent;
+  double s = 0.5;
+  if (ac->exact == 0 || ac->exact == 3) s *= cos_scale;
+  if (ac->exact < 0 || ac->exact > 2) return 1;  // "Choose an exact solution." elliptic.C:657
+  std::vector<double> hu((size_t)c->g), hu2((size_t)c->g), hd((size_t)c->nd);
+  std::vector<int> ind(d, 0);
+  std::vector<double> x(d);
+  long long gi = 0, di = 0;
+  for (long long node = 0; node < c->m; node++) {
+    bool bdy = false;
+    for (int j = 0; j < d; j++) {
+      x[j] = cos(ind[j] * M_PI / (c->dim[j] - 1));  // elliptic.C:279
+      bdy = bdy || ind[j] == 0 || ind[j] == c->dim[j] - 1;
+    }
+    double v = 1.0, w = 0.0;
+    switch (ac->exact) {
+      case 0: {  // elliptic.C:620-632
+        for (int j = 0; j < d; j++) v *= cos(s * PI_ * x[j]);
+        const double eta = 1.0 + gamma * pow(v, exponent);
+        const double deta = (fabs(exponent) < 1e-10) ? 0.0 : gamma * exponent * pow(v, exponent - 1.0);
+        for (int j = 0; j < d; j++) {
+          double dv = 1.0;
+          for (int k = 0; k < d; k++) dv *= (k == j) ? -s * PI_ * sin(s * PI_ * x[k]) : cos(s * PI_ * x[k]);
+          const double d2v = -(s * PI_) * (s * PI_) * v;
+          w += deta * dv * dv + eta * d2v;
+        }
+        w = -w;
+      } break;
+      case 1:  // elliptic.C:633-643
+        for (int j = 0; j < d; j++) {
+          v *= (1 - x[j]) * (1 + x[j]);
+          double z = 1.0;
+          for (int k = 0; k < d; k++)
+            if (k != j) z *= 2.0 * (1 - x[k]) * (1 + x[k]);
+          w += z;
+        }
+        break;
+      case 2:  // elliptic.C:644-655
+        for (int j = 0; j < d; j++) {
+          v *= pow(x[j], 4 + j);
+          double z = 1.0;
+          for (int k = 0; k < d; k++) z *= (k == j) ? (4 + k) * (3 + k) * pow(x[k], 2 + k) : pow(x[k], 4 + k);
+          w -= z;
+        }
+        break;
+    }
+    if (bdy) hd[di++] = v;
+    else {
+      hu[gi] = v;
+      hu2[gi++] = w;
+    }
+    for (int j = d - 1; j >= 0; j--) {  // BlockIt::next (elliptic.C:27-40)
+      if (++ind[j] < c->dim[j]) break;
+      ind[j] = 0;
+    }
+  }
+  CHK(VecSetValuesHost(u, hu.data()));
+  CHK(VecSetValuesHost(u2, hu2.data()));
+  CHK(VecSetValuesHost(ac->b, hu2.data()));  // VecCopy(u2, ac->b) elliptic.C:674
+  // scatterLD into c->dirichlet (elliptic.C:672)
+  void* dd = nullptr;
+  CHK(sb200_malloc(&dd, hd.size() * sizeof(double) + 8));
+  CHK(sb200_memcpy_h2d(dd, hd.data(), hd.size() * sizeof(double), nullptr));
+  CHK(sb200_elliptic_set_dirichlet(c->e, (const double*)dd, nullptr));
+  CHK(sb200_stream_sync(nullptr));
+  CHK(sb200_free(dd));
+  return 0;
+}
+
+// ---- stokes.C ----------------------------------------------------------------------------------
+struct StokesCtxB200 {
+  sb200_stokes* s;
+  StokesOptionsB200 opt;
+  long long m, g, gp, gv, dv;
+  Mat MatVV, MatPV, MatVP, MatSchur;
+};
+
+static void stokes_exact(const StokesOptionsB200& o, const double* c, double* value, double* rhs) {
+  // StokesExact0..2 (stokes.C:1948-2012); value[d] for -exact 2 in 3-D is defined as 0
+  const int d = o.numDims;
+  for (int i = 0; i <= d; i++) value[i] = rhs[i] = 0.0;
+  if (o.exact == 0) return;
+  const double eta = 1.0;
+  const double u = sin(0.5 * M_PI * c[0]) * cos(0.5 * M_PI * c[1]);
+  const double v = -cos(0.5 * M_PI * c[0]) * sin(0.5 * M_PI * c[1]);
+  value[0] = u;
+  value[1] = v;
+  rhs[0] = (0.5 * M_PI) * (0.5 * M_PI) * eta * u;
+  rhs[1] = (0.5 * M_PI) * (0.5 * M_PI) * eta * v;
+  if (o.exact == 1) {
+    value[d] = 0.25 * (cos(M_PI * c[0]) + cos(M_PI * c[1])) + 10 * (c[0] + c[1]);
+    rhs[0] += -0.25 * M_PI * sin(M_PI * c[0]) + 10;
+    rhs[1] += -0.25 * M_PI * sin(M_PI * c[1]) + 10;
+  }
+}
+
+static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std::vector<double>* U2, std::vector<double>* D) {
+  const int d = c->opt.numDims;
+  int ind[3] = {0, 0, 0};
+  long long gi = 0, di = 0;
+  for (long long node = 0; node < c->m; node++) {
+    double x[3], val[4], rhs[4];
+    bool bdy = false;
+    for (int j = 0; j < d; j++) {
+      x[j] = cos(ind[j] * M_PI / (c->opt.dim[j] - 1));  // stokes.C:296
+      bdy = bdy || ind[j] == 0 || ind[j] == c->opt.dim[j] - 1;
+    }
+    stokes_exact(c->opt, x, val, rhs);
+    if (bdy) {
+      if (D) for (int k = 0; k < d; k++) (*D)[di * d + k] = val[k];
+      di++;
+    } else {
+      if (U) for (int k = 0; k <= d; k++) (*U)[gi * (d + 1) + k] = val[k];
+      if (U2) for (int k = 0; k <= d; k++) (*U2)[gi * (d + 1) + k] = rhs[k];
+      gi++;
+    }
+    for (int j = d - 1; j >= 0; j--) {
+      if (++ind[j] < c->opt.dim[j]) break;
+      ind[j] = 0;
+    }
+  }
+  return 0;
+}
+
+PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A, Vec* x, StokesCtxB200** ctx) {
+  // stokes.C:257-345 with StokesProcessOptions' switches (stokes.C:434-493)
+  if (opt->exact < 0 || opt->exact > 2) return SB200_ERR_SUP;      // stokes.C:452 (exact 3 is 2-D only, not wired)
+  if (opt->rheology < 0 || opt->rheology > 1) return SB200_ERR_SUP;  // stokes.C:492
+  StokesCtxB200* c = new StokesCtxB200();
+  c->opt = *opt;
+  int dim[3] = {opt->dim[0], opt->dim[1], opt->dim[2]};
+  PetscErrorCode rc = sb200_stokes_create(opt->numDims, dim, &c->s);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  sb200_stokes_sizes(c->s, &c->m, &c->g, &c->gp, &c->gv, &c->dv);
+  CHK(sb200_stokes_set_rheology(c->s, opt->rheology, opt->hardness, opt->exponent, opt->regularization, opt->gamma0));
+  // Dirichlet values = exact solution on the boundary (StokesDirichlet, stokes.C:2039-2050)
+  std::vector<double> D((size_t)c->dv);
+  stokes_fill(c, nullptr, nullptr, &D);
+  void* dd = nullptr;
+  CHK(sb200_malloc(&dd, D.size() * sizeof(double) + 8));
+  CHK(sb200_memcpy_h2d(dd, D.data(), D.size() * sizeof(double), nullptr));
+  CHK(sb200_stokes_set_dirichlet(c->s, (const double*)dd, nullptr));
+  CHK(sb200_stream_sync(nullptr));
+  CHK(sb200_free(dd));
+  CHK(VecCreateSeqCUDA(comm, (PetscInt)c->g, x));
+  CHK(MatCreateShell(comm, (PetscInt)c->g, (PetscInt)c->g, 0, 0, c, A));
+  CHK(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))StokesMatMult));  // stokes.C:309
+  CHK(MatCreateShell(comm, (PetscInt)c->gp, (PetscInt)c->gp, 0, 0, c, &c->MatSchur));
+  CHK(MatShellSetOperation(c->MatSchur, MATOP_GET_DIAGONAL, (void (*)(void))StokesMatGetDiagonalSchur));  // :319
+  CHK(MatCreateShell(comm, (PetscInt)c->gp, (PetscInt)c->gv, 0, 0, c, &c->MatPV));
+  CHK(MatShellSetOperation(c->MatPV, MATOP_MULT, (void (*)(void))StokesMatMultPV));  // :321
+  CHK(MatCreateShell(comm, (PetscInt)c->gv, (PetscInt)c->gp, 0, 0, c, &c->MatVP));
+  CHK(MatShellSetOperation(c->MatVP, MATOP_MULT, (void (*)(void))StokesMatMultVP));  // :323
+  CHK(MatCreateShell(comm, (PetscInt)c->gv, (PetscInt)c->gv, 0, 0, c, &c->MatVV));
+  CHK(MatShellSetOperation(c->MatVV, MATOP_MULT, (void (*)(void))StokesMatMultVV));  // :325
+  *ctx = c;
+  return 0;
+}
+
+PetscErrorCode StokesDestroy(StokesCtxB200* c) {  // stokes.C:348-388
+  if (!c) return 0;
+  MatDestroy(c->MatSchur);
+  MatDestroy(c->MatPV);
+  MatDestroy(c->MatVP);
+  MatDestroy(c->MatVV);
+  PetscErrorCode rc = sb200_stokes_destroy(c->s);
+  delete c;
+  return rc;
+}
+
+#define STOKES_SHELL(NAME, CALL)                                 \
+  PetscErrorCode NAME(Mat A, Vec xG, Vec yG) {                   \
+    StokesCtxB200* c = nullptr;                                  \
+    CHK(MatShellGetContext(A, (void**)&c));                      \
+    const PetscScalar* x;                                        \
+    PetscScalar* y;                                              \
+    CHK(VecCUDAGetArrayRead(xG, &x));                            \
+    CHK(VecCUDAGetArrayWrite(yG, &y));                           \
+    return CALL(c->s, x, y, nullptr);                            \
+  }
+STOKES_SHELL(StokesMatMult, sb200_stokes_matmult)        // stokes.C:499-519
+STOKES_SHELL(StokesMatMultVV, sb200_stokes_matmult_vv)   // stokes.C:623-676
+STOKES_SHELL(StokesMatMultPV, sb200_stokes_matmult_pv)   // stokes.C:557-566
+STOKES_SHELL(StokesMatMultVP, sb200_stokes_matmult_vp)   // stokes.C:599-619
+
+PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y) {  // stokes.C:542-553
+  StokesCtxB200* c = nullptr;
+  CHK(MatShellGetContext(S, (void**)&c));
+  PetscScalar* a;
+  CHK(VecCUDAGetArrayWrite(y, &a));
+  return sb200_stokes_get_diagonal_schur(c->s, a, nullptr);
+}
+
+PetscErrorCode StokesFunction(SNES, Vec xG, Vec yG, void* ctx) {  // stokes.C:680-758
+  StokesCtxB200* c = (StokesCtxB200*)ctx;
+  const PetscScalar* x;
+  PetscScalar* y;
+  CHK(VecCUDAGetArrayRead(xG, &x));
+  CHK(VecCUDAGetArrayWrite(yG, &y));
+  return sb200_stokes_function(c->s, x, y, nullptr);
+}
+
+PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2) {  // stokes.C:942-1003
+  StokesCtxB200* c = nullptr;
+  CHK(SNESGetApplicationContext(snes, (void**)&c));
+  std::vector<double> hu((size_t)c->g), hu2((size_t)c->g);
+  stokes_fill(c, &hu, &hu2, nullptr);
+  CHK(VecSetValuesHost(U, hu.data()));
+  CHK(VecSetValuesHost(U2, hu2.data()));
+  const PetscScalar* f;
+  CHK(VecCUDAGetArrayRead(U2, &f));
+  return sb200_stokes_set_force(c->s, f, nullptr);  // VecCopy(U2, c->force) stokes.C:1001
+}
+
+PetscErrorCode StokesGetShells(StokesCtxB200* c, Mat* MatVV, Mat* MatPV, Mat* MatVP, Mat* MatSchur) {
+  if (MatVV) *MatVV = c->MatVV;
+  if (MatPV) *MatPV = c->MatPV;
+  if (MatVP) *MatVP = c->MatVP;
+  if (MatSchur) *MatSchur = c->MatSchur;
+  return 0;
+}
+
+PetscErrorCode StokesSetContinuation(StokesCtxB200* c, PetscReal exponent, PetscReal regularization) {
+  c->opt.exponent = exponent;
+  c->opt.regularization = regularization;
+  return sb200_stokes_set_rheology(c->s, c->opt.rheology, c->opt.hardness, exponent, regularization, c->opt.gamma0);
+}
+
+}  // extern "C"

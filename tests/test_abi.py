@@ -63,3 +63,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 txt = open(os.path.join(root, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_reference_named_entry_points_exported():
+    """The host layer keeps the reference's own function names (sb200_reference_api.h)."""
+    import spectral_petsc_b200 as sp
+
+    L = sp.lib()
+    txt = open(os.path.join(ROOT, "include", "sb200_reference_api.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"PetscErrorCode\s+([A-Za-z_0-9]+)\s*\(", txt))
+    assert {"MatCreateCheb", "ChebMult", "ChebDestroy", "MatCreate_Elliptic", "MatMult_Elliptic", "FormFunction",
+            "StokesCreate", "StokesMatMult", "StokesMatMultVV", "StokesMatMultPV", "StokesMatMultVP", "StokesFunction"} <= names
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    shim = open(os.path.join(ROOT, "include", "sb200_petsc_shim.h")).read()
+    shim = re.sub(r"/\*.*?\*/", "", shim, flags=re.S)
+    for n in set(re.findall(r"PetscErrorCode\s+([A-Za-z_0-9]+)\s*\(", shim)):
+        assert hasattr(L, n), n
