@@ -13,6 +13,7 @@
 // two shared-memory loads that feed the B fragments; Ae/Bo stay resident in shared memory.
 #pragma once
 #include "common.cuh"
+#include "persist.h"
 
 namespace sb200 {
 
@@ -219,43 +220,53 @@ __device__ __forceinline__ void load_block(double* Xw, const double* __restrict_
 // field is ever materialised.  All extents equal P; `axis` is the chain axis, n0 the first line.
 template <int P, bool RIGHT>
 __device__ __forceinline__ void load_block_from_U(double* Xw, const double* __restrict__ U, int d, int axis,
-                                                  unsigned n0, int lane) {
+                                                  unsigned n0, int lane, const SlabGeom sg) {
   using E = EO<P>;
-  // decode the d-1 digits (base P) of line n0 over the axes other than `axis`, fastest axis first
+  // decode the d-1 digits (base P) of line n0 over the axes other than `axis`, fastest axis first;
+  // the slowest digit is whatever remains (axis 0 may have a local extent != P in slab mode)
   unsigned rem = n0;
-  long long gb = 0;      // global id of (line, m = 1) for c = 0
-  long long ist = 1;     // interior stride of the axis being visited
+  long long gb = -sg.goff;  // global id of (line, m = 1) for c = 0, relative to the local vector
+  long long ist = 1;        // interior stride of the axis being visited
   long long ist_a = 1, ist_fast = 1;
   int dig_fast = 0;
   bool inter = true;
   const int fast = RIGHT ? d - 2 : d - 1;
+  const int slowest = axis == 0 ? 1 : 0;
   for (int j = d - 1; j >= 0; j--) {
     if (j == axis) {
       ist_a = ist;
     } else {
-      const int dig = (int)(rem % P);
-      rem /= P;
+      int dig;
+      if (j == slowest) {
+        dig = (int)rem;
+      } else {
+        dig = (int)(rem % P);
+        rem /= P;
+      }
+      const int lo = 1, hi = (j == 0 ? sg.n0g : P) - 2;
+      const int gdig = dig + (j == 0 ? sg.i0 : 0);
       if (j == fast) {
-        dig_fast = dig;
+        dig_fast = gdig;
         ist_fast = ist;
       } else {
-        inter = inter && dig >= 1 && dig <= P - 2;
+        inter = inter && gdig >= lo && gdig <= hi;
       }
-      gb += (long long)(dig - 1) * ist;
+      gb += (long long)(gdig - 1) * ist;
     }
     ist *= (P - 2);
   }
+  const int fast_hi = (fast == 0 ? sg.n0g : P) - 2;
   if (RIGHT) {
     // lanes run along the line (contiguous in U); 8 lines, P/32 passes each
 #pragma unroll 4
     for (int i = 0; i < 8 * (P / 32); i++) {
       const int c = i / (P / 32), m = lane + 32 * (i % (P / 32));
-      const bool ok = inter && (dig_fast + c >= 1) && (dig_fast + c <= P - 2) && m >= 1 && m <= P - 2;
+      const bool ok = inter && (dig_fast + c >= 1) && (dig_fast + c <= fast_hi) && m >= 1 && m <= P - 2;
       cp_async8(Xw + c * E::LDR + m, U + (ok ? gb + c * ist_fast + (m - 1) : 0), ok);
     }
   } else {
     const int c = lane & 7;
-    const bool okc = inter && (dig_fast + c >= 1) && (dig_fast + c <= P - 2);
+    const bool okc = inter && (dig_fast + c >= 1) && (dig_fast + c <= fast_hi);
     const double* src = U + gb + c - ist_a;  // + m * ist_a  (ist_fast == 1 for the last axis)
 #pragma unroll 4
     for (int m = lane >> 3; m < P; m += 4) {

@@ -16,6 +16,7 @@
 #include "chain.cuh"
 #include "deriv.h"
 #include "elliptic.h"
+#include "persist.h"
 
 #ifdef SB200_TRACE
 #define STAMP(k) do { if (lane == 0 && p.trace) tr[k] = clock64(); } while (0)
@@ -27,31 +28,13 @@ namespace sb200 {
 
 namespace {
 
-struct PersistParams {
-  const double* Ae;
-  const double* Bo;
-  const double* U;     // global vector (g): the pad is applied by the block loader
-  const double* eta;   // m
-  const double* deta;  // m
-  const double* g0[SB200_MAX_DIM];   // gradu[k]
-  double* part[SB200_MAX_DIM];       // partial fields of the non-last axes
-  double* V;                         // g: cropped result
-  long long R[SB200_MAX_DIM];        // stride of axis k
-  long long nlines;                  // m / P (same for every axis)
-  int d;
-  int dim[SB200_MAX_DIM];
-  unsigned* sync;  // phase A: [0] ticket, [1] exited warps; phase B: [4], [5]
-  int stagger;       // start delay per warp group, in clocks
-  int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
-  long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
-};
 
 template <int P, int NT, bool RIGHT>
 __device__ __forceinline__ void load_item(double* Xw, const double* __restrict__ U, int d, int axis,
-                                          long long n0, int lane) {
+                                          long long n0, int lane, const SlabGeom sg) {
   constexpr int BE = RIGHT ? EO<P>::BLOCK_ELEMS_RIGHT : EO<P>::BLOCK_ELEMS_LEFT;
 #pragma unroll
-  for (int j = 0; j < NT; j++) load_block_from_U<P, RIGHT>(Xw + j * BE, U, d, axis, (unsigned)(n0 + 8 * j), lane);
+  for (int j = 0; j < NT; j++) load_block_from_U<P, RIGHT>(Xw + j * BE, U, d, axis, (unsigned)(n0 + 8 * j), lane, sg);
 }
 
 // Flux operands of two tiles (top and bottom pair each): eta, deta, gradu.
@@ -196,13 +179,19 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
       long long n = n0 + 8 * j + g, gid = 0, mul = 1;
       bool vint = true;
       for (int q = p.d - 2; q >= 0; q--) {
-        const int iq = (int)(n % p.dim[q]);
-        n /= p.dim[q];
-        vint = vint && iq > 0 && iq < p.dim[q] - 1;
+        int iq;
+        if (q == 0) {
+          iq = (int)n + p.sg.i0;  // slowest digit: whatever remains (+ slab offset)
+        } else {
+          iq = (int)(n % P);
+          n /= P;
+        }
+        const int ext = q == 0 ? p.sg.n0g : P;
+        vint = vint && iq > 0 && iq < ext - 1;
         gid += (long long)(iq - 1) * mul;
-        mul *= p.dim[q] - 2;
+        mul *= P - 2;
       }
-      const long long vrow = gid * (P - 2) - 1;  // V index of row m is vrow + m
+      const long long vrow = gid * (P - 2) - p.sg.goff - 1;  // V index of row m is vrow + m
 #pragma unroll
       for (int ib = 0; ib < E::MT; ib += 4) {
         double2 ot[4], ob[4];
@@ -279,7 +268,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   unsigned* sync = p.sync + (LASTPHASE ? 4 : 0);  // [0] ticket, [1] exited warps
 
   const unsigned items_per_axis = (unsigned)(p.nlines / (8 * NT));
-  const unsigned total = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1);
+  const unsigned total = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1 - p.first_axis);
   if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   load_matrices<P>(sm, p.Ae, p.Bo);
@@ -291,9 +280,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   };
   auto issue_load = [&](unsigned tk) {
     if (tk >= total) return;
-    const int axis = LASTPHASE ? p.d - 1 : tk / items_per_axis;
-    const long long n0 = (long long)(tk - (LASTPHASE ? 0 : axis * items_per_axis)) * (8 * NT);
-    load_item<P, NT, LASTPHASE>(Xw, p.U, p.d, axis, n0, lane);
+    const int arel = LASTPHASE ? 0 : tk / items_per_axis;
+    const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
+    const long long n0 = (long long)(tk - arel * items_per_axis) * (8 * NT);
+    load_item<P, NT, LASTPHASE>(Xw, p.U, p.d, axis, n0, lane, p.sg);
   };
 
   constexpr bool DEEP = (NWARPS * NT <= 8);  // 255 registers available
@@ -310,8 +300,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   }
 
   while (tk < total) {
-    const int axis = LASTPHASE ? p.d - 1 : tk / items_per_axis;
-    const long long n0 = (long long)(tk - (LASTPHASE ? 0 : axis * items_per_axis)) * (8 * NT);
+    const int arel = LASTPHASE ? 0 : tk / items_per_axis;
+    const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
+    const long long n0 = (long long)(tk - arel * items_per_axis) * (8 * NT);
     run_item<P, NT, LASTPHASE, DEEP>(p, axis, n0, Ae, Bo, Xw, lane);
     tk = grab();
     issue_load(tk);  // run_item waits for it at its top
@@ -335,7 +326,8 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1);
+  const long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
+  if (items <= 0) return 0;
   long long grid = (items + NWARPS - 1) / NWARPS;
   if (grid > sms) grid = sms;  // one persistent CTA per SM
   if (grid < 1) grid = 1;
@@ -355,42 +347,10 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
 }
 
 template <int P, int NWARPS, int NT>
-int launch_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
+int run_cfg(PersistParams& p, cudaStream_t s) {
   using E = EO<P>;
   constexpr int BEMAX = E::BLOCK_ELEMS_RIGHT > E::BLOCK_ELEMS_LEFT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
   const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * NT * BEMAX) * sizeof(double);
-  if (!e.sync) {
-    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
-    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
-  }
-  const int d = e.gd.d;
-  PersistParams p;
-  p.Ae = e.Dax[0]->d_Ae;
-  p.Bo = e.Dax[0]->d_Bo;
-  p.U = U;
-  p.eta = e.eta;
-  p.deta = e.deta;
-  p.V = V;
-  p.nlines = e.gd.m / P;
-  p.d = d;
-  for (int k = 0; k < d; k++) {
-    p.g0[k] = e.gradu[k];
-    p.part[k] = e.w[1 + k];
-    p.R[k] = e.gd.stride[k];
-    p.dim[k] = e.gd.dim[k];
-  }
-  p.sync = e.sync;
-  p.trace = e.trace;
-  {
-    static int stg = -1;
-    if (stg < 0) {
-      const char* c = getenv("SB200_STAGGER");
-      stg = c ? atoi(c) : 6000;  // measured best on B200 (profiles/r01_notes.md)
-    }
-    p.stagger = stg;
-    const char* xf = getenv("SB200_XFLAGS");
-    p.xflags = xf ? atoi(xf) : 0;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -410,25 +370,60 @@ bool elliptic_persist_supported(const EllipticCtx& e) {
   return (P == 32 || P == 64 || P == 128) && (e.gd.m / P) % 16 == 0;
 }
 
-int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
-  static int cfg = -1;
+int persist_run(int P, PersistParams& p, cudaStream_t s) {
+  static int cfg = -1, stg = -1;
   if (cfg < 0) {
     const char* c = getenv("SB200_PERSIST_CFG");
-    cfg = c ? atoi(c) : 2;  // 8 warps x 255 registers measured best on B200
+    cfg = c ? atoi(c) : 2;  // 8 warps x 255 registers measured best on B200 (profiles/r01_notes.md)
+    const char* g = getenv("SB200_STAGGER");
+    stg = g ? atoi(g) : 6000;
   }
-  switch (e.gd.dim[0]) {
-    case 32: return launch_persist<32, 16, 1>(e, U, V, s);
-    case 64: return launch_persist<64, 16, 1>(e, U, V, s);
+  p.stagger = stg;
+  const char* xf = getenv("SB200_XFLAGS");
+  p.xflags = xf ? atoi(xf) : 0;
+  SB_CHECK(p.nlines % 16 == 0, SB200_ERR_SUP, "persistent path: line count must be a multiple of 16");
+  switch (P) {
+    case 32: return run_cfg<32, 16, 1>(p, s);
+    case 64: return run_cfg<64, 16, 1>(p, s);
     case 128:
       switch (cfg) {
-        case 1: return launch_persist<128, 12, 1>(e, U, V, s);
-        case 2: return launch_persist<128, 8, 1>(e, U, V, s);
-        case 3: return launch_persist<128, 8, 2>(e, U, V, s);
-        default: return launch_persist<128, 16, 1>(e, U, V, s);
+        case 0: return run_cfg<128, 16, 1>(p, s);
+        case 1: return run_cfg<128, 12, 1>(p, s);
+        case 3: return run_cfg<128, 8, 2>(p, s);
+        default: return run_cfg<128, 8, 1>(p, s);
       }
   }
   set_last_error("persistent path: unsupported extent");
   return SB200_ERR_SUP;
+}
+
+int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
+  const int P = e.gd.dim[0], d = e.gd.d;
+  if (!e.sync) {
+    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
+    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
+  }
+  PersistParams p;
+  p.Ae = e.Dax[0]->d_Ae;
+  p.Bo = e.Dax[0]->d_Bo;
+  p.U = U;
+  p.eta = e.eta;
+  p.deta = e.deta;
+  p.V = V;
+  p.nlines = e.gd.m / P;
+  p.d = d;
+  for (int k = 0; k < d; k++) {
+    p.g0[k] = e.gradu[k];
+    p.part[k] = e.w[1 + k];
+    p.R[k] = e.gd.stride[k];
+  }
+  p.sync = e.sync;
+  p.sg.i0 = 0;
+  p.sg.n0g = P;
+  p.sg.goff = 0;
+  p.first_axis = 0;
+  p.trace = e.trace;
+  return persist_run(P, p, s);
 }
 
 }  // namespace sb200

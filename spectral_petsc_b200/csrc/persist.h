@@ -1,0 +1,41 @@
+// Internal: parameters of the persistent chain kernels (elliptic_persist.cu), shared with the slab
+// (multi-GPU) driver in elliptic_slab.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "elliptic.h"
+
+namespace sb200 {
+
+// Slab view of axis 0 for the multi-GPU partition: the local array holds planes [i0, i0+nloc) of a
+// global grid whose axis 0 has extent n0g; goff = global id of the first locally stored interior node.
+// Single GPU: i0 = 0, n0g = P, goff = 0.
+struct SlabGeom {
+  int i0, n0g;
+  long long goff;
+};
+
+struct PersistParams {
+  const double* Ae;
+  const double* Bo;
+  const double* U;     // global vector (g): the pad is applied by the block loader
+  const double* eta;   // m
+  const double* deta;  // m
+  const double* g0[SB200_MAX_DIM];   // gradu[k]
+  double* part[SB200_MAX_DIM];       // partial fields of the non-last axes
+  double* V;                         // g: cropped result
+  long long R[SB200_MAX_DIM];        // stride of axis k
+  long long nlines;                  // m / P (same for every axis)
+  int d;
+  unsigned* sync;  // phase A: [0] ticket, [1] exited warps; phase B: [4], [5]
+  SlabGeom sg;       // axis-0 slab view (single GPU: {0, P, 0})
+  int first_axis;    // phase A runs axes first_axis..d-2 (0; 1 in slab mode where axis 0 is exchanged)
+  int stagger;       // start delay per warp group, in clocks
+  int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
+  long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
+};
+
+// Runs phase A (axes first_axis..d-2) and phase B (last axis) for extent P in {32, 64, 128}.
+int persist_run(int P, PersistParams& p, cudaStream_t s);
+
+}  // namespace sb200
