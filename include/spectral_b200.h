@@ -90,6 +90,25 @@ int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, v
 int sb200_elliptic_set_path(sb200_elliptic* e, int path);
 /* Debug hook (only active in SB200_TRACE builds): device buffer receiving per-item phase clocks. */
 int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf);
+/* ---- slab partition over the GPUs of one node (no counterpart in the reference, which builds every Vec with
+ * VecCreateSeq on PETSC_COMM_SELF, elliptic.C:167,262; this is what an MPI-parallel MatCreate_Elliptic would
+ * be).  One process per GPU; rank r keeps planes [r*dim[0]/nranks, (r+1)*dim[0]/nranks) of every local array
+ * and the matching contiguous range [goff, goff + g) of the global Vec (lexicographic interior order), so
+ * sb200_elliptic_sizes() reports LOCAL sizes and every vector argument is the local part.  Axis-0 derivatives
+ * read / write the peers' memory directly over NVLink; all collective entry points (matmult, function) must be
+ * called by every rank in the same order.  dim[0] must be divisible by nranks (<= 8). */
+int sb200_elliptic_create_slab(int d, const int* dim, int rank, int nranks, sb200_elliptic** out);
+int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, int* i0, int* nloc, long long* goff, long long* gtotal);
+/* Synchronises the stream and reports how many device-side waits on a peer's flag gave up (~4 s each):
+ * non-zero means the ranks did not make the same sequence of collective calls (or a peer died). */
+int sb200_elliptic_slab_status(sb200_elliptic* e, long long* timeouts, void* stream);
+/* Peer mapping: each rank exports one CUDA IPC handle (sb200_ipc_handle_bytes() = 64 bytes), the host code
+ * exchanges them (MPI_Allgather / torch.distributed.all_gather) and attaches every peer's handle.
+ * attach_local maps a peer context living in the SAME process (several ranks driven by one process). */
+int sb200_ipc_handle_bytes(void);
+int sb200_elliptic_ipc_export(sb200_elliptic* e, void* handle);
+int sb200_elliptic_ipc_attach(sb200_elliptic* e, int peer_rank, const void* handle);
+int sb200_elliptic_attach_local(sb200_elliptic* e, int peer_rank, sb200_elliptic* peer);
 /* MatDestroy_Elliptic (elliptic.C:343-368). */
 int sb200_elliptic_destroy(sb200_elliptic* e);
 

@@ -115,16 +115,43 @@ class Cheb:
 class Elliptic:
     """MatCreate_Elliptic + the MatMult_Elliptic / FormFunction callbacks (elliptic.C)."""
 
-    def __init__(self, dim, gamma=0.0, exponent=2.0):
+    def __init__(self, dim, gamma=0.0, exponent=2.0, rank=0, nranks=1):
+        """nranks > 1: slab partition along axis 0 (one rank per GPU); m, g, nd are then LOCAL sizes and
+        every vector is the local part.  The peers must be attached (dist.attach_peers / attach_in_process)
+        before the first collective call."""
         dim = [int(v) for v in dim]
         arr = (ctypes.c_int * len(dim))(*dim)
         self._h = ctypes.c_void_p()
-        _ck(lib().sb200_elliptic_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        if nranks == 1:
+            _ck(lib().sb200_elliptic_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        else:
+            _ck(lib().sb200_elliptic_create_slab(ctypes.c_int(len(dim)), arr, ctypes.c_int(rank), ctypes.c_int(nranks), ctypes.byref(self._h)))
         m, g, nd = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
         _ck(lib().sb200_elliptic_sizes(self._h, ctypes.byref(m), ctypes.byref(g), ctypes.byref(nd)))
         self.dim, self.d = dim, len(dim)
         self.m, self.g, self.nd = m.value, g.value, nd.value
+        self.rank, self.nranks = rank, nranks
+        i0, nloc, goff, gtot = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong(), ctypes.c_longlong()
+        _ck(lib().sb200_elliptic_slab_info(self._h, None, None, ctypes.byref(i0), ctypes.byref(nloc), ctypes.byref(goff), ctypes.byref(gtot)))
+        self.i0, self.nloc, self.goff, self.gtotal = i0.value, nloc.value, goff.value, gtot.value
         self.set_params(gamma, exponent)
+
+    # peer mapping for the slab partition (see dist.py)
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(lib().sb200_ipc_handle_bytes())
+        _ck(lib().sb200_elliptic_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, peer_rank, handle):
+        _ck(lib().sb200_elliptic_ipc_attach(self._h, ctypes.c_int(peer_rank), ctypes.c_char_p(handle)))
+
+    def slab_timeouts(self):
+        n = ctypes.c_longlong()
+        _ck(lib().sb200_elliptic_slab_status(self._h, ctypes.byref(n), _stream()))
+        return n.value
+
+    def attach_local(self, peer_rank, peer):
+        _ck(lib().sb200_elliptic_attach_local(self._h, ctypes.c_int(peer_rank), peer._h))
 
     def set_params(self, gamma, exponent):
         _ck(lib().sb200_elliptic_set_params(self._h, ctypes.c_double(gamma), ctypes.c_double(exponent)))

@@ -185,11 +185,61 @@ int sb200_elliptic_create(int d, const int* dim, sb200_elliptic** out) {
   SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
   *out = nullptr;
   EllipticCtx* c = nullptr;
-  SB_TRY(EllipticCtx::create(d, dim, &c));
+  SB_TRY(EllipticCtx::create(d, dim, 0, 1, &c));
   sb200_elliptic* e = new sb200_elliptic();
   e->c = c;
   *out = e;
   return 0;
+}
+
+int sb200_elliptic_create_slab(int d, const int* dim, int rank, int nranks, sb200_elliptic** out) {
+  SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
+  *out = nullptr;
+  EllipticCtx* c = nullptr;
+  SB_TRY(EllipticCtx::create(d, dim, rank, nranks, &c));
+  sb200_elliptic* e = new sb200_elliptic();
+  e->c = c;
+  *out = e;
+  return 0;
+}
+
+int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, int* i0, int* nloc, long long* goff,
+                             long long* gtotal) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  if (rank) *rank = e->c->arena.rank;
+  if (nranks) *nranks = e->c->arena.nranks;
+  if (i0) *i0 = e->c->gd.i0;
+  if (nloc) *nloc = e->c->gd.dim[0];
+  if (goff) *goff = e->c->gd.goff;
+  if (gtotal) *gtotal = e->c->gtot;
+  return 0;
+}
+
+int sb200_elliptic_slab_status(sb200_elliptic* e, long long* timeouts, void* stream) {
+  SB_CHECK(e && timeouts, SB200_ERR_ARG, "null pointer");
+  unsigned long long n = 0;
+  SB_TRY(e->c->arena.timeouts((cudaStream_t)stream, &n));
+  *timeouts = (long long)n;
+  return 0;
+}
+
+int sb200_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int sb200_elliptic_ipc_export(sb200_elliptic* e, void* handle) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  return e->c->arena.export_handle(handle);
+}
+
+int sb200_elliptic_ipc_attach(sb200_elliptic* e, int peer_rank, const void* handle) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  return e->c->arena.attach(peer_rank, handle);
+}
+
+int sb200_elliptic_attach_local(sb200_elliptic* e, int peer_rank, sb200_elliptic* peer) {
+  SB_CHECK(e && peer, SB200_ERR_ARG, "null context");
+  SB_CHECK(peer->c->arena.rank == peer_rank && peer->c->arena.nranks == e->c->arena.nranks, SB200_ERR_USER,
+           "attach_local: peer context has a different rank / partition");
+  return e->c->arena.attach_ptr(peer_rank, peer->c->arena.base);
 }
 
 int sb200_elliptic_sizes(const sb200_elliptic* e, long long* m, long long* g, long long* nd) {

@@ -16,6 +16,11 @@ struct DerivParams {
   int xs, xoff;       // element e of x lives at x[e*xs + xoff]  (AoS component access)
   int ys, yoff;       // same for y / yin
   int mode;           // DerivMode: y = acc | yin - acc | yin + acc
+  // Slab-partitioned axis (multi-GPU, O == 1): input row k is read from xpeer[k / nloc] at local row
+  // k % nloc (peer memory over NVLink, the "all-gather" is the operand load itself); this rank computes
+  // output rows [row0, row0 + nloc) and stores them at local rows 0..nloc-1.  npeer <= 1: off.
+  int npeer = 0, nloc = 0, row0 = 0;
+  const double* xpeer[8] = {};
 };
 
 int deriv_apply(const DerivParams& p, cudaStream_t stream);

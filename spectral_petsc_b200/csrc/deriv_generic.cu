@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(NTHREADS) deriv_kernel(DerivParams p) {
   const int wm0 = (warp / WN) * (TM / WM);
   const int wn0 = (warp % WN) * 32;
   const int m0 = blockIdx.z * TM;
+  const bool slab = p.npeer > 1;
+  const int mout = slab ? p.nloc : p.P;  // output rows this launch produces
 
   // Column bookkeeping.
   const long long R = p.R;
@@ -74,16 +76,23 @@ __global__ void __launch_bounds__(NTHREADS) deriv_kernel(DerivParams p) {
     // A tile: D[m0 + m][k0 + k], 16-byte copies (D is padded: Pp % 32 == 0, rows 16B aligned).
     for (int idx = tid; idx < TM * (KC / 2); idx += NTHREADS) {
       int m = idx / (KC / 2), k2 = (idx % (KC / 2)) * 2;
-      bool ok = (m0 + m) < p.Pp;
-      const double* src = p.D + (size_t)(ok ? (m0 + m) : 0) * p.Pp + k0 + k2;
+      bool ok = (m0 + m) < (slab ? mout : p.Pp);
+      const double* src = p.D + (size_t)(ok ? (p.row0 + m0 + m) : 0) * p.Pp + k0 + k2;
       cp_async16(As + m * LDK + k2, src, ok);
     }
     if (LEFT) {
-      const double* xo = p.x;
       for (int idx = tid; idx < KC * TN; idx += NTHREADS) {
         int k = idx / TN, n = idx % TN;
         bool ok = (k0 + k) < p.P && n < ncols;
-        long long e = o_base * PR + (long long)(k0 + k) * R + r_base + n;
+        const double* xo = p.x;
+        long long e;
+        if (slab) {
+          const int kg = ok ? k0 + k : 0, q = kg / p.nloc;
+          xo = p.xpeer[q];
+          e = (long long)(kg - q * p.nloc) * R + r_base + n;
+        } else {
+          e = o_base * PR + (long long)(k0 + k) * R + r_base + n;
+        }
         cp_async8(Bs + k * Cfg::LDB + n, xo + (ok ? e * p.xs + p.xoff : 0), ok);
       }
     } else {
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS) deriv_kernel(DerivParams p) {
 #pragma unroll
   for (int i = 0; i < MT; i++) {
     const int row = m0 + wm0 + i * 8 + g;
-    if (row >= p.P) continue;
+    if (row >= mout) continue;
 #pragma unroll
     for (int j = 0; j < NT; j++) {
 #pragma unroll
@@ -188,7 +197,8 @@ int launch_cfg(const DerivParams& p, cudaStream_t stream) {
   if (LEFT) {
     const long long nb = ((p.R + TN - 1) / TN) * p.O;
     SB_CHECK(nb < (1ll << 31), SB200_ERR_SUP, "deriv: grid too large");
-    grid = dim3((unsigned)nb, 1, (unsigned)((p.P + TM - 1) / TM));
+    const int mout = p.npeer > 1 ? p.nloc : p.P;
+    grid = dim3((unsigned)nb, 1, (unsigned)((mout + TM - 1) / TM));
   } else {
     int groups = TN / (int)p.R;
     grid = dim3((unsigned)((p.O + groups - 1) / groups), 1, (unsigned)((p.P + TM - 1) / TM));
@@ -201,9 +211,10 @@ int launch_cfg(const DerivParams& p, cudaStream_t stream) {
 
 template <bool LEFT>
 int launch_by_P(const DerivParams& p, cudaStream_t stream) {
-  if (p.P <= 16) return launch_cfg<16, 1, 8, LEFT>(p, stream);
-  if (p.P <= 32) return launch_cfg<32, 1, 8, LEFT>(p, stream);
-  if (p.P <= 64) return launch_cfg<64, 2, 4, LEFT>(p, stream);
+  const int rows = p.npeer > 1 ? p.nloc : p.P;  // the row tile follows the rows this rank produces
+  if (rows <= 16) return launch_cfg<16, 1, 8, LEFT>(p, stream);
+  if (rows <= 32) return launch_cfg<32, 1, 8, LEFT>(p, stream);
+  if (rows <= 64) return launch_cfg<64, 2, 4, LEFT>(p, stream);
   return launch_cfg<128, 4, 2, LEFT>(p, stream);
 }
 
@@ -212,6 +223,10 @@ int launch_by_P(const DerivParams& p, cudaStream_t stream) {
 int deriv_apply(const DerivParams& p, cudaStream_t stream) {
   SB_CHECK(p.P >= 2 && p.O >= 1 && p.R >= 1, SB200_ERR_USER, "deriv: bad extents");
   SB_CHECK(p.x != p.y, SB200_ERR_ARG, "deriv: x and y must not alias (chebyshev.c:127)");
+  if (p.npeer > 1) {
+    SB_CHECK(p.O == 1 && p.nloc >= 1 && p.nloc * p.npeer == p.P, SB200_ERR_USER, "deriv: bad slab partition");
+    return launch_by_P<true>(p, stream);
+  }
   // LEFT needs enough contiguous columns per slab to fill a tile; otherwise batch o-groups.
   const int tn = p.P <= 32 ? 256 : (p.P <= 64 ? 128 : 64);
   if (p.R >= tn / 2) return launch_by_P<true>(p, stream);

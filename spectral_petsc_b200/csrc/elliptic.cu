@@ -30,17 +30,20 @@ struct LineInfo {
 
 __device__ __forceinline__ LineInfo decode_line(const GridDesc& gd, long long line) {
   // Same walk-order semantics as SetupBC (elliptic.C:386-415), specialised to whole last-axis lines.
+  // Slab view: axis-0 indices are offset by gd.i0 inside a global extent gd.n0g and the ordinals are
+  // relative to the first locally stored interior / boundary node.
   const int d = gd.d, PL = gd.dim[d - 1];
-  long long rem = line, cnt = 0;
+  long long rem = line, cnt = -gd.goff;
   bool prefix_int = true;
   for (int j = 0; j < d - 1; j++) {
     const long long s = gd.stride[j] / PL;
-    const int i = (int)(rem / s);
-    rem -= (long long)i * s;
-    const bool b = (i == 0) || (i == gd.dim[j] - 1);
+    const int il = (int)(rem / s);
+    rem -= (long long)il * s;
+    const int i = gd.gidx(j, il), ext = gd.gext(j);
+    const bool b = (i == 0) || (i == ext - 1);
     if (prefix_int) {
       int c = i - 1;
-      c = c < 0 ? 0 : (c > gd.dim[j] - 2 ? gd.dim[j] - 2 : c);
+      c = c < 0 ? 0 : (c > ext - 2 ? ext - 2 : c);
       cnt += (long long)c * gd.istride[j];
       if (b) prefix_int = false;
     }
@@ -171,13 +174,33 @@ int GridDesc::init(int d_, const int* dim_) {
     m *= dim[j];
     g *= dim[j] - 2;
   }
+  i0 = 0;
+  n0g = dim[0];
+  goff = 0;
+  return 0;
+}
+
+int GridDesc::init_slab(int d_, const int* dim_global, int rank, int nranks) {
+  SB_TRY(init(d_, dim_global));
+  if (nranks == 1) return 0;
+  SB_CHECK(d >= 2, SB200_ERR_USER, "slab partition needs at least two axes");
+  SB_CHECK(dim[0] % nranks == 0, SB200_ERR_USER, "slab partition: the outermost extent must be divisible by the number of ranks");
+  const int nloc = dim[0] / nranks;
+  n0g = dim[0];
+  i0 = rank * nloc;
+  dim[0] = nloc;
+  m = (long long)nloc * stride[0];
+  // interior planes among [i0, i0 + nloc)
+  const int lo = i0 < 1 ? 1 : i0, hi = (i0 + nloc > n0g - 1) ? n0g - 1 : i0 + nloc;  // [lo, hi)
+  g = (long long)(hi > lo ? hi - lo : 0) * istride[0];
+  goff = (long long)(lo - 1) * istride[0];
   return 0;
 }
 
 // ---- EllipticCtx ---------------------------------------------------------------------------
-int EllipticCtx::create(int d, const int* dim, EllipticCtx** out) {
+int EllipticCtx::create(int d, const int* dim, int rank, int nranks, EllipticCtx** out) {
   EllipticCtx* e = new EllipticCtx();
-  int rc = e->init(d, dim);
+  int rc = e->init(d, dim, rank, nranks);
   if (rc) {
     delete e;
     return rc;
@@ -186,21 +209,36 @@ int EllipticCtx::create(int d, const int* dim, EllipticCtx** out) {
   return 0;
 }
 
-int EllipticCtx::init(int d, const int* dim) {
-  SB_TRY(gd.init(d, dim));
+int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
+  SB_TRY(gd.init_slab(d, dim, rank, nranks));
+  gtot = 1;
+  for (int k = 0; k < d; k++) {
+    gdim[k] = dim[k];
+    gtot *= dim[k] - 2;
+  }
   nw = 2 + d;  // elliptic.C:259
   const size_t mb = (size_t)gd.m * sizeof(double);
-  for (int k = 0; k < nw; k++) SB_CUDA(cudaMalloc((void**)&w[k], mb));
+  const size_t gmax = (size_t)(gd.m / gd.stride[0]) * gd.istride[0];  // upper bound of any rank's local Vec
+  // every exchangeable array comes from one peer-mapped arena, in the same order on every rank
+  const int narr = nw + d + 2 + (nranks > 1 ? 3 : 0);
+  SB_TRY(arena.init((size_t)narr * (mb + 256) + (gmax * sizeof(double) + 256), rank, nranks));
+  for (int k = 0; k < nw; k++) SB_CHECK((w[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   for (int k = 0; k < d; k++) {
-    SB_CUDA(cudaMalloc((void**)&gradu[k], mb));
+    SB_CHECK((gradu[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CUDA(cudaMemset(gradu[k], 0, mb));
   }
-  SB_CUDA(cudaMalloc((void**)&eta, mb));
-  SB_CUDA(cudaMalloc((void**)&deta, mb));
+  SB_CHECK((eta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+  SB_CHECK((deta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+  if (nranks > 1) {
+    SB_CHECK((eta_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((deta_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((g0_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((Usym = arena.alloc_doubles(gmax)), SB200_ERR_CUDA, "arena exhausted");
+  }
   SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
   SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
-  SB_CUDA(cudaMalloc((void**)&b, (size_t)gd.g * sizeof(double)));
-  SB_CUDA(cudaMemset(b, 0, (size_t)gd.g * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&b, std::max<size_t>(8, (size_t)gd.g * sizeof(double))));
+  SB_CUDA(cudaMemset(b, 0, std::max<size_t>(8, (size_t)gd.g * sizeof(double))));
   {  // VecSet(eta, 1.0); VecSet(deta, 0.0) elliptic.C:266-267
     std::vector<double> ones((size_t)gd.m, 1.0);
     SB_CUDA(cudaMemcpy(eta, ones.data(), mb, cudaMemcpyHostToDevice));
@@ -209,10 +247,10 @@ int EllipticCtx::init(int d, const int* dim) {
   for (int k = 0; k < d; k++) {
     Dax[k] = nullptr;
     for (int q = 0; q < k; q++)
-      if (gd.dim[q] == gd.dim[k]) Dax[k] = Dax[q];
+      if (gdim[q] == gdim[k]) Dax[k] = Dax[q];
     if (!Dax[k]) {
       DiffMatrix* dm = new DiffMatrix();
-      SB_TRY(DiffMatrix::create(gd.dim[k], dm));
+      SB_TRY(DiffMatrix::create(gdim[k], dm));
       owned.push_back(dm);
       Dax[k] = dm;
     }
@@ -221,12 +259,7 @@ int EllipticCtx::init(int d, const int* dim) {
 }
 
 EllipticCtx::~EllipticCtx() {
-  for (int k = 0; k < SB200_MAX_DIM + 2; k++)
-    if (w[k]) cudaFree(w[k]);
-  for (int k = 0; k < SB200_MAX_DIM; k++)
-    if (gradu[k]) cudaFree(gradu[k]);
-  if (eta) cudaFree(eta);
-  if (deta) cudaFree(deta);
+  arena.destroy();
   if (dirichlet) cudaFree(dirichlet);
   if (b) cudaFree(b);
   if (sync) cudaFree(sync);
@@ -249,6 +282,17 @@ int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, 
   p.xs = p.ys = 1;
   p.xoff = p.yoff = 0;
   p.mode = mode;
+  if (axis == 0 && arena.nranks > 1) {
+    // the partitioned axis: operand rows are pulled from the planes' owners (x must be an arena array);
+    // the barriers order the peers' writes of x before our reads and our reads before their next writes
+    p.npeer = arena.nranks;
+    p.nloc = gd.dim[0];
+    p.row0 = gd.i0;
+    for (int q = 0; q < arena.nranks; q++) p.xpeer[q] = arena.on(q, x);
+    SB_TRY(arena.barrier(s));
+    SB_TRY(deriv_apply(p, s));
+    return arena.barrier(s);
+  }
   return deriv_apply(p, s);
 }
 
@@ -277,11 +321,15 @@ int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStr
 int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
   SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
   const int d = gd.d;
-  if (path == 3 || (path == 0 && elliptic_persist_supported(*this))) {
+  if (arena.nranks > 1) {
+    SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+    if ((path == 0 || path == 3) && elliptic_slab_fused_supported(*this)) return elliptic_matmult_slab_fused(*this, U, V, s);
+    SB_CHECK(path <= 1, SB200_ERR_SUP, "slab partition: the fused path needs equal extents P in {32,64,128}");
+  } else if (path == 3 || (path == 0 && elliptic_persist_supported(*this))) {
     SB_CHECK(elliptic_persist_supported(*this), SB200_ERR_SUP, "persistent path needs equal extents P in {32,64,128}");
     return elliptic_matmult_persist(*this, U, V, s);
   }
-  if (path == 2) {
+  if (path == 2 && arena.nranks == 1) {
     SB_CHECK(elliptic_fused_supported(*this), SB200_ERR_SUP, "fused path needs equal extents P in {32,64,128}");
     return elliptic_matmult_fused(*this, U, V, s);
   }
@@ -316,6 +364,7 @@ int EllipticCtx::function(const double* U, double* F, cudaStream_t s) {
   SB_CUDA(cudaGetLastError());
   for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[1 + k], w[0], k == 0 ? nullptr : w[0], DERIV_SUB, s));  // :520-524
   SB_TRY(crop(w[0], b, F, s));  // :528-531
+  pencil_valid = false;         // eta / deta / gradu[0] changed: the axis-0 pencil copies are stale
   return 0;
 }
 

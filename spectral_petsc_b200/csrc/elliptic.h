@@ -4,6 +4,8 @@
 
 #include <vector>
 
+#include "symm.h"
+
 #define SB200_MAX_DIM 10  // elliptic.C:138 "Maximum number of dimensions"
 
 namespace sb200 {
@@ -25,7 +27,16 @@ struct GridDesc {
   long long stride[SB200_MAX_DIM];   // row-major strides of the full grid
   long long istride[SB200_MAX_DIM];  // row-major strides of the interior (dim-2) grid
   long long m, g;                    // local nodes, interior (global) nodes
+  // Slab view of axis 0 (multi-GPU partition along the outermost axis): the local arrays hold planes
+  // [i0, i0 + dim[0]) of a grid whose axis 0 has n0g nodes; goff = interior nodes in the planes before
+  // i0 (the local global-vector starts there).  Single GPU: i0 = 0, n0g = dim[0], goff = 0.
+  int i0, n0g;
+  long long goff;
   int init(int d, const int* dim);
+  // dim_global: the full grid; this rank keeps planes [rank*nloc, (rank+1)*nloc), nloc = dim_global[0]/nranks
+  int init_slab(int d, const int* dim_global, int rank, int nranks);
+  __host__ __device__ int gext(int j) const { return j == 0 ? n0g : dim[j]; }
+  __host__ __device__ int gidx(int j, int i) const { return j == 0 ? i + i0 : i; }
 };
 
 struct EllipticCtx {
@@ -43,10 +54,21 @@ struct EllipticCtx {
   unsigned* sync = nullptr;  // ticket / completion counters of the persistent kernel
   DiffMatrix* Dax[SB200_MAX_DIM] = {};
   std::vector<DiffMatrix*> owned;
+  // slab partition (nranks == 1: plain single-GPU context; all device arrays live in the arena)
+  SymmArena arena;
+  int gdim[SB200_MAX_DIM] = {};     // global extents
+  long long gtot = 0;               // global Vec length over all ranks
+  double* Usym = nullptr;           // staged copy of the input vector, readable by the peers
+  double* eta_p = nullptr;          // axis-0 pencil copies of eta / deta / gradu[0] for the fused MatMult
+  double* deta_p = nullptr;
+  double* g0_p = nullptr;
+  bool pencil_valid = false;
+  unsigned long long mm_epoch = 0;  // fused MatMult epoch (SYMM_READY / SYMM_DONE flags)
 
-  static int create(int d, const int* dim, EllipticCtx** out);
-  int init(int d, const int* dim);
+  static int create(int d, const int* dim, int rank, int nranks, EllipticCtx** out);
+  int init(int d, const int* dim, int rank, int nranks);
   ~EllipticCtx();
+  int refresh_pencils(cudaStream_t s);
   int deriv(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);
   int pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s);
   int crop(const double* local, const double* rhs, double* V, cudaStream_t s);
@@ -58,5 +80,9 @@ bool elliptic_fused_supported(const EllipticCtx& e);
 int elliptic_matmult_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
 bool elliptic_persist_supported(const EllipticCtx& e);
 int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
+bool elliptic_slab_fused_supported(const EllipticCtx& e);
+int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
+// x_pencil[m][nl] = x_slab(plane m, line rank*R/G + nl) pulled from the owners of the planes
+int slab_to_pencil(const SymmArena& a, const double* x_slab, double* x_pencil, int P, long long R, cudaStream_t s);
 
 }  // namespace sb200

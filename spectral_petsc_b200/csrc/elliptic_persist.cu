@@ -85,16 +85,20 @@ __device__ __forceinline__ void flux_apply(const FluxBuf& f, const Own<P, RIGHT>
 
 // The whole chain for one item.  Returns after the epilogue stores are issued.
 // DEEP: keep one flux batch in flight across GEMM1 and double-buffer the batches (needs registers).
-template <int P, int NT, bool RIGHT, bool DEEP>
+// PENCIL (slab mode, axis 0): n0 is the line index inside this rank's pencil; the flux operands come
+// from the pencil-layout state and the result rows are pushed to the part[0] array of the planes' owners.
+// WAITDONE (slab mode, last axis): part[0] is complete once every rank has raised its DONE flag.
+template <int P, int NT, bool RIGHT, bool DEEP, bool PENCIL = false, bool WAITDONE = false>
 __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long long n0, const double* Ae,
                                          const double* Bo, double* Xw, int lane) {
   using E = EO<P>;
+  static_assert(!(PENCIL && RIGHT), "pencil items are strided-axis items");
   constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
   const int g = lane >> 2, t = lane & 3;
   LineGeom lg;
-  lg.R = p.R[axis];
+  lg.R = PENCIL ? p.Rp : p.R[axis];
   lg.PR = (long long)P * lg.R;
-  lg.nlines = p.nlines;
+  lg.nlines = PENCIL ? p.Rp : p.nlines;
   Own<P, RIGHT> own[NT];
   long long base0[NT];
 #pragma unroll
@@ -106,19 +110,21 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     own[j].g = g;
     own[j].t = t;
   }
-  const double* __restrict__ g0 = p.g0[axis];
-  const double* __restrict__ etap = (p.xflags & 1) ? nullptr : p.eta;
+  const double* __restrict__ g0 = PENCIL ? p.g0_p : p.g0[axis];
+  const double* __restrict__ eta_a = PENCIL ? p.eta_p : p.eta;
+  const double* __restrict__ deta_a = PENCIL ? p.deta_p : p.deta;
+  const double* __restrict__ etap = (p.xflags & 1) ? nullptr : eta_a;
 #ifdef SB200_TRACE
   long long* tr = p.trace ? p.trace + ((long long)axis * (p.nlines / (8 * NT)) + n0 / (8 * NT)) * 8 : nullptr;
   if (lane == 0 && p.trace) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); tr[6] = smid; tr[7] = threadIdx.x >> 5; }
 #endif
   STAMP(0);
   FluxBuf f0, f1;
-  if (DEEP) flux_load<P, RIGHT>(f0, own[0], 0, etap, p.deta, g0);
+  if (DEEP) flux_load<P, RIGHT>(f0, own[0], 0, etap, deta_a, g0);
 #pragma unroll
   for (int j = 0; j < NT; j++) {
-    prefetch_block<P, RIGHT>(p.eta, base0[j], lg.R, lane);
-    prefetch_block<P, RIGHT>(p.deta, base0[j], lg.R, lane);
+    prefetch_block<P, RIGHT>(eta_a, base0[j], lg.R, lane);
+    prefetch_block<P, RIGHT>(deta_a, base0[j], lg.R, lane);
     prefetch_block<P, RIGHT>(g0, base0[j], lg.R, lane);
   }
   cp_async_wait<0>();
@@ -134,18 +140,18 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     double* Xj = Xw + j * BE;
     if (DEEP) {
       // software pipeline: batch k+1 is in flight while batch k is applied
-      if (j > 0) flux_load<P, RIGHT>(f0, own[j], 0, etap, p.deta, g0);
+      if (j > 0) flux_load<P, RIGHT>(f0, own[j], 0, etap, deta_a, g0);
 #pragma unroll
       for (int ib = 0; ib < E::MT; ib += 4) {
-        flux_load<P, RIGHT>(f1, own[j], ib + 2, etap, p.deta, g0);
+        flux_load<P, RIGHT>(f1, own[j], ib + 2, etap, deta_a, g0);
         flux_apply<P, RIGHT>(f0, own[j], ib, Xj, a[j], b[j]);
-        if (ib + 4 < E::MT) flux_load<P, RIGHT>(f0, own[j], ib + 4, etap, p.deta, g0);
+        if (ib + 4 < E::MT) flux_load<P, RIGHT>(f0, own[j], ib + 4, etap, deta_a, g0);
         flux_apply<P, RIGHT>(f1, own[j], ib + 2, Xj, a[j], b[j]);
       }
     } else {
 #pragma unroll
       for (int ib = 0; ib < E::MT; ib += 2) {
-        flux_load<P, RIGHT>(f0, own[j], ib, etap, p.deta, g0);
+        flux_load<P, RIGHT>(f0, own[j], ib, etap, deta_a, g0);
         flux_apply<P, RIGHT>(f0, own[j], ib, Xj, a[j], b[j]);
       }
     }
@@ -159,6 +165,20 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   if (p.xflags & 2) {
     // experiment: no epilogue traffic (keep one dependent store so the GEMM is not dead code)
     if (a[0][0][0] + b[0][0][0] == 12345.678) p.V[0] = 1.0;
+  } else if (PENCIL) {
+    // axis 0 of the slab partition: rows of D f go to the part[0] array of the rank that owns the plane
+    const int nloc = 1 << p.lognloc;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const long long col = (long long)p.rank * p.Rp + n0 + 8 * j + 2 * t;  // line index inside a plane
+#pragma unroll
+      for (int i = 0; i < E::MT; i++) {
+        const int mt = i * 8 + g, mb = P - 1 - mt;
+        const int qt = mt >> p.lognloc, qb = mb >> p.lognloc;
+        st2(p.part0peer[qt] + (long long)(mt - qt * nloc) * p.R0 + col, a[j][i][0] + b[j][i][0], a[j][i][1] + b[j][i][1]);
+        st2(p.part0peer[qb] + (long long)(mb - qb * nloc) * p.R0 + col, b[j][i][0] - a[j][i][0], b[j][i][1] - a[j][i][1]);
+      }
+    }
   } else if (!RIGHT) {
     // non-last axis: partial_k = D f
     double* __restrict__ part = p.part[axis];
@@ -174,6 +194,10 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     // last axis: phase A (all partials) must be complete and visible, then
     // V = crop(((0 - p_0) - p_1 ...) - D f)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (WAITDONE) {
+      if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_DONE + lane, p.epoch, p.sf.f[p.rank]);
+      __syncwarp();
+    }
 #pragma unroll
     for (int j = 0; j < NT; j++) {
       long long n = n0 + 8 * j + g, gid = 0, mul = 1;
@@ -256,7 +280,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   STAMP(5);
 }
 
-template <int P, int NWARPS, int NT, bool LASTPHASE>
+template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
 __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p) {
   using E = EO<P>;
   extern __shared__ double sm[];
@@ -268,7 +292,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   unsigned* sync = p.sync + (LASTPHASE ? 4 : 0);  // [0] ticket, [1] exited warps
 
   const unsigned items_per_axis = (unsigned)(p.nlines / (8 * NT));
-  const unsigned total = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1 - p.first_axis);
+  // slab phase A: the axis-0 pencil items come first (their operands cross NVLink), then the local axes
+  const unsigned items0 = (SLAB && !LASTPHASE) ? (unsigned)(p.Rp / (8 * NT)) : 0u;
+  const unsigned total = LASTPHASE ? items_per_axis : items0 + items_per_axis * (p.d - 1 - p.first_axis);
   if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   load_matrices<P>(sm, p.Ae, p.Bo);
@@ -278,11 +304,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     if (lane == 0) tk = atomicAdd(sync, 1u);
     return __shfl_sync(0xffffffffu, tk, 0);
   };
+  bool peers_ready = false;
   auto issue_load = [&](unsigned tk) {
     if (tk >= total) return;
-    const int arel = LASTPHASE ? 0 : tk / items_per_axis;
+    if (SLAB && !LASTPHASE && tk < items0) {
+      if (!peers_ready) {
+        // every rank's staged input vector must be complete before its planes are read
+        if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_READY + lane, p.epoch, p.sf.f[p.rank]);
+        __syncwarp();
+        peers_ready = true;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; j++)
+        load_block_from_peers<P>(Xw + j * E::BLOCK_ELEMS_LEFT, p, (unsigned)((long long)p.rank * p.Rp + (long long)tk * (8 * NT) + 8 * j), lane);
+      return;
+    }
+    const unsigned tl = tk - items0;
+    const int arel = LASTPHASE ? 0 : tl / items_per_axis;
     const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
-    const long long n0 = (long long)(tk - arel * items_per_axis) * (8 * NT);
+    const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
     load_item<P, NT, LASTPHASE>(Xw, p.U, p.d, axis, n0, lane, p.sg);
   };
 
@@ -300,33 +340,45 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   }
 
   while (tk < total) {
-    const int arel = LASTPHASE ? 0 : tk / items_per_axis;
-    const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
-    const long long n0 = (long long)(tk - arel * items_per_axis) * (8 * NT);
-    run_item<P, NT, LASTPHASE, DEEP>(p, axis, n0, Ae, Bo, Xw, lane);
+    if (SLAB && !LASTPHASE && tk < items0) {
+      run_item<P, NT, false, DEEP, true>(p, 0, (long long)tk * (8 * NT), Ae, Bo, Xw, lane);
+    } else {
+      const unsigned tl = tk - items0;
+      const int arel = LASTPHASE ? 0 : tl / items_per_axis;
+      const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
+      const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
+      run_item<P, NT, LASTPHASE, DEEP, false, SLAB && LASTPHASE>(p, axis, n0, Ae, Bo, Xw, lane);
+    }
     tk = grab();
     issue_load(tk);  // run_item waits for it at its top
   }
   cp_async_wait<0>();
+  if (SLAB && !LASTPHASE) __threadfence_system();  // this warp's pushes are out before it counts as gone
   // the last warp to leave re-arms the counters for the next launch
   if (lane == 0) {
     const unsigned gone = atomicAdd(sync + 1, 1u);
     if (gone == gridDim.x * NWARPS - 1) {
       sync[0] = 0;
       sync[1] = 0;
+      if (SLAB && !LASTPHASE) {
+        // every axis-0 result of this rank has been pushed: tell all ranks (including this one)
+        __threadfence_system();
+        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
+      }
     }
   }
 }
 
-template <int P, int NWARPS, int NT, bool LASTPHASE>
+template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
 int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
-  auto kern = persist_kernel<P, NWARPS, NT, LASTPHASE>;
+  auto kern = persist_kernel<P, NWARPS, NT, LASTPHASE, SLAB>;
   static bool attr = false;
   if (!attr) {
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
+  long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
+  if (SLAB && !LASTPHASE) items += p.Rp / (8 * NT);
   if (items <= 0) return 0;
   long long grid = (items + NWARPS - 1) / NWARPS;
   if (grid > sms) grid = sms;  // one persistent CTA per SM
@@ -354,8 +406,13 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  SB_TRY((launch_phase<P, NWARPS, NT, false>(p, smem, sms, s)));
-  SB_TRY((launch_phase<P, NWARPS, NT, true>(p, smem, sms, s)));
+  if (p.nranks > 1) {
+    SB_TRY((launch_phase<P, NWARPS, NT, false, true>(p, smem, sms, s)));
+    SB_TRY((launch_phase<P, NWARPS, NT, true, true>(p, smem, sms, s)));
+    return 0;
+  }
+  SB_TRY((launch_phase<P, NWARPS, NT, false, false>(p, smem, sms, s)));
+  SB_TRY((launch_phase<P, NWARPS, NT, true, false>(p, smem, sms, s)));
   return 0;
 }
 
@@ -363,7 +420,7 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
 
 bool elliptic_persist_supported(const EllipticCtx& e) {
   const int d = e.gd.d;
-  if (d < 2) return false;
+  if (d < 2 || e.arena.nranks > 1) return false;
   const int P = e.gd.dim[0];
   for (int j = 1; j < d; j++)
     if (e.gd.dim[j] != P) return false;
@@ -403,7 +460,7 @@ int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStr
     SB_CUDA(cudaMalloc((void**)&e.sync, 64));
     SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
   }
-  PersistParams p;
+  PersistParams p = {};
   p.Ae = e.Dax[0]->d_Ae;
   p.Bo = e.Dax[0]->d_Bo;
   p.U = U;
@@ -422,6 +479,8 @@ int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStr
   p.sg.n0g = P;
   p.sg.goff = 0;
   p.first_axis = 0;
+  p.nranks = 1;
+  p.rank = 0;
   p.trace = e.trace;
   return persist_run(P, p, s);
 }

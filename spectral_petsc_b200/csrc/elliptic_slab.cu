@@ -1,0 +1,156 @@
+// Slab-partitioned MatMult_Elliptic (elliptic.C:297-339) over 2/4/8 GPUs: the grid is cut along its
+// outermost axis, one process per GPU.  Derivatives along the local axes never leave the GPU.  The
+// axis-0 chain  D_0 (eta D_0 w + eta' w g0)  runs on "pencils" (all P planes of 1/G of the lines):
+// the persistent chain kernel (elliptic_persist.cu) loads the operand planes straight from the owners'
+// staged input vectors over NVLink (the forward all-to-all is the operand load) and stores the result
+// rows straight into the owners' partial field (the backward all-to-all is the epilogue store).  Ranks
+// order themselves with two epoch flags in peer memory (READY: my input is staged; DONE: all my
+// results are pushed), never through the host.  Launches per application: stage+signal, phase A
+// (pencil items + local axes), phase B (last axis, waits for DONE).
+#include "../../include/spectral_b200.h"
+#include "common.cuh"
+#include "deriv.h"
+#include "elliptic.h"
+#include "persist.h"
+
+namespace sb200 {
+
+namespace {
+
+__global__ void stage_kernel(const double* __restrict__ U, double* __restrict__ Usym, long long n, unsigned* counter,
+                             SymmFlags sf, unsigned long long epoch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) Usym[i] = U[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int q = 0; q < sf.nranks; q++) st_release_sys(sf.f[q] + SYMM_READY + sf.rank, epoch);
+    }
+  }
+}
+
+struct PeerPtrs {
+  const double* x[SB200_MAX_RANKS];
+};
+
+__global__ void slab_to_pencil_kernel(PeerPtrs pp, double* __restrict__ xp, int P, int nloc, long long R0, long long Rp,
+                                      int rank) {
+  const long long total = (long long)P * Rp, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int m = (int)(i / Rp);
+    const long long nl = i - (long long)m * Rp;
+    const int q = m / nloc;
+    xp[i] = __ldcg(pp.x[q] + (long long)(m - q * nloc) * R0 + (long long)rank * Rp + nl);
+  }
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) l++;
+  return l;
+}
+
+}  // namespace
+
+int slab_to_pencil(const SymmArena& a, const double* x_slab, double* x_pencil, int P, long long R0, cudaStream_t s) {
+  PeerPtrs pp;
+  for (int q = 0; q < SB200_MAX_RANKS; q++) pp.x[q] = q < a.nranks ? a.on(q, x_slab) : nullptr;
+  const long long Rp = R0 / a.nranks, total = (long long)P * Rp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  slab_to_pencil_kernel<<<(unsigned)blocks, 256, 0, s>>>(pp, x_pencil, P, P / a.nranks, R0, Rp, a.rank);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int EllipticCtx::refresh_pencils(cudaStream_t s) {
+  // collective: every rank reaches this at the same point (first MatMult after a FormFunction)
+  SB_TRY(arena.barrier(s));
+  const int P = gdim[0];
+  SB_TRY(slab_to_pencil(arena, eta, eta_p, P, gd.stride[0], s));
+  SB_TRY(slab_to_pencil(arena, deta, deta_p, P, gd.stride[0], s));
+  SB_TRY(slab_to_pencil(arena, gradu[0], g0_p, P, gd.stride[0], s));
+  pencil_valid = true;
+  return 0;
+}
+
+bool elliptic_slab_fused_supported(const EllipticCtx& e) {
+  const int d = e.gd.d, G = e.arena.nranks;
+  if (G < 2 || d < 2) return false;
+  const int P = e.gdim[0];
+  for (int j = 1; j < d; j++)
+    if (e.gdim[j] != P) return false;
+  if (!(P == 32 || P == 64 || P == 128)) return false;
+  if ((G & (G - 1)) != 0 || P % G != 0) return false;
+  const long long R0 = e.gd.stride[0];
+  if (R0 % G != 0 || (R0 / G) % 16 != 0) return false;
+  return (e.gd.m / P) % 16 == 0;
+}
+
+int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
+  SB_CHECK(e.arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+  const int P = e.gdim[0], d = e.gd.d, G = e.arena.nranks;
+  if (!e.sync) {
+    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
+    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
+  }
+  if (!e.pencil_valid) SB_TRY(e.refresh_pencils(s));
+  const unsigned long long epoch = ++e.mm_epoch;
+  SymmFlags sf;
+  for (int q = 0; q < SB200_MAX_RANKS; q++) sf.f[q] = q < G ? e.arena.flags(q) : nullptr;
+  sf.rank = e.arena.rank;
+  sf.nranks = G;
+  {
+    long long blocks = (e.gd.g + 1023) / 1024;
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(U, e.Usym, e.gd.g, e.sync + 8, sf, epoch);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  PersistParams p = {};
+  p.Ae = e.Dax[0]->d_Ae;
+  p.Bo = e.Dax[0]->d_Bo;
+  p.U = U;
+  p.eta = e.eta;
+  p.deta = e.deta;
+  p.V = V;
+  p.nlines = e.gd.m / P;
+  p.d = d;
+  for (int k = 0; k < d; k++) {
+    p.g0[k] = e.gradu[k];
+    p.part[k] = e.w[1 + k];
+    p.R[k] = e.gd.stride[k];
+  }
+  p.sync = e.sync;
+  p.sg.i0 = e.gd.i0;
+  p.sg.n0g = e.gd.n0g;
+  p.sg.goff = e.gd.goff;
+  p.first_axis = 1;
+  p.nranks = G;
+  p.rank = e.arena.rank;
+  const int nloc = P / G;
+  p.lognloc = ilog2(nloc);
+  for (int q = 0; q < G; q++) {
+    p.Upeer[q] = e.arena.on(q, e.Usym);
+    const int lo = q * nloc < 1 ? 1 : q * nloc;
+    p.goffq[q] = (long long)(lo - 1) * e.gd.istride[0];
+    p.part0peer[q] = e.arena.on(q, e.w[1]);
+  }
+  p.eta_p = e.eta_p;
+  p.deta_p = e.deta_p;
+  p.g0_p = e.g0_p;
+  p.R0 = e.gd.stride[0];
+  p.Rp = p.R0 / G;
+  p.sf = sf;
+  p.epoch = epoch;
+  p.trace = nullptr;
+  return persist_run(P, p, s);
+}
+
+}  // namespace sb200

@@ -30,12 +30,24 @@ struct PersistParams {
   unsigned* sync;  // phase A: [0] ticket, [1] exited warps; phase B: [4], [5]
   SlabGeom sg;       // axis-0 slab view (single GPU: {0, P, 0})
   int first_axis;    // phase A runs axes first_axis..d-2 (0; 1 in slab mode where axis 0 is exchanged)
+  // ---- slab mode (nranks > 1): axis 0 runs on "pencils" (all P planes of R0/nranks lines) --------
+  int nranks, rank, lognloc;            // nloc = P / nranks = 1 << lognloc planes per rank
+  const double* Upeer[SB200_MAX_RANKS]; // staged input vector of every rank (peer memory)
+  long long goffq[SB200_MAX_RANKS];     // global id of the first interior node stored by rank q
+  double* part0peer[SB200_MAX_RANKS];   // part[0] (slab layout) of every rank: axis-0 results are pushed
+  const double* eta_p;                  // pencil-layout copies [P][Rp] of eta / deta / gradu[0]
+  const double* deta_p;
+  const double* g0_p;
+  long long R0, Rp;                     // lines per plane; lines per pencil (R0 / nranks)
+  SymmFlags sf;
+  unsigned long long epoch;             // READY / DONE flag value of this application
   int stagger;       // start delay per warp group, in clocks
   int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
   long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
 };
 
-// Runs phase A (axes first_axis..d-2) and phase B (last axis) for extent P in {32, 64, 128}.
+// Runs phase A (axes first_axis..d-2; in slab mode also the axis-0 pencil items) and phase B (last
+// axis) for extent P in {32, 64, 128}.
 int persist_run(int P, PersistParams& p, cudaStream_t s);
 
 }  // namespace sb200

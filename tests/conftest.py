@@ -3,6 +3,13 @@ import sys
 
 import pytest
 
+# several slab ranks are driven from one process on separate streams (tests/test_gpu_slab.py): give every
+# stream its own hardware queue so a kernel waiting for a peer never blocks that peer's launch
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and load every kernel at start-up: a lazy module load blocks the host until running kernels finish,
+# which would stall the launch of the very kernel a spinning peer rank is waiting for
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
