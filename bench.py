@@ -52,53 +52,75 @@ def alg_bytes(dim):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every ~10 ms on a background thread for
+    the whole measurement (the timed region is only milliseconds long, so nvidia-smi's 100 ms loop cannot
+    see it).  Reports the median clock over the samples taken under load (GPU utilisation or power up)."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+
+        self.samples = []
+        self.ok = False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # LOCAL_RANK indexes the visible devices; map through CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            try:
+                phys = int(vis.split(",")[gpu_index]) if vis else gpu_index
+            except (ValueError, IndexError):
+                phys = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
         except Exception:
-            self.p = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            # median over the samples taken under load (upper half of the observed clocks)
-            hi = sorted(sm)[len(sm) // 2:]
-            out["sm_mhz"] = statistics.median(hi)
-            out["sm_max_mhz"] = max(smax)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        self._stop.set()
+        self.t.join(timeout=2)
+        nv = self.nv
+        if not self.samples:
+            return out
+        pmax = max(p for _, p, _ in self.samples)
+        pmin = min(p for _, p, _ in self.samples)
+        thr = pmin + 0.5 * (pmax - pmin)
+        load = [x for x in self.samples if x[1] >= thr] or self.samples
+        out["sm_mhz"] = statistics.median(x[0] for x in load)
+        out["sm_max_mhz"] = self.smax
+        out["samples"] = len(self.samples)
+        out["samples_under_load"] = len(load)
+        out["power_w_max"] = pmax
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        seen = set()
+        for _, _, rs in load:
+            for k, bit in names.items():
+                if rs & bit:
+                    seen.add(k)
+        out["reasons"] = sorted(seen)
         return out
 
 
@@ -169,28 +191,36 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    G = sp.Elliptic(DIM, gamma=GAMMA, exponent=EXPONENT)
+    # N > 1: slab partition along axis 0, one rank per GPU; the axis-0 chain crosses NVLink through peer
+    # memory inside the chain kernel (no NCCL call on the data path).  Vectors are the ranks' local parts.
+    G = sp.Elliptic(DIM, gamma=GAMMA, exponent=EXPONENT, rank=rank, nranks=world)
+    if world > 1:
+        from spectral_petsc_b200 import dist as spd
+
+        spd.attach_peers(G)
     if args.path is not None:
         G.set_path(args.path)
-    Us = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(G.g)).to(dev)
+    sl = slice(G.goff, G.goff + G.g)
+    Us = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(G.gtotal)[sl].copy()).to(dev)
     G.form_function(Us)  # populates eta / deta / gradu
-    U_host = torch.from_numpy(np.random.default_rng(0).standard_normal(G.g)).pin_memory()
+    U_host = torch.from_numpy(np.random.default_rng(0).standard_normal(G.gtotal)[sl].copy()).pin_memory()
     V_host = torch.empty(G.g, dtype=torch.float64).pin_memory()
     U = U_host.to(dev)
     V = torch.empty_like(U)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+    m_global = int(np.prod(DIM))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         G.mat_mult(U, V)
     barrier()
 
     # ---- device-resident timing: per-step CUDA events, L2 flushed between steps ----------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = sp.launch_count()
     barrier()
@@ -205,12 +235,13 @@ def run_cuda(args):
     total_ms = sum(step_ms)
     # back-to-back (L2-warm) figure for context
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hot_steps = max(args.steps, 2000)  # >= 0.2 s under load so the clock sampler sees the loaded state
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(hot_steps):
         G.mat_mult(U, V)
     e1.record()
     barrier()
-    hot_ms = e0.elapsed_time(e1)
+    hot_ms = e0.elapsed_time(e1) * args.steps / hot_steps
     clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end through the host-buffer C-ABI call (H2D + op + D2H every step) ----------
@@ -234,7 +265,7 @@ def run_cuda(args):
     total_ms, hot_ms, e2e_ms = t.tolist()
 
     if rank == 0:
-        ndof = G.m * world  # replicas until the slab partition lands: every rank applies the full operator
+        ndof = m_global  # one global operator application per step, whatever the number of ranks
         value = ndof * args.steps / (total_ms * 1e-3) / 1e9
         fl = alg_flops(DIM)
         achieved = fl * args.steps / (total_ms * 1e-3) / 1e12
@@ -242,18 +273,18 @@ def run_cuda(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "elliptic 3D -dim 128,128,128 MatMult_Elliptic, variable coefficients (gamma=4, exponent=2)",
-                       "n_dof_per_step": G.m, "global_vec_len": G.g, "l2": "256 MiB flush between timed steps (per-step CUDA events, flush untimed)",
+                       "n_dof_per_step": m_global, "global_vec_len": G.gtotal, "l2": "256 MiB flush between timed steps (per-step CUDA events, flush untimed)",
                        "value_l2_warm": ndof * args.steps / (hot_ms * 1e-3) / 1e9,
-                       "parallelism": "replicas" if world > 1 else "single"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                       "parallelism": ("slab%d: axis 0 cut over %d GPUs, axis-0 chain through NVLink peer memory inside the chain kernel" % (world, world)) if world > 1 else "single"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS * world, "unit": "TFLOP/s", "frac": achieved / (FP64_PEAK_TFLOPS * world),
                          "traffic": None, "pipe": "fp64 DMMA", "peak_source": "tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.jsonl); MEASURED_PEAKS.json has no fp64 entry",
-                         "algorithmic_flops_per_step": fl, "kernel": "whole MatMult step (all launches)",
-                         "hbm": {"achieved": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_step": alg_bytes(DIM)}},
-            "e2e": {"value": ndof * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": G.g * 8, "d2h_bytes_per_step": G.g * 8,
+                         "algorithmic_flops_per_step": fl, "kernel": "persist_kernel<128,8,1> phases A+B (the whole MatMult step: 2 PDL-linked launches)" if world == 1 else "slab step: stage + persist_kernel phases A+B per rank",
+                         "hbm": {"achieved": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                                 "frac": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9 / (hbm_peak * world), "algorithmic_bytes_per_step": alg_bytes(DIM)}},
+            "e2e": {"value": ndof * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": G.gtotal * 8, "d2h_bytes_per_step": G.gtotal * 8,
                     "api": "sb200_elliptic_matmult_host (pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,

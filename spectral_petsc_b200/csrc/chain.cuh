@@ -277,39 +277,4 @@ __device__ __forceinline__ void load_block_from_U(double* Xw, const double* __re
   cp_async_commit();
 }
 
-// Slab mode, axis 0: the 8-line block (global line index n0 over axes 1..d-1) spans all P planes; plane m
-// is read from the staged vector of its owner, rank m >> lognloc (peer memory over NVLink).
-template <int P>
-__device__ __forceinline__ void load_block_from_peers(double* Xw, const PersistParams& p, unsigned n0, int lane) {
-  unsigned rem = n0;
-  long long gb = 0, ist = 1;
-  int dig_fast = 0;
-  bool inter = true;
-  const int d = p.d;
-  for (int j = d - 1; j >= 1; j--) {
-    int dig;
-    if (j == 1) {
-      dig = (int)rem;
-    } else {
-      dig = (int)(rem % P);
-      rem /= P;
-    }
-    if (j == d - 1) dig_fast = dig;
-    else inter = inter && dig >= 1 && dig <= P - 2;
-    gb += (long long)(dig - 1) * ist;
-    ist *= (P - 2);
-  }
-  const long long ist_a = ist;  // interior stride of axis 0
-  const int c = lane & 7;
-  const bool okc = inter && (dig_fast + c >= 1) && (dig_fast + c <= P - 2);
-#pragma unroll 4
-  for (int m = lane >> 3; m < P; m += 4) {
-    const bool ok = okc && m >= 1 && m <= P - 2;
-    const int q = m >> p.lognloc;
-    const double* src = p.Upeer[q] + (ok ? gb + c + (long long)(m - 1) * ist_a - p.goffq[q] : 0);
-    cp_async8(Xw + xaddr<P, false>(m, c), src, ok);
-  }
-  cp_async_commit();
-}
-
 }  // namespace sb200

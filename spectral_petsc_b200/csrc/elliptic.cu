@@ -218,10 +218,9 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
   }
   nw = 2 + d;  // elliptic.C:259
   const size_t mb = (size_t)gd.m * sizeof(double);
-  const size_t gmax = (size_t)(gd.m / gd.stride[0]) * gd.istride[0];  // upper bound of any rank's local Vec
   // every exchangeable array comes from one peer-mapped arena, in the same order on every rank
-  const int narr = nw + d + 2 + (nranks > 1 ? 3 : 0);
-  SB_TRY(arena.init((size_t)narr * (mb + 256) + (gmax * sizeof(double) + 256), rank, nranks));
+  const int narr = nw + d + 2 + (nranks > 1 ? 4 : 0);
+  SB_TRY(arena.init((size_t)narr * (mb + 256), rank, nranks));
   for (int k = 0; k < nw; k++) SB_CHECK((w[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   for (int k = 0; k < d; k++) {
     SB_CHECK((gradu[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
@@ -233,7 +232,7 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
     SB_CHECK((eta_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CHECK((deta_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CHECK((g0_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
-    SB_CHECK((Usym = arena.alloc_doubles(gmax)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((Wp = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   }
   SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
   SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));

@@ -58,7 +58,7 @@ struct EllipticCtx {
   SymmArena arena;
   int gdim[SB200_MAX_DIM] = {};     // global extents
   long long gtot = 0;               // global Vec length over all ranks
-  double* Usym = nullptr;           // staged copy of the input vector, readable by the peers
+  double* Wp = nullptr;             // axis-0 pencil [P][R0/G] of the padded input vector, pushed by all ranks
   double* eta_p = nullptr;          // axis-0 pencil copies of eta / deta / gradu[0] for the fused MatMult
   double* deta_p = nullptr;
   double* g0_p = nullptr;

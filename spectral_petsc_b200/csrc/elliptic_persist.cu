@@ -174,7 +174,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
 #pragma unroll
       for (int i = 0; i < E::MT; i++) {
         const int mt = i * 8 + g, mb = P - 1 - mt;
-        const int qt = mt >> p.lognloc, qb = mb >> p.lognloc;
+        const int qt = (p.xflags & 16) ? p.rank : mt >> p.lognloc, qb = (p.xflags & 16) ? p.rank : mb >> p.lognloc;
         st2(p.part0peer[qt] + (long long)(mt - qt * nloc) * p.R0 + col, a[j][i][0] + b[j][i][0], a[j][i][1] + b[j][i][1]);
         st2(p.part0peer[qb] + (long long)(mb - qb * nloc) * p.R0 + col, b[j][i][0] - a[j][i][0], b[j][i][1] - a[j][i][1]);
       }
@@ -194,7 +194,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     // last axis: phase A (all partials) must be complete and visible, then
     // V = crop(((0 - p_0) - p_1 ...) - D f)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (WAITDONE) {
+    if (WAITDONE && !(p.xflags & 8)) {
       if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_DONE + lane, p.epoch, p.sf.f[p.rank]);
       __syncwarp();
     }
@@ -280,6 +280,43 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   STAMP(5);
 }
 
+// Forward all-to-all of the slab partition, folded into the head of phase A: this CTA pads its share of
+// the local input vector (zero Dirichlet rows, elliptic.C:305-308) and pushes plane (i0 + ml), lines
+// [q*Rp, (q+1)*Rp) into rank q's pencil with 16-byte stores that are contiguous along the last axis.
+template <int P>
+__device__ __forceinline__ void stage_push_share(const PersistParams& p, int nwarps) {
+  const int d = p.d, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nloc = 1 << p.lognloc;
+  const long long lpp = p.R0 / P, nl = (long long)nloc * lpp;  // lines per plane, local lines
+  const long long per = (nl + gridDim.x - 1) / gridDim.x;
+  const long long l0 = (long long)blockIdx.x * per, l1 = l0 + per < nl ? l0 + per : nl;
+  for (long long line = l0 + warp; line < l1; line += nwarps) {
+    const int ml = (int)(line / lpp);
+    const long long lin = line - (long long)ml * lpp;
+    long long rem = lin, gid = 0, ist = P - 2;
+    bool inter = true;
+    for (int j = d - 2; j >= 1; j--) {
+      const int ij = (int)(rem % P);
+      rem /= P;
+      inter = inter && ij >= 1 && ij <= P - 2;
+      gid += (long long)(ij - 1) * ist;
+      ist *= (P - 2);
+    }
+    const int i0g = ml + p.sg.i0;
+    inter = inter && i0g >= 1 && i0g <= p.sg.n0g - 2;
+    gid += (long long)(i0g - 1) * ist - p.sg.goff;  // ist == istride[0] here
+    const long long n0 = lin * P;
+#pragma unroll
+    for (int k = 2 * lane; k < P; k += 64) {
+      const double v0 = (inter && k >= 1) ? p.U[gid + k - 1] : 0.0;
+      const double v1 = (inter && k + 1 <= P - 2) ? p.U[gid + k] : 0.0;
+      const long long n = n0 + k;
+      const int q = (int)(n / p.Rp);
+      st2(p.wppeer[q] + (long long)i0g * p.Rp + (n - (long long)q * p.Rp), v0, v1);
+    }
+  }
+}
+
 template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
 __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p) {
   using E = EO<P>;
@@ -292,12 +329,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   unsigned* sync = p.sync + (LASTPHASE ? 4 : 0);  // [0] ticket, [1] exited warps
 
   const unsigned items_per_axis = (unsigned)(p.nlines / (8 * NT));
-  // slab phase A: the axis-0 pencil items come first (their operands cross NVLink), then the local axes
+  // slab phase A: the local axes come first; the axis-0 pencil items follow once every rank's planes have
+  // arrived (tickets [nlocal, total))
   const unsigned items0 = (SLAB && !LASTPHASE) ? (unsigned)(p.Rp / (8 * NT)) : 0u;
-  const unsigned total = LASTPHASE ? items_per_axis : items0 + items_per_axis * (p.d - 1 - p.first_axis);
+  const unsigned nlocal = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1 - p.first_axis);
+  const unsigned total = nlocal + items0;
   if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   load_matrices<P>(sm, p.Ae, p.Bo);
+  if (SLAB && !LASTPHASE && !(p.xflags & 32)) {
+    stage_push_share<P>(p, NWARPS);
+    __syncthreads();  // the CTA's pushes happen-before thread 0's fence
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(sync + 3, 1u) == gridDim.x - 1) {
+        sync[3] = 0;
+        __threadfence_system();
+        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_READY + p.rank, p.epoch);
+      }
+    }
+  }
 
   auto grab = [&]() -> unsigned {
     unsigned tk = 0;
@@ -307,19 +358,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   bool peers_ready = false;
   auto issue_load = [&](unsigned tk) {
     if (tk >= total) return;
-    if (SLAB && !LASTPHASE && tk < items0) {
-      if (!peers_ready) {
-        // every rank's staged input vector must be complete before its planes are read
+    if (SLAB && !LASTPHASE && tk >= nlocal) {
+      if (!peers_ready && !(p.xflags & 4)) {
+        // every rank must have pushed its planes of the padded input into this rank's pencil
         if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_READY + lane, p.epoch, p.sf.f[p.rank]);
         __syncwarp();
         peers_ready = true;
       }
+      LineGeom lg;
+      lg.R = p.Rp;
+      lg.PR = (long long)P * p.Rp;
+      lg.nlines = p.Rp;
 #pragma unroll
       for (int j = 0; j < NT; j++)
-        load_block_from_peers<P>(Xw + j * E::BLOCK_ELEMS_LEFT, p, (unsigned)((long long)p.rank * p.Rp + (long long)tk * (8 * NT) + 8 * j), lane);
+        load_block<P, false>(Xw + j * E::BLOCK_ELEMS_LEFT, p.Wp, lg, (long long)(tk - nlocal) * (8 * NT) + 8 * j, lane);
       return;
     }
-    const unsigned tl = tk - items0;
+    const unsigned tl = tk;
     const int arel = LASTPHASE ? 0 : tl / items_per_axis;
     const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
     const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
@@ -339,11 +394,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     }
   }
 
+  unsigned pencil_done = 0;  // pencil items this warp has finished and not yet reported
+  auto report_pencils = [&]() {
+    // all pushes of this warp are out; the rank whose last pencil item this was raises DONE everywhere
+    __threadfence_system();
+    if (lane == 0) {
+      const unsigned before = atomicAdd(sync + 2, pencil_done);
+      if (before + pencil_done == items0) {
+        sync[2] = 0;
+        __threadfence_system();
+        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
+      }
+    }
+    pencil_done = 0;
+  };
   while (tk < total) {
-    if (SLAB && !LASTPHASE && tk < items0) {
-      run_item<P, NT, false, DEEP, true>(p, 0, (long long)tk * (8 * NT), Ae, Bo, Xw, lane);
+    if (SLAB && !LASTPHASE && tk >= nlocal) {
+      run_item<P, NT, false, DEEP, true>(p, 0, (long long)(tk - nlocal) * (8 * NT), Ae, Bo, Xw, lane);
+      pencil_done++;
     } else {
-      const unsigned tl = tk - items0;
+      const unsigned tl = tk;
       const int arel = LASTPHASE ? 0 : tl / items_per_axis;
       const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
       const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
@@ -353,18 +423,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     issue_load(tk);  // run_item waits for it at its top
   }
   cp_async_wait<0>();
-  if (SLAB && !LASTPHASE) __threadfence_system();  // this warp's pushes are out before it counts as gone
+  if (SLAB && !LASTPHASE && pencil_done) report_pencils();
   // the last warp to leave re-arms the counters for the next launch
   if (lane == 0) {
     const unsigned gone = atomicAdd(sync + 1, 1u);
     if (gone == gridDim.x * NWARPS - 1) {
       sync[0] = 0;
       sync[1] = 0;
-      if (SLAB && !LASTPHASE) {
-        // every axis-0 result of this rank has been pushed: tell all ranks (including this one)
-        __threadfence_system();
-        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
-      }
     }
   }
 }
@@ -382,6 +447,11 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
   if (items <= 0) return 0;
   long long grid = (items + NWARPS - 1) / NWARPS;
   if (grid > sms) grid = sms;  // one persistent CTA per SM
+  if (const char* mc = getenv("SB200_MAX_CTAS")) {
+    // test hook: several slab ranks emulated on ONE device must all be resident at the same time
+    const int lim = atoi(mc);
+    if (lim > 0 && grid > lim) grid = lim;
+  }
   if (grid < 1) grid = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);

@@ -1,12 +1,15 @@
 // Slab-partitioned MatMult_Elliptic (elliptic.C:297-339) over 2/4/8 GPUs: the grid is cut along its
 // outermost axis, one process per GPU.  Derivatives along the local axes never leave the GPU.  The
 // axis-0 chain  D_0 (eta D_0 w + eta' w g0)  runs on "pencils" (all P planes of 1/G of the lines):
-// the persistent chain kernel (elliptic_persist.cu) loads the operand planes straight from the owners'
-// staged input vectors over NVLink (the forward all-to-all is the operand load) and stores the result
-// rows straight into the owners' partial field (the backward all-to-all is the epilogue store).  Ranks
-// order themselves with two epoch flags in peer memory (READY: my input is staged; DONE: all my
-// results are pushed), never through the host.  Launches per application: stage+signal, phase A
-// (pencil items + local axes), phase B (last axis, waits for DONE).
+// the persistent chain kernel (elliptic_persist.cu) first pads its local input and pushes each plane's
+// lines into the owning rank's pencil with contiguous stores over NVLink (the forward all-to-all), runs
+// the local-axis items while those arrive, then the pencil items out of local memory, whose epilogue
+// stores the result rows straight into the plane owners' partial field (the backward all-to-all).  Ranks
+// order themselves with two epoch flags in peer memory (READY: my planes are in your pencil; DONE: all
+// my results are in your partial field), never through the host.  Two launches per application, as on
+// one GPU: phase A (push, local axes, pencil items), phase B (last axis; reads part[0] after DONE).
+#include <cstdlib>
+
 #include "../../include/spectral_b200.h"
 #include "common.cuh"
 #include "deriv.h"
@@ -16,22 +19,6 @@
 namespace sb200 {
 
 namespace {
-
-__global__ void stage_kernel(const double* __restrict__ U, double* __restrict__ Usym, long long n, unsigned* counter,
-                             SymmFlags sf, unsigned long long epoch) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) Usym[i] = U[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(counter, 1u);
-    if (done == gridDim.x - 1) {
-      *counter = 0;
-      __threadfence_system();
-      for (int q = 0; q < sf.nranks; q++) st_release_sys(sf.f[q] + SYMM_READY + sf.rank, epoch);
-    }
-  }
-}
 
 struct PeerPtrs {
   const double* x[SB200_MAX_RANKS];
@@ -105,14 +92,6 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   for (int q = 0; q < SB200_MAX_RANKS; q++) sf.f[q] = q < G ? e.arena.flags(q) : nullptr;
   sf.rank = e.arena.rank;
   sf.nranks = G;
-  {
-    long long blocks = (e.gd.g + 1023) / 1024;
-    if (blocks > 148) blocks = 148;
-    if (blocks < 1) blocks = 1;
-    stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(U, e.Usym, e.gd.g, e.sync + 8, sf, epoch);
-    count_launch();
-    SB_CUDA(cudaGetLastError());
-  }
   PersistParams p = {};
   p.Ae = e.Dax[0]->d_Ae;
   p.Bo = e.Dax[0]->d_Bo;
@@ -137,11 +116,10 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   const int nloc = P / G;
   p.lognloc = ilog2(nloc);
   for (int q = 0; q < G; q++) {
-    p.Upeer[q] = e.arena.on(q, e.Usym);
-    const int lo = q * nloc < 1 ? 1 : q * nloc;
-    p.goffq[q] = (long long)(lo - 1) * e.gd.istride[0];
     p.part0peer[q] = e.arena.on(q, e.w[1]);
+    p.wppeer[q] = e.arena.on(q, e.Wp);
   }
+  p.Wp = e.Wp;
   p.eta_p = e.eta_p;
   p.deta_p = e.deta_p;
   p.g0_p = e.g0_p;

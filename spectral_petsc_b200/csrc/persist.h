@@ -32,8 +32,8 @@ struct PersistParams {
   int first_axis;    // phase A runs axes first_axis..d-2 (0; 1 in slab mode where axis 0 is exchanged)
   // ---- slab mode (nranks > 1): axis 0 runs on "pencils" (all P planes of R0/nranks lines) --------
   int nranks, rank, lognloc;            // nloc = P / nranks = 1 << lognloc planes per rank
-  const double* Upeer[SB200_MAX_RANKS]; // staged input vector of every rank (peer memory)
-  long long goffq[SB200_MAX_RANKS];     // global id of the first interior node stored by rank q
+  const double* Wp;                     // this rank's pencil [P][Rp] of the padded input, pushed by all ranks
+  double* wppeer[SB200_MAX_RANKS];      // Wp of every rank (forward all-to-all: planes are pushed at kernel start)
   double* part0peer[SB200_MAX_RANKS];   // part[0] (slab layout) of every rank: axis-0 results are pushed
   const double* eta_p;                  // pencil-layout copies [P][Rp] of eta / deta / gradu[0]
   const double* deta_p;

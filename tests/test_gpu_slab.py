@@ -18,6 +18,17 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
+@pytest.fixture(autouse=True)
+def small_persistent_grids():
+    """All emulated ranks share one device and wait for each other on it, so every rank's persistent
+    kernels (two phases each) must be resident together: cap their grids."""
+    import os
+
+    os.environ["SB200_MAX_CTAS"] = "12"
+    yield
+    del os.environ["SB200_MAX_CTAS"]
+
+
 class Ranks:
     """nranks slab contexts on one device, one stream each."""
 
@@ -105,6 +116,7 @@ def test_slab_fused_matches_single_gpu_and_oracle(cuda, dim, nranks):
     assert rel_max(V, Vo) < TOL
     V2 = run_matmult(O, R, U)  # flags / counters re-armed
     assert np.array_equal(V, V2)
+    assert all(c.slab_timeouts() == 0 for c in R.ctx)
     # generic slab path on the same state
     for c in R.ctx:
         c.set_path(1)
