@@ -109,6 +109,9 @@ int sb200_ipc_handle_bytes(void);
 int sb200_elliptic_ipc_export(sb200_elliptic* e, void* handle);
 int sb200_elliptic_ipc_attach(sb200_elliptic* e, int peer_rank, const void* handle);
 int sb200_elliptic_attach_local(sb200_elliptic* e, int peer_rank, sb200_elliptic* peer);
+/* Debug: global-timer stamps (ns; 10 (min,max) pairs) of the slab step's milestones, recorded when the
+ * environment has SB200_XFLAGS bit 64; reading re-arms them.  See tools/slab_timeline.py. */
+int sb200_elliptic_debug_timeline(sb200_elliptic* e, unsigned long long* h_out20, void* stream);
 /* MatDestroy_Elliptic (elliptic.C:343-368). */
 int sb200_elliptic_destroy(sb200_elliptic* e);
 

@@ -344,6 +344,20 @@ int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf) {
   return 0;
 }
 
+int sb200_elliptic_debug_timeline(sb200_elliptic* e, unsigned long long* h_out20, void* stream) {
+  // slots (min,max) x 10 written by the slab kernels when SB200_XFLAGS has bit 64; read and re-armed here
+  SB_CHECK(e && h_out20, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(e->c->sync, SB200_ERR_USER, "no persistent launch yet");
+  unsigned long long* ts = reinterpret_cast<unsigned long long*>(e->c->sync) + 16;
+  SB_CUDA(cudaMemcpyAsync(h_out20, ts, 20 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  unsigned long long init[20];
+  for (int i = 0; i < 20; i++) init[i] = (i & 1) ? 0ull : ~0ull;
+  SB_CUDA(cudaMemcpyAsync(ts, init, sizeof(init), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  SB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 int sb200_elliptic_destroy(sb200_elliptic* e) {
   if (!e) return 0;
   delete e->c;

@@ -28,6 +28,21 @@ namespace sb200 {
 
 namespace {
 
+// Debug timeline (xflags & 64): global-timer stamps of the slab step's milestones, kept behind the
+// counters in the sync block ((unsigned long long*)sync + 16 ...): even slots take a minimum, odd a maximum.
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_stamp(const PersistParams& p, int slot) {
+  if (!(p.xflags & 64) || p.epoch != p.tl_epoch) return;
+  unsigned long long* ts = reinterpret_cast<unsigned long long*>(p.sync) + 16;
+  const unsigned long long t = gtime();
+  atomicMin(ts + 2 * slot, t);
+  atomicMax(ts + 2 * slot + 1, t);
+}
+
 
 template <int P, int NT, bool RIGHT>
 __device__ __forceinline__ void load_item(double* Xw, const double* __restrict__ U, int d, int axis,
@@ -195,8 +210,10 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     // V = crop(((0 - p_0) - p_1 ...) - D f)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (WAITDONE && !(p.xflags & 8)) {
+      if (lane == 0) tl_stamp(p, 6);
       if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_DONE + lane, p.epoch, p.sf.f[p.rank]);
       __syncwarp();
+      if (lane == 0) tl_stamp(p, 7);
     }
 #pragma unroll
     for (int j = 0; j < NT; j++) {
@@ -284,35 +301,72 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
 // the local input vector (zero Dirichlet rows, elliptic.C:305-308) and pushes plane (i0 + ml), lines
 // [q*Rp, (q+1)*Rp) into rank q's pencil with 16-byte stores that are contiguous along the last axis.
 template <int P>
-__device__ __forceinline__ void stage_push_share(const PersistParams& p, int nwarps) {
-  const int d = p.d, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nloc = 1 << p.lognloc;
-  const long long lpp = p.R0 / P, nl = (long long)nloc * lpp;  // lines per plane, local lines
-  const long long per = (nl + gridDim.x - 1) / gridDim.x;
-  const long long l0 = (long long)blockIdx.x * per, l1 = l0 + per < nl ? l0 + per : nl;
-  for (long long line = l0 + warp; line < l1; line += nwarps) {
-    const int ml = (int)(line / lpp);
-    const long long lin = line - (long long)ml * lpp;
-    long long rem = lin, gid = 0, ist = P - 2;
-    bool inter = true;
-    for (int j = d - 2; j >= 1; j--) {
-      const int ij = (int)(rem % P);
-      rem /= P;
-      inter = inter && ij >= 1 && ij <= P - 2;
-      gid += (long long)(ij - 1) * ist;
-      ist *= (P - 2);
-    }
-    const int i0g = ml + p.sg.i0;
-    inter = inter && i0g >= 1 && i0g <= p.sg.n0g - 2;
-    gid += (long long)(i0g - 1) * ist - p.sg.goff;  // ist == istride[0] here
-    const long long n0 = lin * P;
+__device__ __forceinline__ void stage_push_share(const PersistParams& p, int warp, int nwarps) {
+  constexpr int LB = 4;        // lines in flight per warp: all their loads are issued before the first store
+  constexpr int IT = (P + 63) / 64;  // 16-byte chunks per lane and line
+  const int d = p.d, lane = threadIdx.x & 31;
+  const unsigned nloc = 1u << p.lognloc;
+  const unsigned lpp = (unsigned)(p.R0 / P), nl = nloc * lpp;  // lines per plane, local lines
+  const unsigned per = (nl + gridDim.x - 1) / gridDim.x;
+  const unsigned l0 = blockIdx.x * per, l1 = l0 + per < nl ? l0 + per : nl;
+  const unsigned Rp = (unsigned)p.Rp;
+  const double* __restrict__ U = p.U;
+  for (unsigned base = l0 + warp * LB; base < l1; base += nwarps * LB) {
+    double v[LB][IT][2];
+    double* dst[LB][IT];
 #pragma unroll
-    for (int k = 2 * lane; k < P; k += 64) {
-      const double v0 = (inter && k >= 1) ? p.U[gid + k - 1] : 0.0;
-      const double v1 = (inter && k + 1 <= P - 2) ? p.U[gid + k] : 0.0;
-      const long long n = n0 + k;
-      const int q = (int)(n / p.Rp);
-      st2(p.wppeer[q] + (long long)i0g * p.Rp + (n - (long long)q * p.Rp), v0, v1);
+    for (int b = 0; b < LB; b++) {
+      const unsigned line = base + b;
+      const bool live = line < l1;
+      const unsigned ml = line / lpp, lin = line - ml * lpp;
+      unsigned rem = lin;
+      long long gid = 0, ist = P - 2;
+      bool inter = live;
+      for (int j = d - 2; j >= 1; j--) {
+        const int ij = (int)(rem % P);
+        rem /= P;
+        inter = inter && ij >= 1 && ij <= P - 2;
+        gid += (long long)(ij - 1) * ist;
+        ist *= (P - 2);
+      }
+      const int i0g = (int)ml + p.sg.i0;
+      inter = inter && i0g >= 1 && i0g <= p.sg.n0g - 2;
+      gid += (long long)(i0g - 1) * ist - p.sg.goff;  // ist == istride[0] here
+#pragma unroll
+      for (int it = 0; it < IT; it++) {
+        const int k = 2 * lane + 64 * it;
+        v[b][it][0] = (inter && k >= 1 && k <= P - 2) ? U[gid + k - 1] : 0.0;
+        v[b][it][1] = (inter && k + 1 <= P - 2) ? U[gid + k] : 0.0;
+        const unsigned n = lin * P + k, q = n / Rp;
+        dst[b][it] = (live && k < P) ? p.wppeer[q] + (long long)i0g * Rp + (n - q * Rp) : nullptr;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < LB; b++)
+#pragma unroll
+      for (int it = 0; it < IT; it++)
+        if (dst[b][it]) st2(dst[b][it], v[b][it][0], v[b][it][1]);
+  }
+}
+
+// The forward all-to-all as its own small kernel (no shared memory, so its CTAs share the SMs with phase A,
+// which is launched as a programmatic dependent and runs the local-axis items while the planes cross
+// NVLink).  The last block to finish raises READY on every rank.
+// Blocks are small (128 threads, <= 80 registers) because phase A's CTA already takes ~53K of the SM's 64K
+// registers: only then do the two kernels really share an SM.
+template <int P>
+__global__ void __launch_bounds__(128, 6) stage_kernel(PersistParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  stage_push_share<P>(p, threadIdx.x >> 5, blockDim.x >> 5);
+  if (threadIdx.x == 0) tl_stamp(p, 1);
+  __syncthreads();  // the block's pushes happen-before thread 0's fence
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    tl_stamp(p, 2);
+    if (atomicAdd(p.sync + 3, 1u) == gridDim.x - 1) {
+      p.sync[3] = 0;
+      __threadfence_system();
+      for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_READY + p.rank, p.epoch);
     }
   }
 }
@@ -337,18 +391,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   load_matrices<P>(sm, p.Ae, p.Bo);
-  if (SLAB && !LASTPHASE && !(p.xflags & 32)) {
-    stage_push_share<P>(p, NWARPS);
-    __syncthreads();  // the CTA's pushes happen-before thread 0's fence
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      if (atomicAdd(sync + 3, 1u) == gridDim.x - 1) {
-        sync[3] = 0;
-        __threadfence_system();
-        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_READY + p.rank, p.epoch);
-      }
-    }
-  }
+  if (SLAB && threadIdx.x == 0) tl_stamp(p, LASTPHASE ? 5 : 0);
 
   auto grab = [&]() -> unsigned {
     unsigned tk = 0;
@@ -363,6 +406,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
         // every rank must have pushed its planes of the padded input into this rank's pencil
         if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_READY + lane, p.epoch, p.sf.f[p.rank]);
         __syncwarp();
+        if (lane == 0) tl_stamp(p, 3);
         peers_ready = true;
       }
       LineGeom lg;
@@ -384,10 +428,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   constexpr bool DEEP = (NWARPS * NT <= 8);  // 255 registers available
   // De-phase the warps of each SM sub-partition (warp w runs on SMSP w % 4): identical items started
   // together stay in lockstep, which serialises the tensor phases against the memory phases.
-  unsigned tk = grab();
-  issue_load(tk);
-  cp_async_wait<0>();
-  __syncthreads();  // matrices visible to all warps (the only CTA-wide barrier)
+  unsigned tk = 0;
+  if (SLAB && !LASTPHASE) {
+    // a first ticket may be a pencil item that waits for the peers: never hold the CTA barrier behind it
+    cp_async_wait<0>();
+    __syncthreads();
+    tk = grab();
+    issue_load(tk);
+  } else {
+    tk = grab();
+    issue_load(tk);
+    cp_async_wait<0>();
+    __syncthreads();  // matrices visible to all warps (the only CTA-wide barrier)
+  }
   if (p.stagger > 0) {
     const long long until = clock64() + (long long)(warp / 4) * p.stagger;
     while (clock64() < until) {
@@ -401,6 +454,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     if (lane == 0) {
       const unsigned before = atomicAdd(sync + 2, pencil_done);
       if (before + pencil_done == items0) {
+        tl_stamp(p, 4);
         sync[2] = 0;
         __threadfence_system();
         for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
@@ -430,6 +484,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     if (gone == gridDim.x * NWARPS - 1) {
       sync[0] = 0;
       sync[1] = 0;
+      if (SLAB) tl_stamp(p, LASTPHASE ? 9 : 8);
     }
   }
 }
@@ -462,7 +517,8 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = LASTPHASE ? 1 : 0;  // phase B may start while phase A drains
+  // phase B may start while phase A drains; slab phase A may start while the stage kernel pushes
+  cfg.numAttrs = (LASTPHASE || SLAB) ? 1 : 0;
   SB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
   return 0;
@@ -477,6 +533,13 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (p.nranks > 1) {
+    if (!(p.xflags & 32)) {
+      int blocks = sms;
+      if (const char* mc = getenv("SB200_MAX_CTAS")) blocks = atoi(mc) > 0 ? atoi(mc) : blocks;
+      stage_kernel<P><<<blocks, 128, 0, s>>>(p);
+      count_launch();
+      SB_CUDA(cudaGetLastError());
+    }
     SB_TRY((launch_phase<P, NWARPS, NT, false, true>(p, smem, sms, s)));
     SB_TRY((launch_phase<P, NWARPS, NT, true, true>(p, smem, sms, s)));
     return 0;
@@ -527,8 +590,8 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
 int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s) {
   const int P = e.gd.dim[0], d = e.gd.d;
   if (!e.sync) {
-    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
-    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
+    SB_CUDA(cudaMalloc((void**)&e.sync, 512));
+    SB_CUDA(cudaMemsetAsync(e.sync, 0, 512, s));
   }
   PersistParams p = {};
   p.Ae = e.Dax[0]->d_Ae;

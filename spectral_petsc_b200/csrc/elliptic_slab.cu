@@ -83,8 +83,8 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   SB_CHECK(e.arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
   const int P = e.gdim[0], d = e.gd.d, G = e.arena.nranks;
   if (!e.sync) {
-    SB_CUDA(cudaMalloc((void**)&e.sync, 64));
-    SB_CUDA(cudaMemsetAsync(e.sync, 0, 64, s));
+    SB_CUDA(cudaMalloc((void**)&e.sync, 512));
+    SB_CUDA(cudaMemsetAsync(e.sync, 0, 512, s));
   }
   if (!e.pencil_valid) SB_TRY(e.refresh_pencils(s));
   const unsigned long long epoch = ++e.mm_epoch;
@@ -127,6 +127,14 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   p.Rp = p.R0 / G;
   p.sf = sf;
   p.epoch = epoch;
+  {
+    static long long tl = -1;
+    if (tl < 0) {
+      const char* c = getenv("SB200_TL_EPOCH");
+      tl = c ? atoll(c) : 0;
+    }
+    p.tl_epoch = (unsigned long long)tl;
+  }
   p.trace = nullptr;
   return persist_run(P, p, s);
 }

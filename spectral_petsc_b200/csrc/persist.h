@@ -41,6 +41,7 @@ struct PersistParams {
   long long R0, Rp;                     // lines per plane; lines per pencil (R0 / nranks)
   SymmFlags sf;
   unsigned long long epoch;             // READY / DONE flag value of this application
+  unsigned long long tl_epoch;          // debug timeline: the application to stamp (SB200_TL_EPOCH)
   int stagger;       // start delay per warp group, in clocks
   int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
   long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
