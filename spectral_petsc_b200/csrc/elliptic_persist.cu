@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128, 6) stage_kernel(PersistParams p) {
     if (atomicAdd(p.sync + 3, 1u) == gridDim.x - 1) {
       p.sync[3] = 0;
       __threadfence_system();
-      for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_READY + p.rank, p.epoch);
+      for (int q = 0; q < p.nranks; q++) st_relaxed_sys(p.sf.f[q] + SYMM_READY + p.rank, p.epoch);
     }
   }
 }
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
         tl_stamp(p, 4);
         sync[2] = 0;
         __threadfence_system();
-        for (int q = 0; q < p.nranks; q++) st_release_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
+        for (int q = 0; q < p.nranks; q++) st_relaxed_sys(p.sf.f[q] + SYMM_DONE + p.rank, p.epoch);
       }
     }
     pencil_done = 0;
@@ -500,8 +500,9 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
   long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
   if (SLAB && !LASTPHASE) items += p.Rp / (8 * NT);
   if (items <= 0) return 0;
-  long long grid = (items + NWARPS - 1) / NWARPS;
-  if (grid > sms) grid = sms;  // one persistent CTA per SM
+  // one persistent CTA per SM; with fewer items than warps spread them over all SMs (a warp alone on its
+  // SM sub-partition issues DMMAs ~1.5x faster than two sharing it)
+  long long grid = items < sms ? items : sms;
   if (const char* mc = getenv("SB200_MAX_CTAS")) {
     // test hook: several slab ranks emulated on ONE device must all be resident at the same time
     const int lim = atoi(mc);

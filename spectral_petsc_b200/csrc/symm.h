@@ -62,6 +62,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Flag store without its own fence: issue ONE __threadfence_system() and then publish to every peer with
+// these (a st.release.sys per peer costs a full system-scope fence each, ~2 us, and they serialise).
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Bounded spin on an epoch flag: a rank that never shows up (mismatched collective calls, a dead peer)
 // must not hang the GPU.  After ~4 s the wait gives up and records the failure in the flag block's
 // SYMM_TIMEOUT word (sb200_*_slab_status reports it); results are then undefined but the kernel exits.
