@@ -98,6 +98,9 @@ int sb200_elliptic_debug_trace(sb200_elliptic* e, long long* d_buf);
  * read / write the peers' memory directly over NVLink; all collective entry points (matmult, function) must be
  * called by every rank in the same order.  dim[0] must be divisible by nranks (<= 8). */
 int sb200_elliptic_create_slab(int d, const int* dim, int rank, int nranks, sb200_elliptic** out);
+/* The partition arithmetic alone (host only, no device needed): planes [i0, i0+nloc), Vec range [goff, goff+g_local). */
+int sb200_slab_geometry(int d, const int* dim, int rank, int nranks, int* i0, int* nloc, long long* goff, long long* g_local,
+                        long long* m_local, long long* nd_local);
 int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, int* i0, int* nloc, long long* goff, long long* gtotal);
 /* Synchronises the stream and reports how many device-side waits on a peer's flag gave up (~4 s each):
  * non-zero means the ranks did not make the same sequence of collective calls (or a peer died). */
@@ -153,6 +156,34 @@ int sb200_stokes_get_state(sb200_stokes* s, int which, double* d_out, void* stre
 int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stream);
 /* StokesDestroy (stokes.C:348-388). */
 int sb200_stokes_destroy(sb200_stokes* s);
+
+/* ---- KSP: device-resident FGMRES(m), the solver the reference selects in code and the direct caller of the
+ * MatShells (KSPSetType(ksp, KSPFGMRES): elliptic.C:181-182, stokes.C:155-157; inner KSPs stokes.C:328-341).
+ * PETSc's algorithm restated: right-preconditioned flexible Arnoldi, classical Gram-Schmidt, KSPConvergedDefault.
+ * Operator and preconditioner are callbacks on DEVICE vectors (MatMult / PCApply); pc may be NULL (PCNONE).  The
+ * PC itself (ILU / hypre / LU on the finite-difference matrix) stays PETSc's and is out of scope. */
+typedef struct sb200_ksp sb200_ksp;
+typedef int (*sb200_apply_fn)(void* ctx, const double* d_x, double* d_y, void* stream);
+int sb200_ksp_create(long long n, int restart, sb200_ksp** out);                 /* KSPCreate + KSPGMRESSetRestart (default 30) */
+/* vectors are slab-partitioned: n_local values here, dot products summed over the ranks through peer memory */
+int sb200_ksp_create_slab(long long n_local, int restart, int rank, int nranks, sb200_ksp** out);
+int sb200_ksp_set_operators(sb200_ksp* k, sb200_apply_fn op, void* op_ctx, sb200_apply_fn pc, void* pc_ctx); /* KSPSetOperators / PCShell */
+int sb200_ksp_set_tolerances(sb200_ksp* k, double rtol, double atol, double dtol, int maxits);                 /* KSPSetTolerances */
+/* KSPSolve(ksp, b, x); guess_nonzero = KSPSetInitialGuessNonzero.  Synchronises the stream once per iteration. */
+int sb200_ksp_solve(sb200_ksp* k, const double* d_b, double* d_x, int guess_nonzero, void* stream);
+/* KSPGetIterationNumber / KSPGetResidualNorm / KSPGetConvergedReason (PETSc's reason codes: 2 rtol, 3 atol, -3 its, -4 dtol). */
+int sb200_ksp_get_result(const sb200_ksp* k, int* its, double* rnorm, double* bnorm, int* reason);
+int sb200_ksp_get_history(const sb200_ksp* k, double* h_hist, int cap, int* n);   /* KSPGetResidualHistory */
+/* CUDA-event times of the last solve, split the way the north star asks: operator / PC ("timed separately") / KSP vector work. */
+int sb200_ksp_get_times(const sb200_ksp* k, double* ms_operator, double* ms_pc, double* ms_orthogonalisation);
+int sb200_ksp_ipc_export(sb200_ksp* k, void* handle);
+int sb200_ksp_ipc_attach(sb200_ksp* k, int peer_rank, const void* handle);
+int sb200_ksp_attach_local(sb200_ksp* k, int peer_rank, sb200_ksp* peer);
+int sb200_ksp_destroy(sb200_ksp* k);
+/* The MatShell MULT operations in sb200_apply_fn form (ctx = the operator context). */
+int sb200_apply_elliptic_matmult(void* ctx, const double* d_x, double* d_y, void* stream);
+int sb200_apply_stokes_matmult(void* ctx, const double* d_x, double* d_y, void* stream);
+int sb200_apply_stokes_matmult_vv(void* ctx, const double* d_x, double* d_y, void* stream);
 
 #ifdef __cplusplus
 }

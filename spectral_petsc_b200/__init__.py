@@ -14,7 +14,8 @@ from .capi import (  # noqa: F401
     Cheb,
     Elliptic,
     Stokes,
+    KSP,
     cheb_matrix,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "cheb_matrix"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix"]

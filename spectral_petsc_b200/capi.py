@@ -352,6 +352,109 @@ class Stokes:
             pass
 
 
+_APPLY = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+
+class KSP:
+    """KSPCreate + KSPSetType(KSPFGMRES) (elliptic.C:181-182, stokes.C:155-157): device-resident FGMRES(restart).
+
+    The operator is a MatShell context of this package (Elliptic / Stokes: its MULT runs natively, no Python in
+    the iteration) or a Python callable on torch tensors; the preconditioner is a Python callable (the PC stays
+    outside this package, e.g. a host LU of the finite-difference matrix) or None."""
+
+    def __init__(self, n, restart=30, rank=0, nranks=1):
+        self._h = ctypes.c_void_p()
+        _ck(lib().sb200_ksp_create_slab(ctypes.c_longlong(n), ctypes.c_int(restart), ctypes.c_int(rank), ctypes.c_int(nranks), ctypes.byref(self._h)))
+        self.n, self.rank, self.nranks = n, rank, nranks
+        self._keep = []
+
+    def _as_fn(self, f):
+        n = self.n
+
+        def cb(_ctx, d_x, d_y, _stream):
+            try:
+                y = _wrap(d_y, n)
+                y.copy_(f(_wrap(d_x, n)))
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        c = _APPLY(cb)
+        self._keep.append(c)
+        return c, None
+
+    def set_operators(self, op, pc=None, stokes_block=None):
+        L = lib()
+        if isinstance(op, Elliptic):
+            fn, ctx = ctypes.cast(L.sb200_apply_elliptic_matmult, ctypes.c_void_p), op._h
+        elif isinstance(op, Stokes):
+            name = "sb200_apply_stokes_matmult_vv" if stokes_block == "vv" else "sb200_apply_stokes_matmult"
+            fn, ctx = ctypes.cast(getattr(L, name), ctypes.c_void_p), op._h
+        else:
+            fn, ctx = self._as_fn(op)
+        self._keep.append(op)
+        pfn, pctx = (None, None) if pc is None else self._as_fn(pc)
+        _ck(L.sb200_ksp_set_operators(self._h, fn, ctx, pfn, pctx))
+
+    def set_tolerances(self, rtol=1e-5, atol=1e-50, dtol=1e5, maxits=10000):
+        _ck(lib().sb200_ksp_set_tolerances(self._h, ctypes.c_double(rtol), ctypes.c_double(atol), ctypes.c_double(dtol), ctypes.c_int(maxits)))
+
+    def solve(self, b, x=None, guess_nonzero=False):
+        import torch
+
+        if x is None:
+            x = torch.zeros_like(b)
+        assert b.numel() == self.n and x.numel() == self.n
+        _ck(lib().sb200_ksp_solve(self._h, _ptr(b), _ptr(x), ctypes.c_int(int(guess_nonzero)), _stream()))
+        return x
+
+    @property
+    def result(self):
+        its, reason = ctypes.c_int(), ctypes.c_int()
+        rn, bn = ctypes.c_double(), ctypes.c_double()
+        _ck(lib().sb200_ksp_get_result(self._h, ctypes.byref(its), ctypes.byref(rn), ctypes.byref(bn), ctypes.byref(reason)))
+        return {"its": its.value, "rnorm": rn.value, "bnorm": bn.value, "reason": reason.value}
+
+    @property
+    def history(self):
+        n = ctypes.c_int()
+        _ck(lib().sb200_ksp_get_history(self._h, None, 0, ctypes.byref(n)))
+        buf = np.empty(max(n.value, 1))
+        _ck(lib().sb200_ksp_get_history(self._h, _hptr(buf), ctypes.c_int(n.value), ctypes.byref(n)))
+        return buf[:n.value]
+
+    @property
+    def times_ms(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        _ck(lib().sb200_ksp_get_times(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"operator": a.value, "pc": b.value, "ksp_vector_work": c.value}
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(lib().sb200_ipc_handle_bytes())
+        _ck(lib().sb200_ksp_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, peer_rank, handle):
+        _ck(lib().sb200_ksp_ipc_attach(self._h, ctypes.c_int(peer_rank), ctypes.c_char_p(handle)))
+
+    def attach_local(self, peer_rank, peer):
+        _ck(lib().sb200_ksp_attach_local(self._h, ctypes.c_int(peer_rank), peer._h))
+
+    def destroy(self):
+        if self._h:
+            _ck(lib().sb200_ksp_destroy(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 def _wrap(ptr, n):
     """View n doubles of device memory owned by the library as a torch tensor (no copy)."""
     import torch

@@ -223,6 +223,22 @@ int sb200_elliptic_slab_status(sb200_elliptic* e, long long* timeouts, void* str
   return 0;
 }
 
+int sb200_slab_geometry(int d, const int* dim, int rank, int nranks, int* i0, int* nloc, long long* goff, long long* g_local,
+                        long long* m_local, long long* nd_local) {
+  SB_CHECK(dim, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(nranks >= 1 && nranks <= SB200_MAX_RANKS && rank >= 0 && rank < nranks, SB200_ERR_USER,
+           "slab partition: rank / nranks out of range (at most 8 ranks)");
+  GridDesc gd;
+  SB_TRY(gd.init_slab(d, dim, rank, nranks));
+  if (i0) *i0 = gd.i0;
+  if (nloc) *nloc = gd.dim[0];
+  if (goff) *goff = gd.goff;
+  if (g_local) *g_local = gd.g;
+  if (m_local) *m_local = gd.m;
+  if (nd_local) *nd_local = gd.m - gd.g;
+  return 0;
+}
+
 int sb200_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
 int sb200_elliptic_ipc_export(sb200_elliptic* e, void* handle) {

@@ -20,7 +20,8 @@ enum SymmFlag {
   SYMM_READY = 8,   // [8..15]  fused MatMult: peer q's staged input vector is ready
   SYMM_DONE = 16,   // [16..23] fused MatMult: peer q has pushed all its axis-0 results
   SYMM_TIMEOUT = 24,  // number of flag waits that gave up (0 in a healthy run)
-  SYMM_NFLAGS = 32,
+  SYMM_AR = 32,       // [32..39] small all-reduce (KSP dot products): peer q's contribution is in my slot q
+  SYMM_NFLAGS = 48,
 };
 
 struct SymmArena {

@@ -53,22 +53,46 @@ def attach_in_process(ctxs):
                 a.attach_local(q, b)
 
 
+def exchange_handles(handle, group=None):
+    """All-gather one fixed-size bytes object per rank (the 64-byte CUDA IPC handles); works on gloo and nccl."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda()
+    handles = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(handles, mine, group=group)
+    return [bytes(h.cpu().numpy().tobytes()) for h in handles]
+
+
 def attach_peers(ctx, group=None):
     """One process per GPU: all-gather the CUDA IPC handles and map every peer's arena."""
-    import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world != ctx.nranks or rank != ctx.rank:
         raise ValueError("context partition does not match the process group")
-    mine = torch.frombuffer(bytearray(ctx.ipc_export()), dtype=torch.uint8)
-    backend = dist.get_backend(group)
-    if backend == "nccl":
-        mine = mine.cuda()
-    handles = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(handles, mine, group=group)
-    for q, h in enumerate(handles):
+    for q, h in enumerate(exchange_handles(ctx.ipc_export(), group)):
         if q != rank:
-            ctx.ipc_attach(q, bytes(h.cpu().numpy().tobytes()))
+            ctx.ipc_attach(q, h)
     dist.barrier(group)
+
+
+def gather_global(local, group=None):
+    """Reassemble the global Vec from the ranks' local parts (test / benchmark helper, not on the data path)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    nmax = int(max(int(s.item()) for s in sizes))
+    buf = torch.zeros(nmax, dtype=local.dtype, device=local.device)
+    buf[:local.numel()] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:int(s.item())] for p, s in zip(parts, sizes)])
