@@ -175,6 +175,57 @@ def run_reference(args):
     return 0
 
 
+def ksp_secondary(sp, torch, dev, G128, U128):
+    """Secondary metric of BASELINE.json: 'KSP time to rtol 1e-10'.
+    (a) config 1, ./elliptic -dim 16,16,16 -exact 2 -ksp_rtol 1e-10: device FGMRES(30) on the MatShell with a host LU of
+        the finite-difference matrix as the PC stand-in (PETSc's PC is out of scope and timed separately);
+    (b) 128^3: one full FGMRES(30) cycle (30 iterations, no PC) on the benchmark operator: operator time vs KSP vector work."""
+    import scipy.sparse.linalg as spla
+
+    from oracle.elliptic import MatElliptic  # checker-side input only: exact solution, FD matrix for the stand-in PC
+
+    out = {}
+    dim = [16, 16, 16]
+    O = MatElliptic(dim, gamma=0.0)
+    u, _ = O.create_exact_solution(2)
+    O.form_function(np.zeros(O.g))
+    lu = spla.splu(O.form_jacobian_matrix().tocsc())
+    G = sp.Elliptic(dim, gamma=0.0)
+    G.set_dirichlet(torch.from_numpy(O.dirichlet).to(dev))
+    G.set_rhs(torch.from_numpy(O.b).to(dev))
+    F = G.form_function(torch.zeros(G.g, dtype=torch.float64, device=dev))
+    K = sp.KSP(G.g)
+    K.set_operators(G, pc=lambda r: torch.from_numpy(lu.solve(r.cpu().numpy())).to(dev))
+    K.set_tolerances(rtol=1e-10)
+    rhs = -F
+    K.solve(rhs)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dx = K.solve(rhs)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    r, t = K.result, K.times_ms
+    out["config1_elliptic16_exact2"] = {"ksp_rtol": 1e-10, "iterations": r["its"], "reason": r["reason"], "time_ms_total": wall,
+                                        "time_ms_operator": t["operator"], "time_ms_pc_host_lu_standin": t["pc"], "time_ms_ksp_vector_work": t["ksp_vector_work"],
+                                        "time_ms_without_pc": wall - t["pc"], "norm_of_error": float((dx.cpu() - torch.from_numpy(u)).abs().max())}
+    K.destroy()
+    G.destroy()
+    K = sp.KSP(G128.g)
+    K.set_operators(G128)
+    K.set_tolerances(rtol=1e-30, maxits=30)
+    K.solve(U128)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    K.solve(U128)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    r, t = K.result, K.times_ms
+    out["fgmres30_cycle_128"] = {"iterations": r["its"], "time_ms_total": wall, "time_ms_operator": t["operator"], "time_ms_ksp_vector_work": t["ksp_vector_work"],
+                                 "ms_per_iteration": wall / max(r["its"], 1), "residual_reduction": r["rnorm"] / r["bnorm"]}
+    K.destroy()
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -291,6 +342,8 @@ def run_cuda(args):
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_ksp:
+            line["ksp"] = ksp_secondary(sp, torch, dev, G, U)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -305,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--path", type=int, default=None, help="kernel path override (1 generic, 2 fused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ksp", action="store_true", help="skip the secondary 'KSP time to rtol 1e-10' measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -154,6 +154,16 @@ int sb200_stokes_eta_minmax(sb200_stokes* s, double* h_min, double* h_max, void*
 int sb200_stokes_get_state(sb200_stokes* s, int which, double* d_out, void* stream);
 /* StokesPressureReduceOrder (stokes.C:1029-1080) applied in place to a local pressure array of m doubles. */
 int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stream);
+/* Slab partition of the Stokes shells over the GPUs of one node (see sb200_elliptic_create_slab): rank r keeps the planes
+ * [r*dim[0]/nranks, ...) of every local field and the matching contiguous range of the global Vec (AoS [v,p] per interior
+ * node: (d+1)*goff_nodes values precede it).  All sizes reported by sb200_stokes_sizes are then LOCAL.  Axis-0 derivatives
+ * pull their operand planes from the owners over NVLink; the axis-0 pass of the pressure extrapolation is a rank-ordered sum. */
+int sb200_stokes_create_slab(int d, const int* dim, int rank, int nranks, sb200_stokes** out);
+int sb200_stokes_slab_info(const sb200_stokes* s, int* rank, int* nranks, int* i0, int* nloc, long long* goff_nodes);
+int sb200_stokes_ipc_export(sb200_stokes* s, void* handle);
+int sb200_stokes_ipc_attach(sb200_stokes* s, int peer_rank, const void* handle);
+int sb200_stokes_attach_local(sb200_stokes* s, int peer_rank, sb200_stokes* peer);
+int sb200_stokes_slab_status(sb200_stokes* s, long long* timeouts, void* stream);
 /* StokesDestroy (stokes.C:348-388). */
 int sb200_stokes_destroy(sb200_stokes* s);
 

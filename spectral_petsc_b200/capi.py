@@ -236,16 +236,40 @@ _VSOLVE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctype
 class Stokes:
     """StokesCreate + the StokesMatMult{,VV,PV,VP,Schur} shells and StokesFunction (stokes.C), -boundary 0."""
 
-    def __init__(self, dim, rheology=0, hardness=1.0, exponent=1.0, regularization=1.0, gamma0=1.0):
+    def __init__(self, dim, rheology=0, hardness=1.0, exponent=1.0, regularization=1.0, gamma0=1.0, rank=0, nranks=1):
+        """nranks > 1: slab partition along axis 0 (see Elliptic); all sizes and vectors are then the local parts."""
         dim = [int(v) for v in dim]
         arr = (ctypes.c_int * len(dim))(*dim)
         self._h = ctypes.c_void_p()
-        _ck(lib().sb200_stokes_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        if nranks == 1:
+            _ck(lib().sb200_stokes_create(ctypes.c_int(len(dim)), arr, ctypes.byref(self._h)))
+        else:
+            _ck(lib().sb200_stokes_create_slab(ctypes.c_int(len(dim)), arr, ctypes.c_int(rank), ctypes.c_int(nranks), ctypes.byref(self._h)))
         v = [ctypes.c_longlong() for _ in range(5)]
         _ck(lib().sb200_stokes_sizes(self._h, *[ctypes.byref(x) for x in v]))
         self.m, self.g, self.gp, self.gv, self.dv = [x.value for x in v]
         self.dim, self.d = dim, len(dim)
+        self.rank, self.nranks = rank, nranks
+        i0, nloc, goff = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+        _ck(lib().sb200_stokes_slab_info(self._h, None, None, ctypes.byref(i0), ctypes.byref(nloc), ctypes.byref(goff)))
+        self.i0, self.nloc, self.goff = i0.value, nloc.value, goff.value
         self.set_rheology(rheology, hardness, exponent, regularization, gamma0)
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(lib().sb200_ipc_handle_bytes())
+        _ck(lib().sb200_stokes_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, peer_rank, handle):
+        _ck(lib().sb200_stokes_ipc_attach(self._h, ctypes.c_int(peer_rank), ctypes.c_char_p(handle)))
+
+    def attach_local(self, peer_rank, peer):
+        _ck(lib().sb200_stokes_attach_local(self._h, ctypes.c_int(peer_rank), peer._h))
+
+    def slab_timeouts(self):
+        n = ctypes.c_longlong()
+        _ck(lib().sb200_stokes_slab_status(self._h, ctypes.byref(n), _stream()))
+        return n.value
 
     def set_rheology(self, rheology, hardness=1.0, exponent=1.0, regularization=1.0, gamma0=1.0):
         _ck(lib().sb200_stokes_set_rheology(self._h, ctypes.c_int(rheology), ctypes.c_double(hardness), ctypes.c_double(exponent),

@@ -19,10 +19,56 @@ int sb200_stokes_create(int d, const int* dim, sb200_stokes** out) {
   SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
   *out = nullptr;
   StokesCtx* c = nullptr;
-  SB_TRY(StokesCtx::create(d, dim, &c));
+  SB_TRY(StokesCtx::create(d, dim, 0, 1, &c));
   sb200_stokes* s = new sb200_stokes();
   s->c = c;
   *out = s;
+  return 0;
+}
+
+int sb200_stokes_create_slab(int d, const int* dim, int rank, int nranks, sb200_stokes** out) {
+  SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");
+  *out = nullptr;
+  StokesCtx* c = nullptr;
+  SB_TRY(StokesCtx::create(d, dim, rank, nranks, &c));
+  sb200_stokes* s = new sb200_stokes();
+  s->c = c;
+  *out = s;
+  return 0;
+}
+
+int sb200_stokes_slab_info(const sb200_stokes* s, int* rank, int* nranks, int* i0, int* nloc, long long* goff_nodes) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  if (rank) *rank = s->c->arena.rank;
+  if (nranks) *nranks = s->c->arena.nranks;
+  if (i0) *i0 = s->c->gd.i0;
+  if (nloc) *nloc = s->c->gd.dim[0];
+  if (goff_nodes) *goff_nodes = s->c->gd.goff;
+  return 0;
+}
+
+int sb200_stokes_ipc_export(sb200_stokes* s, void* handle) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  return s->c->arena.export_handle(handle);
+}
+
+int sb200_stokes_ipc_attach(sb200_stokes* s, int peer_rank, const void* handle) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  return s->c->arena.attach(peer_rank, handle);
+}
+
+int sb200_stokes_attach_local(sb200_stokes* s, int peer_rank, sb200_stokes* peer) {
+  SB_CHECK(s && peer, SB200_ERR_ARG, "null context");
+  SB_CHECK(peer->c->arena.rank == peer_rank && peer->c->arena.nranks == s->c->arena.nranks, SB200_ERR_USER,
+           "attach_local: peer context has a different rank / partition");
+  return s->c->arena.attach_ptr(peer_rank, peer->c->arena.base);
+}
+
+int sb200_stokes_slab_status(sb200_stokes* s, long long* timeouts, void* stream) {
+  SB_CHECK(s && timeouts, SB200_ERR_ARG, "null pointer");
+  unsigned long long n = 0;
+  SB_TRY(s->c->arena.timeouts((cudaStream_t)stream, &n));
+  *timeouts = (long long)n;
   return 0;
 }
 

@@ -27,17 +27,19 @@ struct NodeInfo {
 };
 
 __device__ __forceinline__ NodeInfo decode_node(const GridDesc& gd, long long idx) {
-  // walk-order semantics of StokesSetupDomain (stokes.C:791-879) / BlockIt::normal (util.C:70-82)
-  long long rem = idx, cnt = 0;
+  // walk-order semantics of StokesSetupDomain (stokes.C:791-879) / BlockIt::normal (util.C:70-82); in a slab
+  // view axis-0 indices are global (offset gd.i0 inside gd.n0g) and the ordinals are local to this rank
+  long long rem = idx, cnt = -gd.goff;
   bool prefix_int = true, bdy = false;
   for (int j = 0; j < gd.d; j++) {
     const long long s = gd.stride[j];
-    const int i = (int)(rem / s);
-    rem -= (long long)i * s;
-    const bool b = (i == 0) || (i == gd.dim[j] - 1);
+    const int il = (int)(rem / s);
+    rem -= (long long)il * s;
+    const int i = gd.gidx(j, il), ext = gd.gext(j);
+    const bool b = (i == 0) || (i == ext - 1);
     if (prefix_int) {
       int c = i - 1;
-      c = c < 0 ? 0 : (c > gd.dim[j] - 2 ? gd.dim[j] - 2 : c);
+      c = c < 0 ? 0 : (c > ext - 2 ? ext - 2 : c);
       cnt += (long long)c * gd.istride[j];
       if (b) prefix_int = false;
     }
@@ -259,6 +261,32 @@ __global__ void reduce_order_kernel(ReduceArgs a, const double* __restrict__ w0,
   pres[base + (long long)(a.P - 1) * s] = f1;
 }
 
+// Slab partition, extrapolation along the partitioned axis 0: every rank forms the two end-point sums over ITS
+// planes for each of the R0 lines and pushes them to the owners of plane 0 (rank 0) and plane P-1 (last rank).
+__global__ void reduce0_partial_kernel(const double* __restrict__ w0, const double* __restrict__ w1, const double* __restrict__ pres,
+                                       int i0, int nloc, int P, long long R0, double* __restrict__ red_first, double* __restrict__ red_last) {
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= R0) return;
+  double f0 = 0.0, f1 = 0.0;
+  for (int kl = 0; kl < nloc; kl++) {
+    const int k = i0 + kl;
+    if (k < 1 || k > P - 2) continue;
+    const double v = pres[(long long)kl * R0 + line];
+    f0 = fma(w0[k], v, f0);
+    f1 = fma(w1[k], v, f1);
+  }
+  red_first[line] = f0;       // slot [rank][0][line] on rank 0
+  red_last[R0 + line] = f1;   // slot [rank][1][line] on the last rank
+}
+
+__global__ void reduce0_finish_kernel(const double* __restrict__ red, int nranks, int which, long long R0, double* __restrict__ plane) {
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= R0) return;
+  double f = 0.0;
+  for (int q = 0; q < nranks; q++) f += __ldcg(red + ((long long)q * 2 + which) * R0 + line);  // rank order: same on every run
+  plane[line] = f;
+}
+
 int grid_for(long long n) {
   long long b = (n + 255) / 256;
   return (int)std::min<long long>(std::max<long long>(b, 1), 148 * 16);
@@ -286,10 +314,10 @@ void extrap_weights(int P, std::vector<double>& w0, std::vector<double>& w1) {
 }  // namespace
 
 // ---- StokesCtx ---------------------------------------------------------------------------
-int StokesCtx::create(int d, const int* dim, StokesCtx** out) {
+int StokesCtx::create(int d, const int* dim, int rank, int nranks, StokesCtx** out) {
   SB_CHECK(d == 2 || d == 3, SB200_ERR_SUP, "Stokes shells are implemented for dimension 2 and 3 (stokes.C:1036)");
   StokesCtx* c = new StokesCtx();
-  int rc = c->init(d, dim);
+  int rc = c->init(d, dim, rank, nranks);
   if (rc) {
     delete c;
     return rc;
@@ -298,21 +326,28 @@ int StokesCtx::create(int d, const int* dim, StokesCtx** out) {
   return 0;
 }
 
-int StokesCtx::init(int d, const int* dim) {
-  SB_TRY(gd.init(d, dim));
+int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
+  SB_TRY(gd.init_slab(d, dim, rank, nranks));
+  for (int k = 0; k < d; k++) gdim[k] = dim[k];
   gp = gd.g;
   gv = gd.g * d;
   g = gd.g * (d + 1);
   dvn = (gd.m - gd.g) * d;
   const size_t mb = (size_t)gd.m * sizeof(double);
-  for (int k = 0; k < 2 + d; k++) SB_CUDA(cudaMalloc((void**)&workV[k], mb * d));  // xL, yL, V[d]
-  for (int k = 0; k < 3; k++) SB_CUDA(cudaMalloc((void**)&workP[k], mb));
+  const size_t lines0 = (size_t)gd.stride[0];
+  // one peer-mapped arena, same allocation order on every rank
+  const size_t total = (size_t)(2 + d) * (mb * d + 256) + 3 * (mb + 256) + (size_t)d * (mb * d + 256) + 2 * (mb + 256) +
+                       ((size_t)nranks * 2 * lines0 * sizeof(double) + 256);
+  SB_TRY(arena.init(total, rank, nranks));
+  for (int k = 0; k < 2 + d; k++) SB_CHECK((workV[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");  // xL, yL, V[d]
+  for (int k = 0; k < 3; k++) SB_CHECK((workP[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   for (int k = 0; k < d; k++) {
-    SB_CUDA(cudaMalloc((void**)&strain[k], mb * d));
+    SB_CHECK((strain[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");
     SB_CUDA(cudaMemset(strain[k], 0, mb * d));
   }
-  SB_CUDA(cudaMalloc((void**)&eta, mb));
-  SB_CUDA(cudaMalloc((void**)&deta, mb));
+  SB_CHECK((eta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+  SB_CHECK((deta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+  SB_CHECK((red = arena.alloc_doubles((size_t)nranks * 2 * lines0)), SB200_ERR_CUDA, "arena exhausted");
   {
     std::vector<double> ones((size_t)gd.m, 1.0);
     SB_CUDA(cudaMemcpy(eta, ones.data(), mb, cudaMemcpyHostToDevice));
@@ -320,26 +355,26 @@ int StokesCtx::init(int d, const int* dim) {
   }
   SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)dvn * sizeof(double))));
   SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)dvn * sizeof(double))));
-  SB_CUDA(cudaMalloc((void**)&force, (size_t)g * sizeof(double)));
-  SB_CUDA(cudaMemset(force, 0, (size_t)g * sizeof(double)));
-  SB_CUDA(cudaMalloc((void**)&vG0, (size_t)gv * sizeof(double)));
-  SB_CUDA(cudaMalloc((void**)&vG1, (size_t)gv * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&force, std::max<size_t>(8, (size_t)g * sizeof(double))));
+  SB_CUDA(cudaMemset(force, 0, std::max<size_t>(8, (size_t)g * sizeof(double))));
+  SB_CUDA(cudaMalloc((void**)&vG0, std::max<size_t>(8, (size_t)gv * sizeof(double))));
+  SB_CUDA(cudaMalloc((void**)&vG1, std::max<size_t>(8, (size_t)gv * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&minmax, 2 * sizeof(double)));
   for (int k = 0; k < d; k++) {
     Dax[k] = nullptr;
     for (int q = 0; q < k; q++)
-      if (gd.dim[q] == gd.dim[k]) {
+      if (gdim[q] == gdim[k]) {
         Dax[k] = Dax[q];
         w0[k] = w0[q];
         w1[k] = w1[q];
       }
     if (!Dax[k]) {
       DiffMatrix* dm = new DiffMatrix();
-      SB_TRY(DiffMatrix::create(gd.dim[k], dm));
+      SB_TRY(DiffMatrix::create(gdim[k], dm));
       owned.push_back(dm);
       Dax[k] = dm;
       std::vector<double> a, b;
-      extrap_weights(gd.dim[k], a, b);
+      extrap_weights(gdim[k], a, b);
       SB_CUDA(cudaMalloc((void**)&w0[k], a.size() * sizeof(double)));
       SB_CUDA(cudaMalloc((void**)&w1[k], b.size() * sizeof(double)));
       SB_CUDA(cudaMemcpy(w0[k], a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -352,14 +387,7 @@ int StokesCtx::init(int d, const int* dim) {
 }
 
 StokesCtx::~StokesCtx() {
-  for (auto& p : workV)
-    if (p) cudaFree(p);
-  for (auto& p : workP)
-    if (p) cudaFree(p);
-  for (auto& p : strain)
-    if (p) cudaFree(p);
-  if (eta) cudaFree(eta);
-  if (deta) cudaFree(deta);
+  arena.destroy();
   if (dirichlet) cudaFree(dirichlet);
   if (force) cudaFree(force);
   if (vG0) cudaFree(vG0);
@@ -370,6 +398,22 @@ StokesCtx::~StokesCtx() {
     dm->destroy();
     delete dm;
   }
+}
+
+// Launch one derivative; along the partitioned axis the operand rows are pulled from the planes' owners
+// (x must be an arena array), bracketed by device-side barriers (see EllipticCtx::deriv).
+int StokesCtx::deriv_common(DerivParams& p, int axis, cudaStream_t s) {
+  if (axis == 0 && arena.nranks > 1) {
+    SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+    p.npeer = arena.nranks;
+    p.nloc = gd.dim[0];
+    p.row0 = gd.i0;
+    for (int q = 0; q < arena.nranks; q++) p.xpeer[q] = arena.on(q, p.x);
+    SB_TRY(arena.barrier(s));
+    SB_TRY(deriv_apply(p, s));
+    return arena.barrier(s);
+  }
+  return deriv_apply(p, s);
 }
 
 int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
@@ -386,7 +430,7 @@ int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, 
   p.xs = p.ys = 1;
   p.xoff = p.yoff = 0;
   p.mode = mode;
-  return deriv_apply(p, s);
+  return deriv_common(p, axis, s);
 }
 
 int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin,
@@ -406,7 +450,7 @@ int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, i
   p.ys = ys;
   p.yoff = yoff;
   p.mode = mode;
-  return deriv_apply(p, s);
+  return deriv_common(p, axis, s);
 }
 
 int StokesCtx::pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s) {
@@ -471,27 +515,59 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
 int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s) {
   // stokes.C:1029-1080: z lines, then y lines, then x lines; later passes consume earlier results
   const int d = gd.d;
+  const bool slab = arena.nranks > 1;
   for (int pass = 0; pass < d; pass++) {
     const int axis = d - 1 - pass;
+    if (gdim[axis] < 3) continue;
+    if (axis == 0 && slab) {
+      // the partitioned axis: partial sums per rank, pushed to the two end-plane owners and added in rank order
+      SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+      const long long R0 = gd.stride[0];
+      const int G = arena.nranks, P = gdim[0];
+      double* mine_on_first = arena.on(0, red) + (size_t)arena.rank * 2 * R0;
+      double* mine_on_last = arena.on(G - 1, red) + (size_t)arena.rank * 2 * R0;
+      reduce0_partial_kernel<<<(unsigned)((R0 + 127) / 128), 128, 0, s>>>(w0[0], w1[0], pL, gd.i0, gd.dim[0], P, R0, mine_on_first, mine_on_last);
+      count_launch();
+      SB_CUDA(cudaGetLastError());
+      SB_TRY(arena.barrier(s));
+      if (arena.rank == 0) {
+        reduce0_finish_kernel<<<(unsigned)((R0 + 127) / 128), 128, 0, s>>>(red, G, 0, R0, pL);
+        count_launch();
+      }
+      if (arena.rank == G - 1) {
+        reduce0_finish_kernel<<<(unsigned)((R0 + 127) / 128), 128, 0, s>>>(red, G, 1, R0, pL + (size_t)(gd.dim[0] - 1) * R0);
+        count_launch();
+      }
+      SB_CUDA(cudaGetLastError());
+      SB_TRY(arena.barrier(s));  // the slots may be overwritten by the next call only after both sums are done
+      continue;
+    }
     ReduceArgs a;
     a.axis = axis;
     a.P = gd.dim[axis];
-    if (a.P < 3) continue;
     for (int j = 0; j < 3; j++) { a.lo[j] = 0; a.hi[j] = 0; a.stride[j] = 0; }
     for (int j = 0; j < d; j++) {
       a.stride[j] = gd.stride[j];
       // axes slower than `axis` were not extended yet: interior only; faster ones already were: full range
-      a.lo[j] = (j < axis) ? 1 : 0;
-      a.hi[j] = (j < axis) ? gd.dim[j] - 2 : gd.dim[j] - 1;
+      int lo = (j < axis) ? 1 : 0;
+      int hi = (j < axis) ? gd.gext(j) - 2 : gd.gext(j) - 1;
+      if (j == 0) {  // clip the global plane range to this rank's slab (local indices)
+        lo = std::max(lo, gd.i0) - gd.i0;
+        hi = std::min(hi, gd.i0 + gd.dim[0] - 1) - gd.i0;
+      }
+      a.lo[j] = lo;
+      a.hi[j] = hi;
     }
     a.nother = 0;
     a.nlines = 1;
+    bool empty = false;
     for (int j = 0; j < d; j++)
       if (j != axis) {
         a.oax[a.nother++] = j;
+        if (a.hi[j] < a.lo[j]) empty = true;
         a.nlines *= (a.hi[j] - a.lo[j] + 1);
       }
-    if (a.nlines <= 0) continue;
+    if (empty || a.nlines <= 0) continue;
     reduce_order_kernel<<<(unsigned)((a.nlines + 127) / 128), 128, 0, s>>>(a, w0[axis], w1[axis], pL);
     count_launch();
     SB_CUDA(cudaGetLastError());

@@ -4,6 +4,7 @@
 
 #include <vector>
 
+#include "deriv.h"
 #include "elliptic.h"  // GridDesc, DiffMatrix
 
 extern "C" typedef int (*sb200_velocity_solve_fn)(void* ctx, const double* d_rhs, double* d_sol, void* stream);
@@ -30,10 +31,15 @@ struct StokesCtx {
   DiffMatrix* Dax[3] = {};
   std::vector<DiffMatrix*> owned;
   std::vector<double*> owned_w;
+  // slab partition along axis 0 (nranks == 1: single GPU); the exchangeable arrays live in the arena
+  SymmArena arena;
+  int gdim[3] = {};
+  double* red = nullptr;  // [nranks][2][lines per plane]: partial end-point sums of the axis-0 extrapolation pass
 
-  static int create(int d, const int* dim, StokesCtx** out);
-  int init(int d, const int* dim);
+  static int create(int d, const int* dim, int rank, int nranks, StokesCtx** out);
+  int init(int d, const int* dim, int rank, int nranks);
   ~StokesCtx();
+  int deriv_common(struct DerivParams& p, int axis, cudaStream_t s);
 
   int deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);
   int deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode,
