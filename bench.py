@@ -38,6 +38,14 @@ def measured_peaks():
         return {}
 
 
+def ncu_traffic():
+    """DRAM bytes per step of the two persistent launches from the committed ncu --set full capture (None if absent)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def alg_flops(dim):
     # SURVEY 8(d): 2*P flop per node per scalar axis-derivative, 2 derivatives per axis
     m = int(np.prod(dim))
@@ -331,7 +339,8 @@ def run_cuda(args):
                        "value_l2_warm": ndof * args.steps / (hot_ms * 1e-3) / 1e9,
                        "parallelism": ("slab%d: axis 0 cut over %d GPUs, axis-0 chain through NVLink peer memory inside the chain kernel" % (world, world)) if world > 1 else "single"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS * world, "unit": "TFLOP/s", "frac": achieved / (FP64_PEAK_TFLOPS * world),
-                         "traffic": None, "pipe": "fp64 DMMA", "peak_source": "tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.jsonl); MEASURED_PEAKS.json has no fp64 entry",
+                         "traffic": ncu_traffic() if world == 1 else None, "traffic_source": "profiles/r01_traffic.json (ncu --set full, both launches of the step)",
+                         "pipe": "fp64 DMMA", "peak_source": "tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.jsonl); MEASURED_PEAKS.json has no fp64 entry",
                          "algorithmic_flops_per_step": fl, "kernel": "persist_kernel<128,8,1> phases A+B (the whole MatMult step: 2 PDL-linked launches)" if world == 1 else "slab step: stage + persist_kernel phases A+B per rank",
                          "hbm": {"achieved": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
                                  "frac": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9 / (hbm_peak * world), "algorithmic_bytes_per_step": alg_bytes(DIM)}},

@@ -31,6 +31,7 @@ struct sb200_cheb {
   DiffMatrix D;
   double* d_x = nullptr;  // staging for *_host
   double* d_y = nullptr;
+  unsigned* sync = nullptr;  // counters of the even-odd derivative kernel
 };
 
 struct sb200_elliptic {
@@ -129,6 +130,7 @@ int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb20
     delete c;
     return rc;
   }
+  if (cudaMalloc((void**)&c->sync, 64) == cudaSuccess) cudaMemset(c->sync, 0, 64);
   *out = c;
   return 0;
 }
@@ -137,6 +139,9 @@ int sb200_cheb_apply(sb200_cheb* c, const double* d_x, double* d_y, void* stream
   SB_CHECK(c && d_x && d_y, SB200_ERR_ARG, "null pointer");
   DerivParams p;
   p.D = c->D.d_D;
+  p.Ae = c->D.d_Ae;
+  p.Bo = c->D.d_Bo;
+  p.sync = c->sync;
   p.P = c->D.P;
   p.Pp = c->D.Pp;
   p.x = d_x;
@@ -167,6 +172,7 @@ int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y) {
 int sb200_cheb_destroy(sb200_cheb* c) {
   if (!c) return 0;
   c->D.destroy();
+  if (c->sync) cudaFree(c->sync);
   if (c->d_x) cudaFree(c->d_x);
   if (c->d_y) cudaFree(c->d_y);
   delete c;

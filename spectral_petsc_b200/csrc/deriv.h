@@ -8,6 +8,9 @@ enum DerivMode { DERIV_STORE = 0, DERIV_SUB = 1, DERIV_ADD = 2 };
 
 struct DerivParams {
   const double* D;    // device, Pp x Pp row-major, zero padded
+  const double* Ae = nullptr;  // even-odd halves of D ([P/2][P/2], P even); with `sync` they enable the even-odd
+  const double* Bo = nullptr;  // persistent kernel (deriv_eo.cu) for P in {16, 32, 64, 128}
+  unsigned* sync = nullptr;    // 2 zero-initialised counters owned by the calling context (ticket, exited warps)
   int P, Pp;          // extent of the differentiated axis, padded extent (multiple of 32)
   const double* x;    // input field
   double* y;          // output field (must not alias x)
@@ -24,6 +27,8 @@ struct DerivParams {
 };
 
 int deriv_apply(const DerivParams& p, cudaStream_t stream);
+bool deriv_eo_supported(const DerivParams& p);
+int deriv_eo_apply(const DerivParams& p, unsigned* sync, cudaStream_t stream);
 
 void count_launch(int n = 1);
 

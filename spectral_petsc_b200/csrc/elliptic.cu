@@ -234,6 +234,8 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
     SB_CHECK((g0_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CHECK((Wp = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   }
+  SB_CUDA(cudaMalloc((void**)&sync, 512));
+  SB_CUDA(cudaMemset(sync, 0, 512));
   SB_CUDA(cudaMalloc((void**)&dirichlet, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
   SB_CUDA(cudaMemset(dirichlet, 0, std::max<size_t>(8, (size_t)(gd.m - gd.g) * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&b, std::max<size_t>(8, (size_t)gd.g * sizeof(double))));
@@ -271,6 +273,9 @@ EllipticCtx::~EllipticCtx() {
 int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
   DerivParams p;
   p.D = Dax[axis]->d_D;
+  p.Ae = Dax[axis]->d_Ae;
+  p.Bo = Dax[axis]->d_Bo;
+  p.sync = sync + 10;  // counters of the even-odd derivative kernel ([0..5]: persistent chain phases, [8]: stage)
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
   p.x = x;

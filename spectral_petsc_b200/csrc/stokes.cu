@@ -360,6 +360,8 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   SB_CUDA(cudaMalloc((void**)&vG0, std::max<size_t>(8, (size_t)gv * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&vG1, std::max<size_t>(8, (size_t)gv * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&minmax, 2 * sizeof(double)));
+  SB_CUDA(cudaMalloc((void**)&sync, 64));
+  SB_CUDA(cudaMemset(sync, 0, 64));
   for (int k = 0; k < d; k++) {
     Dax[k] = nullptr;
     for (int q = 0; q < k; q++)
@@ -393,6 +395,7 @@ StokesCtx::~StokesCtx() {
   if (vG0) cudaFree(vG0);
   if (vG1) cudaFree(vG1);
   if (minmax) cudaFree(minmax);
+  if (sync) cudaFree(sync);
   for (double* p : owned_w) cudaFree(p);
   for (DiffMatrix* dm : owned) {
     dm->destroy();
@@ -420,6 +423,9 @@ int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, 
   // DV[axis]: rank d+1 with trailing component axis of extent d (stokes.C:284-289)
   DerivParams p;
   p.D = Dax[axis]->d_D;
+  p.Ae = Dax[axis]->d_Ae;
+  p.Bo = Dax[axis]->d_Bo;
+  p.sync = sync;
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
   p.x = x;
@@ -438,6 +444,9 @@ int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, i
   // DP[axis] on a scalar field that may live inside an AoS vector (VecStrideGather/Scatter, stokes.C:585,613)
   DerivParams p;
   p.D = Dax[axis]->d_D;
+  p.Ae = Dax[axis]->d_Ae;
+  p.Bo = Dax[axis]->d_Bo;
+  p.sync = sync;
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
   p.x = x;

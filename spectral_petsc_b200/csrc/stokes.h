@@ -34,6 +34,7 @@ struct StokesCtx {
   // slab partition along axis 0 (nranks == 1: single GPU); the exchangeable arrays live in the arena
   SymmArena arena;
   int gdim[3] = {};
+  unsigned* sync = nullptr;  // counters of the even-odd derivative kernel
   double* red = nullptr;  // [nranks][2][lines per plane]: partial end-point sums of the axis-0 extrapolation pass
 
   static int create(int d, const int* dim, int rank, int nranks, StokesCtx** out);
