@@ -29,6 +29,9 @@ struct DerivParams {
 int deriv_apply(const DerivParams& p, cudaStream_t stream);
 bool deriv_eo_supported(const DerivParams& p);
 int deriv_eo_apply(const DerivParams& p, unsigned* sync, cudaStream_t stream);
+#define SB200_EO_MAX_JOBS 3
+// Up to SB200_EO_MAX_JOBS derivatives sharing the matrix (same extent) in ONE launch; outputs must be distinct.
+int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t stream);
 
 void count_launch(int n = 1);
 

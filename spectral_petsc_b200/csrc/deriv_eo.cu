@@ -14,15 +14,28 @@ namespace sb200 {
 
 namespace {
 
+// Up to three derivatives that share the matrix run as ONE launch: the tickets of job j are [start[j], end[j]).
+// (The reference applies D_0, D_1, D_2 back to back - stokes.C:584-590,611-614,639,668-671 - each on the full
+// grid; one launch keeps every SM busy through the tail of each and loads Ae / Bo once.)
+struct EoJob {
+  const double* x;
+  double* y;
+  const double* yin;
+  long long R, nlines;
+  int xs, xoff, ys, yoff, mode;
+  int vec;  // R % 8 == 0, unit strides, 16-byte aligned: the block's 8 lines are adjacent in memory
+  unsigned end;  // exclusive prefix of item counts
+};
 struct EoParams {
-  DerivParams d;
-  long long nlines;   // O * R
-  unsigned items;     // ceil(nlines / 8)
+  EoJob job[SB200_EO_MAX_JOBS];
+  int njobs;
+  const double* Ae;
+  const double* Bo;
+  unsigned items;     // total
   unsigned* sync;     // [0] ticket, [1] exited warps
 };
 
-// VEC: R % 8 == 0 and unit element strides: the 8 lines of a block are adjacent in memory (16-byte accesses).
-template <int P, int NWARPS, bool VEC>
+template <int P, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   using E = EO<P>;
   extern __shared__ double sm[];
@@ -31,25 +44,30 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   double* Xw = sm + E::MAT_ELEMS + warp * E::BLOCK_ELEMS_LEFT;
-  const DerivParams& p = q.d;
-  const long long R = p.R, PR = (long long)P * R;
-
-  load_matrices<P>(sm, p.Ae, p.Bo);
+  load_matrices<P>(sm, q.Ae, q.Bo);
 
   auto grab = [&]() -> unsigned {
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(q.sync, 1u);
     return __shfl_sync(0xffffffffu, tk, 0);
   };
-  auto line_base = [&](long long n) -> long long {  // element index of (line n, m = 0)
+  auto job_of = [&](unsigned tk) -> int {
+    int j = 0;
+    while (j + 1 < q.njobs && tk >= q.job[j].end) j++;
+    return j;
+  };
+  auto line_base = [&](long long n, long long R) -> long long {  // element index of (line n, m = 0)
     const long long o = n / R, r = n - o * R;
-    return o * PR + r;
+    return o * (long long)P * R + r;
   };
   auto issue_load = [&](unsigned tk) {
     if (tk >= q.items) return;
-    const long long n0 = (long long)tk * 8;
-    if (VEC) {
-      const long long b0 = line_base(n0);
+    const int j = job_of(tk);
+    const EoJob& p = q.job[j];
+    const long long R = p.R;
+    const long long n0 = (long long)(tk - (j ? q.job[j - 1].end : 0u)) * 8;
+    if (p.vec) {
+      const long long b0 = line_base(n0, R);
 #pragma unroll 4
       for (int idx = lane; idx < P * 4; idx += 32) {
         const int m = idx >> 2, c2 = (idx & 3) * 2;
@@ -57,8 +75,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
       }
     } else {
       const int c = lane & 7;
-      const bool ok = (n0 + c) < q.nlines;
-      const long long bc = ok ? line_base(n0 + c) : 0;
+      const bool ok = (n0 + c) < p.nlines;
+      const long long bc = ok ? line_base(n0 + c, R) : 0;
 #pragma unroll 4
       for (int m = lane >> 3; m < P; m += 4)
         cp_async8(Xw + xaddr<P, false>(m, c), p.x + (ok ? (bc + (long long)m * R) * p.xs + p.xoff : 0), ok);
@@ -72,7 +90,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   __syncthreads();  // matrices visible to all warps
 
   while (tk < q.items) {
-    const long long n0 = (long long)tk * 8;
+    const int j = job_of(tk);
+    const EoJob& p = q.job[j];
+    const long long R = p.R;
+    const long long n0 = (long long)(tk - (j ? q.job[j - 1].end : 0u)) * 8;
     cp_async_wait<0>();
     __syncwarp();
     double a[E::MT][2], b[E::MT][2];
@@ -82,8 +103,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
     issue_load(nxt);
 
     // thread-owned outputs: lines 2t, 2t+1; rows mt = i*8+g (a+b) and mb = P-1-mt (b-a)
-    if (VEC) {
-      const long long base = line_base(n0) + 2 * t;
+    if (p.vec) {
+      const long long base = line_base(n0, R) + 2 * t;
 #pragma unroll
       for (int i = 0; i < E::MT; i++) {
         const long long et = base + (long long)(i * 8 + g) * R, eb = base + (long long)(P - 1 - i * 8 - g) * R;
@@ -107,8 +128,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const long long n = n0 + 2 * t + h;
-        if (n >= q.nlines) continue;
-        const long long lb = line_base(n);
+        if (n >= p.nlines) continue;
+        const long long lb = line_base(n, R);
 #pragma unroll
         for (int i = 0; i < E::MT; i++) {
           const long long et = (lb + (long long)(i * 8 + g) * R) * p.ys + p.yoff;
@@ -138,12 +159,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   }
 }
 
-unsigned* g_sync = nullptr;  // one ticket block per device stream order (launches on a context are stream-ordered)
-
-template <int P, int NWARPS, bool VEC>
+template <int P, int NWARPS>
 int launch_eo(const EoParams& q, cudaStream_t s) {
   using E = EO<P>;
-  auto kern = eo_deriv_kernel<P, NWARPS, VEC>;
+  auto kern = eo_deriv_kernel<P, NWARPS>;
   const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * E::BLOCK_ELEMS_LEFT) * sizeof(double);
   static bool attr = false;
   if (!attr) {
@@ -162,11 +181,6 @@ int launch_eo(const EoParams& q, cudaStream_t s) {
   return 0;
 }
 
-template <int P, int NWARPS>
-int launch_by_vec(const EoParams& q, bool vec, cudaStream_t s) {
-  return vec ? launch_eo<P, NWARPS, true>(q, s) : launch_eo<P, NWARPS, false>(q, s);
-}
-
 }  // namespace
 
 bool deriv_eo_supported(const DerivParams& p) {
@@ -174,22 +188,45 @@ bool deriv_eo_supported(const DerivParams& p) {
   return p.P == 16 || p.P == 32 || p.P == 64 || p.P == 128;
 }
 
-int deriv_eo_apply(const DerivParams& p, unsigned* sync, cudaStream_t s) {
+int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t s) {
+  SB_CHECK(n >= 1 && n <= SB200_EO_MAX_JOBS, SB200_ERR_USER, "even-odd derivative: bad job count");
   EoParams q;
-  q.d = p;
-  q.nlines = p.O * p.R;
-  q.items = (unsigned)((q.nlines + 7) / 8);
+  q.njobs = n;
+  q.Ae = jobs[0].Ae;
+  q.Bo = jobs[0].Bo;
   q.sync = sync;
-  const bool vec = (p.R % 8 == 0) && p.xs == 1 && p.ys == 1 && p.xoff == 0 && p.yoff == 0 &&
-                   ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.yin)) % 16 == 0);
-  switch (p.P) {
-    case 16: return launch_by_vec<16, 16>(q, vec, s);
-    case 32: return launch_by_vec<32, 16>(q, vec, s);
-    case 64: return launch_by_vec<64, 16>(q, vec, s);
-    case 128: return launch_by_vec<128, 16>(q, vec, s);
+  unsigned total = 0;
+  for (int j = 0; j < n; j++) {
+    const DerivParams& p = jobs[j];
+    SB_CHECK(deriv_eo_supported(p) && p.P == jobs[0].P && p.Ae == q.Ae, SB200_ERR_USER, "even-odd derivative: jobs must share the matrix");
+    SB_CHECK(p.x != p.y, SB200_ERR_ARG, "deriv: x and y must not alias (chebyshev.c:127)");
+    EoJob& e = q.job[j];
+    e.x = p.x;
+    e.y = p.y;
+    e.yin = p.yin;
+    e.R = p.R;
+    e.nlines = p.O * p.R;
+    e.xs = p.xs;
+    e.xoff = p.xoff;
+    e.ys = p.ys;
+    e.yoff = p.yoff;
+    e.mode = p.mode;
+    e.vec = (p.R % 8 == 0) && p.xs == 1 && p.ys == 1 && p.xoff == 0 && p.yoff == 0 &&
+            ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.yin)) % 16 == 0);
+    total += (unsigned)((e.nlines + 7) / 8);
+    e.end = total;
+  }
+  q.items = total;
+  switch (jobs[0].P) {
+    case 16: return launch_eo<16, 16>(q, s);
+    case 32: return launch_eo<32, 16>(q, s);
+    case 64: return launch_eo<64, 16>(q, s);
+    case 128: return launch_eo<128, 16>(q, s);
   }
   set_last_error("even-odd derivative: unsupported extent");
   return SB200_ERR_SUP;
 }
+
+int deriv_eo_apply(const DerivParams& p, unsigned* sync, cudaStream_t s) { return deriv_eo_batch(&p, 1, sync, s); }
 
 }  // namespace sb200

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/spectral_b200.h"
@@ -80,6 +81,25 @@ __global__ void crop_nodes_kernel(GridDesc gd, int nc, const double* __restrict_
       if (add) v = dst[e] + v;             // VecAXPY(vG1, 1.0, vG0) stokes.C:513,750
       if (sub) v = v + (-1.0) * sub[e];    // VecAXPY(yG, -1.0, force) stokes.C:756
       dst[e] = v;
+    }
+  }
+}
+
+struct TermPtrs {
+  const double* t[3];
+};
+
+// dst[gid*dstride + doff + k] = ((0 +- T_0) +- T_1) +- T_2 at interior nodes: the VecAXPY chain of stokes.C:584-590 /
+// 668-671 (w0 = 0; w0 -= D_i V_i in axis order) applied while cropping, same operation order as the reference.
+__global__ void crop_sum_kernel(GridDesc gd, int nc, int nterms, TermPtrs tp, double sign, double* __restrict__ dst, int dstride, int doff) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    const NodeInfo n = decode_node(gd, idx);
+    if (!n.interior) continue;
+    for (int k = 0; k < nc; k++) {
+      double v = 0.0;
+      for (int t = 0; t < nterms; t++) v = __dadd_rn(v, __dmul_rn(sign, tp.t[t][idx * nc + k]));
+      dst[n.gid * dstride + doff + k] = v;
     }
   }
 }
@@ -240,9 +260,12 @@ struct ReduceArgs {
 
 __global__ void reduce_order_kernel(ReduceArgs a, const double* __restrict__ w0, const double* __restrict__ w1,
                                     double* __restrict__ pres) {
-  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (line >= a.nlines) return;
-  long long rem = line, base = 0;
+  // block = 32 lines (threadIdx.x, adjacent in memory) x 8 slices of the line (threadIdx.y): the loads of a warp
+  // are coalesced across lines and every line's sum is finished through shared memory
+  __shared__ double s0[8][33], s1[8][33];
+  const long long line = (long long)blockIdx.x * 32 + threadIdx.x;
+  const bool live = line < a.nlines;
+  long long rem = live ? line : 0, base = 0;
   for (int q = a.nother - 1; q >= 0; q--) {
     const int ax = a.oax[q];
     const int ext = a.hi[ax] - a.lo[ax] + 1;
@@ -252,13 +275,54 @@ __global__ void reduce_order_kernel(ReduceArgs a, const double* __restrict__ w0,
   }
   const long long s = a.stride[a.axis];
   double f0 = 0.0, f1 = 0.0;
-  for (int k = 1; k < a.P - 1; k++) {
-    const double v = pres[base + k * s];
+  if (live)
+    for (int k = 1 + threadIdx.y; k < a.P - 1; k += 8) {
+      const double v = pres[base + k * s];
+      f0 = fma(w0[k], v, f0);
+      f1 = fma(w1[k], v, f1);
+    }
+  s0[threadIdx.y][threadIdx.x] = f0;
+  s1[threadIdx.y][threadIdx.x] = f1;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int j = 0; j < 8; j++) {
+      t0 += s0[j][threadIdx.x];
+      t1 += s1[j][threadIdx.x];
+    }
+    pres[base] = t0;
+    pres[base + (long long)(a.P - 1) * s] = t1;
+  }
+}
+
+// Same pass for the LAST axis (contiguous lines): one warp per line, coalesced loads, shuffle reduction.
+__global__ void reduce_order_lastaxis_kernel(ReduceArgs a, const double* __restrict__ w0, const double* __restrict__ w1,
+                                             double* __restrict__ pres) {
+  const long long line = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (line >= a.nlines) return;
+  long long rem = line, base = 0;
+  for (int q = a.nother - 1; q >= 0; q--) {
+    const int ax = a.oax[q];
+    const int ext = a.hi[ax] - a.lo[ax] + 1;
+    const int i = a.lo[ax] + (int)(rem % ext);
+    rem /= ext;
+    base += (long long)i * a.stride[ax];
+  }
+  double f0 = 0.0, f1 = 0.0;
+  for (int k = 1 + lane; k < a.P - 1; k += 32) {
+    const double v = pres[base + k];
     f0 = fma(w0[k], v, f0);
     f1 = fma(w1[k], v, f1);
   }
-  pres[base] = f0;
-  pres[base + (long long)(a.P - 1) * s] = f1;
+  for (int o = 16; o > 0; o >>= 1) {
+    f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+    f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+  }
+  if (lane == 0) {
+    pres[base] = f0;
+    pres[base + (a.P - 1)] = f1;
+  }
 }
 
 // Slab partition, extrapolation along the partitioned axis 0: every rank forms the two end-point sums over ITS
@@ -336,10 +400,10 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   const size_t mb = (size_t)gd.m * sizeof(double);
   const size_t lines0 = (size_t)gd.stride[0];
   // one peer-mapped arena, same allocation order on every rank
-  const size_t total = (size_t)(2 + d) * (mb * d + 256) + 3 * (mb + 256) + (size_t)d * (mb * d + 256) + 2 * (mb + 256) +
+  const size_t total = (size_t)(3 + d) * (mb * d + 256) + 3 * (mb + 256) + (size_t)d * (mb * d + 256) + 2 * (mb + 256) +
                        ((size_t)nranks * 2 * lines0 * sizeof(double) + 256);
   SB_TRY(arena.init(total, rank, nranks));
-  for (int k = 0; k < 2 + d; k++) SB_CHECK((workV[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");  // xL, yL, V[d]
+  for (int k = 0; k < 3 + d; k++) SB_CHECK((workV[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");  // xL, yL, V[d], term
   for (int k = 0; k < 3; k++) SB_CHECK((workP[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   for (int k = 0; k < d; k++) {
     SB_CHECK((strain[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");
@@ -419,7 +483,7 @@ int StokesCtx::deriv_common(DerivParams& p, int axis, cudaStream_t s) {
   return deriv_apply(p, s);
 }
 
-int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
+DerivParams StokesCtx::job_v(int axis, const double* x, double* y, const double* yin, int mode) const {
   // DV[axis]: rank d+1 with trailing component axis of extent d (stokes.C:284-289)
   DerivParams p;
   p.D = Dax[axis]->d_D;
@@ -436,11 +500,11 @@ int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, 
   p.xs = p.ys = 1;
   p.xoff = p.yoff = 0;
   p.mode = mode;
-  return deriv_common(p, axis, s);
+  return p;
 }
 
-int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin,
-                       int mode, cudaStream_t s) {
+DerivParams StokesCtx::job_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin,
+                             int mode) const {
   // DP[axis] on a scalar field that may live inside an AoS vector (VecStrideGather/Scatter, stokes.C:585,613)
   DerivParams p;
   p.D = Dax[axis]->d_D;
@@ -459,7 +523,41 @@ int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, i
   p.ys = ys;
   p.yoff = yoff;
   p.mode = mode;
+  return p;
+}
+
+int StokesCtx::deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
+  DerivParams p = job_v(axis, x, y, yin, mode);
   return deriv_common(p, axis, s);
+}
+
+int StokesCtx::deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin,
+                       int mode, cudaStream_t s) {
+  DerivParams p = job_p(axis, x, xs, xoff, y, ys, yoff, yin, mode);
+  return deriv_common(p, axis, s);
+}
+
+bool StokesCtx::batchable() const {
+  static int use = -1;
+  if (use < 0) {
+    const char* c = getenv("SB200_NO_EO");
+    const char* b = getenv("SB200_NO_BATCH");
+    use = ((c && atoi(c)) || (b && atoi(b))) ? 0 : 1;
+  }
+  if (!use || arena.nranks > 1 || gd.d > SB200_EO_MAX_JOBS) return false;
+  for (int k = 1; k < gd.d; k++)
+    if (Dax[k] != Dax[0]) return false;
+  DerivParams p = job_p(0, workP[0], 1, 0, workP[1], 1, 0, nullptr, DERIV_STORE);
+  return deriv_eo_supported(p);
+}
+
+int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s) {
+  TermPtrs tp;
+  for (int t = 0; t < 3; t++) tp.t[t] = t < nterms ? terms[t] : nullptr;
+  crop_sum_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, nc, nterms, tp, sign, dst, dstride, doff);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int StokesCtx::pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s) {
@@ -486,6 +584,14 @@ int StokesCtx::crop(int nc, const double* local, double* dst, int dstride, int d
 // y_vel[interior] (=|+=) -sum_j D_j V_j   with V from the pointwise step; shared tail of VV and Function
 int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) {
   const int d = gd.d;
+  if (batchable()) {
+    // one launch for the d terms D_i V_i, the "-=" chain (stokes.C:668-671) is applied by the crop in axis order
+    double* terms[3] = {workV[0], workV[1], workV[2 + d]};
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) jobs[i] = job_v(i, workV[2 + i], terms[i], nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    return crop_sum(d, d, terms, -1.0, dst, dstride, doff, s);
+  }
   double* yL = workV[1];
   for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, workV[2 + i], yL, i == 0 ? nullptr : yL, DERIV_SUB, s));  // :668-671
   return crop(d, yL, dst, dstride, doff, false, nullptr, s);
@@ -495,7 +601,13 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));                                             // :635-637
-  for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
+  if (batchable()) {
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) jobs[i] = job_v(i, xL, workV[2 + i], nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+  } else {
+    for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
+  }
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
@@ -515,6 +627,14 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(x, xstride, xoff, with_dirichlet, xL, s));  // :574-581
+  if (batchable()) {
+    // one launch for the d terms D_i v_i; the "+=" chain (stokes.C:584-590) is applied by the crop in axis order
+    double* terms[3] = {workP[0], workP[1], workP[2]};
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) jobs[i] = job_p(i, xL, d, i, terms[i], 1, 0, nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    return crop_sum(1, d, terms, 1.0, dst, dstride, doff, s);
+  }
   double* acc = workP[2];
   for (int i = 0; i < d; i++)  // :584-590  component i gathered by stride, accumulated in the epilogue
     SB_TRY(deriv_p(i, xL, d, i, acc, 1, 0, i == 0 ? nullptr : acc, DERIV_ADD, s));
@@ -577,7 +697,10 @@ int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s) {
         a.nlines *= (a.hi[j] - a.lo[j] + 1);
       }
     if (empty || a.nlines <= 0) continue;
-    reduce_order_kernel<<<(unsigned)((a.nlines + 127) / 128), 128, 0, s>>>(a, w0[axis], w1[axis], pL);
+    if (axis == d - 1 && gd.stride[axis] == 1)
+      reduce_order_lastaxis_kernel<<<(unsigned)((a.nlines * 32 + 255) / 256), 256, 0, s>>>(a, w0[axis], w1[axis], pL);
+    else
+      reduce_order_kernel<<<(unsigned)((a.nlines + 31) / 32), dim3(32, 8), 0, s>>>(a, w0[axis], w1[axis], pL);
     count_launch();
     SB_CUDA(cudaGetLastError());
   }
@@ -591,7 +714,13 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
   SB_TRY(pad_pres(x, xstride, xoff, pL, s));  // :606-608
   SB_TRY(pressure_reduce_order(pL, s));       // :609
   double* vL = workV[0];
-  for (int i = 0; i < d; i++) SB_TRY(deriv_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE, s));  // :611-614
+  if (batchable()) {
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) jobs[i] = job_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+  } else {
+    for (int i = 0; i < d; i++) SB_TRY(deriv_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE, s));  // :611-614
+  }
   return crop(d, vL, dst, dstride, doff, add, sub, s);                                         // :617
 }
 
@@ -609,7 +738,13 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(xG, d + 1, 0, true, xL, s));                                                 // :691-699
-  for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
+  if (batchable()) {
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) jobs[i] = job_v(i, xL, strain[i], nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+  } else {
+    for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
+  }
   init_minmax_kernel<<<1, 1, 0, s>>>(minmax);
   count_launch();
   Rheo r{rheology, hardness, exponent, regularization, gamma0};

@@ -14,7 +14,7 @@ namespace sb200 {
 struct StokesCtx {
   GridDesc gd;
   long long gp = 0, gv = 0, g = 0, dvn = 0;  // DOF counts printed at stokes.C:891
-  double* workV[2 + 3] = {};  // xL, yL, V[d]   (c->workV, stokes.C:271)
+  double* workV[2 + 3 + 1] = {};  // xL, yL, V[d], one more term buffer   (c->workV, stokes.C:271)
   double* workP[3] = {};      // pL, scratch, accumulator (c->workP)
   double* strain[3] = {};     // c->strain, each m*d
   double* eta = nullptr;
@@ -41,6 +41,11 @@ struct StokesCtx {
   int init(int d, const int* dim, int rank, int nranks);
   ~StokesCtx();
   int deriv_common(struct DerivParams& p, int axis, cudaStream_t s);
+  DerivParams job_v(int axis, const double* x, double* y, const double* yin, int mode) const;
+  DerivParams job_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode) const;
+  // true when the d derivatives can run as one even-odd launch (single GPU, equal extents in {16,32,64,128})
+  bool batchable() const;
+  int crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s);
 
   int deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);
   int deriv_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode,
