@@ -35,4 +35,9 @@ int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t 
 
 void count_launch(int n = 1);
 
+struct SymmArena;
+// Transpose-based derivative along the partitioned axis of a slab-distributed field (slab_deriv.cu).
+bool slab_deriv0_pencil_supported(const SymmArena& a, const DerivParams& p);
+int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, double* Yp, cudaStream_t s);
+
 }  // namespace sb200

@@ -219,7 +219,7 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
   nw = 2 + d;  // elliptic.C:259
   const size_t mb = (size_t)gd.m * sizeof(double);
   // every exchangeable array comes from one peer-mapped arena, in the same order on every rank
-  const int narr = nw + d + 2 + (nranks > 1 ? 4 : 0);
+  const int narr = nw + d + 2 + (nranks > 1 ? 6 : 0);
   SB_TRY(arena.init((size_t)narr * (mb + 256), rank, nranks));
   for (int k = 0; k < nw; k++) SB_CHECK((w[k] = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   for (int k = 0; k < d; k++) {
@@ -233,6 +233,8 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
     SB_CHECK((deta_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CHECK((g0_p = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
     SB_CHECK((Wp = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((Xp = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((Yp = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   }
   SB_CUDA(cudaMalloc((void**)&sync, 512));
   SB_CUDA(cudaMemset(sync, 0, 512));
@@ -287,8 +289,11 @@ int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, 
   p.xoff = p.yoff = 0;
   p.mode = mode;
   if (axis == 0 && arena.nranks > 1) {
-    // the partitioned axis: operand rows are pulled from the planes' owners (x must be an arena array);
-    // the barriers order the peers' writes of x before our reads and our reads before their next writes
+    // the partitioned axis: through the column pencils (two pushes over NVLink) when the columns divide by the
+    // number of ranks; otherwise operand rows are pulled from the planes' owners (x must be an arena array) and the
+    // barriers order the peers' writes of x before our reads and our reads before their next writes
+    SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+    if (slab_deriv0_pencil_supported(arena, p)) return slab_deriv0_pencil(arena, p, gd.dim[0], gd.i0, Xp, Yp, s);
     p.npeer = arena.nranks;
     p.nloc = gd.dim[0];
     p.row0 = gd.i0;

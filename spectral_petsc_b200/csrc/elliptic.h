@@ -62,6 +62,8 @@ struct EllipticCtx {
   double* eta_p = nullptr;          // axis-0 pencil copies of eta / deta / gradu[0] for the fused MatMult
   double* deta_p = nullptr;
   double* g0_p = nullptr;
+  double* Xp = nullptr;             // pencil operand / result buffers of the generic axis-0 derivative
+  double* Yp = nullptr;
   bool pencil_valid = false;
   unsigned long long mm_epoch = 0;  // fused MatMult epoch (SYMM_READY / SYMM_DONE flags)
 

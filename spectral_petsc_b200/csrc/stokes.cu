@@ -400,7 +400,7 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   const size_t mb = (size_t)gd.m * sizeof(double);
   const size_t lines0 = (size_t)gd.stride[0];
   // one peer-mapped arena, same allocation order on every rank
-  const size_t total = (size_t)(3 + d) * (mb * d + 256) + 3 * (mb + 256) + (size_t)d * (mb * d + 256) + 2 * (mb + 256) +
+  const size_t total = (size_t)(3 + d + (nranks > 1 ? 2 : 0)) * (mb * d + 256) + 3 * (mb + 256) + (size_t)d * (mb * d + 256) + 2 * (mb + 256) +
                        ((size_t)nranks * 2 * lines0 * sizeof(double) + 256);
   SB_TRY(arena.init(total, rank, nranks));
   for (int k = 0; k < 3 + d; k++) SB_CHECK((workV[k] = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");  // xL, yL, V[d], term
@@ -412,6 +412,10 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   SB_CHECK((eta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   SB_CHECK((deta = arena.alloc_doubles(gd.m)), SB200_ERR_CUDA, "arena exhausted");
   SB_CHECK((red = arena.alloc_doubles((size_t)nranks * 2 * lines0)), SB200_ERR_CUDA, "arena exhausted");
+  if (nranks > 1) {
+    SB_CHECK((Xp = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");
+    SB_CHECK((Yp = arena.alloc_doubles((size_t)gd.m * d)), SB200_ERR_CUDA, "arena exhausted");
+  }
   {
     std::vector<double> ones((size_t)gd.m, 1.0);
     SB_CUDA(cudaMemcpy(eta, ones.data(), mb, cudaMemcpyHostToDevice));
@@ -472,6 +476,7 @@ StokesCtx::~StokesCtx() {
 int StokesCtx::deriv_common(DerivParams& p, int axis, cudaStream_t s) {
   if (axis == 0 && arena.nranks > 1) {
     SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
+    if (slab_deriv0_pencil_supported(arena, p)) return slab_deriv0_pencil(arena, p, gd.dim[0], gd.i0, Xp, Yp, s);
     p.npeer = arena.nranks;
     p.nloc = gd.dim[0];
     p.row0 = gd.i0;
@@ -544,11 +549,21 @@ bool StokesCtx::batchable() const {
     const char* b = getenv("SB200_NO_BATCH");
     use = ((c && atoi(c)) || (b && atoi(b))) ? 0 : 1;
   }
-  if (!use || arena.nranks > 1 || gd.d > SB200_EO_MAX_JOBS) return false;
+  if (!use || gd.d > SB200_EO_MAX_JOBS) return false;
+  if (arena.nranks > 1 && gd.stride[0] % arena.nranks != 0) return false;  // the axis-0 pencils need R0 % G == 0
   for (int k = 1; k < gd.d; k++)
     if (Dax[k] != Dax[0]) return false;
   DerivParams p = job_p(0, workP[0], 1, 0, workP[1], 1, 0, nullptr, DERIV_STORE);
   return deriv_eo_supported(p);
+}
+
+// The d independent derivatives of one stage (all DERIV_STORE).  Single GPU: one batched even-odd launch.  Slab: axis 0
+// goes through the pencils (two pushes over NVLink), the local axes run as one batch.
+int StokesCtx::run_jobs(DerivParams* jobs, int d, cudaStream_t s) {
+  if (arena.nranks == 1) return deriv_eo_batch(jobs, d, sync, s);
+  SB_TRY(deriv_common(jobs[0], 0, s));
+  if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
+  return 0;
 }
 
 int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s) {
@@ -589,7 +604,7 @@ int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) 
     double* terms[3] = {workV[0], workV[1], workV[2 + d]};
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_v(i, workV[2 + i], terms[i], nullptr, DERIV_STORE);
-    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    SB_TRY(run_jobs(jobs, d, s));
     return crop_sum(d, d, terms, -1.0, dst, dstride, doff, s);
   }
   double* yL = workV[1];
@@ -604,7 +619,7 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   if (batchable()) {
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_v(i, xL, workV[2 + i], nullptr, DERIV_STORE);
-    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    SB_TRY(run_jobs(jobs, d, s));
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
   }
@@ -632,7 +647,7 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
     double* terms[3] = {workP[0], workP[1], workP[2]};
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_p(i, xL, d, i, terms[i], 1, 0, nullptr, DERIV_STORE);
-    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    SB_TRY(run_jobs(jobs, d, s));
     return crop_sum(1, d, terms, 1.0, dst, dstride, doff, s);
   }
   double* acc = workP[2];
@@ -717,7 +732,7 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
   if (batchable()) {
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE);
-    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    SB_TRY(run_jobs(jobs, d, s));
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE, s));  // :611-614
   }
@@ -741,7 +756,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   if (batchable()) {
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_v(i, xL, strain[i], nullptr, DERIV_STORE);
-    SB_TRY(deriv_eo_batch(jobs, d, sync, s));
+    SB_TRY(run_jobs(jobs, d, s));
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
   }

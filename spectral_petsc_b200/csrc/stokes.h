@@ -35,6 +35,8 @@ struct StokesCtx {
   SymmArena arena;
   int gdim[3] = {};
   unsigned* sync = nullptr;  // counters of the even-odd derivative kernel
+  double* Xp = nullptr;   // pencil operand / result buffers of the axis-0 derivative (m*d doubles each)
+  double* Yp = nullptr;
   double* red = nullptr;  // [nranks][2][lines per plane]: partial end-point sums of the axis-0 extrapolation pass
 
   static int create(int d, const int* dim, int rank, int nranks, StokesCtx** out);
@@ -45,6 +47,7 @@ struct StokesCtx {
   DerivParams job_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode) const;
   // true when the d derivatives can run as one even-odd launch (single GPU, equal extents in {16,32,64,128})
   bool batchable() const;
+  int run_jobs(DerivParams* jobs, int d, cudaStream_t s);
   int crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s);
 
   int deriv_v(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);

@@ -35,3 +35,20 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device is visible (there is no CPU fallback)")
     return torch.device("cuda:0")
+
+
+class no_gc_during_collective:
+    """Several emulated ranks are enqueued from ONE host thread: while rank 0's kernels spin (bounded) on flags that
+    rank 1's kernels will raise, the host must not block.  A garbage-collected context from an earlier test would call
+    cudaFree (a device-wide synchronisation) right there, so collect first and keep the collector off meanwhile."""
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        gc.disable()
+
+    def __exit__(self, *a):
+        import gc
+
+        gc.enable()

@@ -11,7 +11,7 @@ import spectral_petsc_b200 as sp
 from spectral_petsc_b200 import dist as spd
 from oracle.elliptic import MatElliptic
 from oracle.fgmres import fgmres
-from conftest import rel_max
+from conftest import rel_max, no_gc_during_collective
 
 pytestmark = pytest.mark.gpu
 
@@ -114,12 +114,13 @@ def test_slab_ksp_two_ranks_in_process(cuda):
                 out[r] = ksp[r].solve(torch.from_numpy(parts[r].copy()).to(cuda)).cpu().numpy()
                 res[r] = ksp[r].result
 
-        torch.cuda.synchronize()
-        th = [threading.Thread(target=run, args=(r,)) for r in range(nr)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join(timeout=120)
+        with no_gc_during_collective():
+            torch.cuda.synchronize()
+            th = [threading.Thread(target=run, args=(r,)) for r in range(nr)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join(timeout=120)
         assert all(o is not None for o in out)
         assert res[0]["its"] == res[1]["its"] and res[0]["rnorm"] == res[1]["rnorm"]  # same bits on every rank
         assert res[0]["reason"] == reason_o and abs(res[0]["its"] - its_o) <= 1

@@ -12,7 +12,7 @@ import torch
 import spectral_petsc_b200 as sp
 from spectral_petsc_b200 import dist as spd
 from oracle.elliptic import MatElliptic
-from conftest import rel_max
+from conftest import rel_max, no_gc_during_collective
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -42,12 +42,13 @@ class Ranks:
     def each(self, fn):
         """Enqueue fn(rank, ctx) for every rank on its own stream (no host sync in between: a rank's
         kernels wait for the peers' kernels on the device)."""
-        torch.cuda.synchronize()
         out = []
-        for r in range(self.n):
-            with torch.cuda.stream(self.streams[r]):
-                out.append(fn(r, self.ctx[r]))
-        torch.cuda.synchronize()
+        with no_gc_during_collective():
+            torch.cuda.synchronize()
+            for r in range(self.n):
+                with torch.cuda.stream(self.streams[r]):
+                    out.append(fn(r, self.ctx[r]))
+            torch.cuda.synchronize()
         return out
 
 

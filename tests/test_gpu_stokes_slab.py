@@ -8,7 +8,7 @@ import torch
 import spectral_petsc_b200 as sp
 from spectral_petsc_b200 import dist as spd
 from oracle.stokes import StokesCtx
-from conftest import rel_max
+from conftest import rel_max, no_gc_during_collective
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -35,16 +35,20 @@ def setup(dim, nranks, rheology, cuda, exponent=3.0, eps=1e-2):
 
 
 def each(ctx, streams, fn):
-    torch.cuda.synchronize()
     out = []
-    for r, c in enumerate(ctx):
-        with torch.cuda.stream(streams[r]):
-            out.append(fn(r, c))
-    torch.cuda.synchronize()
+    with no_gc_during_collective():
+        torch.cuda.synchronize()
+        for r, c in enumerate(ctx):
+            with torch.cuda.stream(streams[r]):
+                out.append(fn(r, c))
+        torch.cuda.synchronize()
     return np.concatenate([o.cpu().numpy() for o in out])
 
 
-CASES = [([8, 6], 2, 0), ([8, 6], 2, 1), ([12, 7, 6], 2, 1), ([12, 7, 6], 3, 0), ([16, 16, 16], 4, 1), ([16, 10, 12], 8, 1), ([20, 20, 20], 2, 1)]
+# [16..], [32..] with equal extents take the pencil (transpose) path for axis 0 + batched even-odd launches; the others
+# the operand-pull path with the generic kernels
+CASES = [([8, 6], 2, 0), ([8, 6], 2, 1), ([12, 7, 6], 2, 1), ([12, 7, 6], 3, 0), ([16, 16, 16], 4, 1), ([16, 10, 12], 8, 1), ([20, 20, 20], 2, 1),
+         ([16, 16], 2, 1), ([32, 32, 32], 2, 1), ([32, 32, 32], 8, 0), ([16, 16, 16], 8, 1)]
 
 
 @pytest.mark.parametrize("dim,nranks,rheology", CASES, ids=lambda v: str(v))
