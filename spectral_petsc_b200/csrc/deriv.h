@@ -39,5 +39,7 @@ struct SymmArena;
 // Transpose-based derivative along the partitioned axis of a slab-distributed field (slab_deriv.cu).
 bool slab_deriv0_pencil_supported(const SymmArena& a, const DerivParams& p);
 int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, double* Yp, cudaStream_t s);
+int slab_deriv0_pencil_begin(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, cudaStream_t s);
+int slab_deriv0_pencil_finish(SymmArena& a, const DerivParams& p, int nloc, double* Xp, double* Yp, cudaStream_t s);
 
 }  // namespace sb200

@@ -34,7 +34,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 
 // out[j] = sum_i x[i] * Y[j*ldy + i],  j in [0, nv).  grid = (nblocks, ceil(nv / CH)).
 __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x, const double* __restrict__ Y, long long ldy, int nv,
-                                                   long long n, double* __restrict__ partial, unsigned* counters, double* __restrict__ out) {
+                                                   long long n, double* __restrict__ partial, unsigned* counters, double* __restrict__ out,
+                                                   int vec2) {
   __shared__ double sm[TPB / 32];
   __shared__ bool last;
   const int j0 = blockIdx.y * CH, cnt = min(CH, nv - j0);
@@ -42,11 +43,33 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
 #pragma unroll
   for (int jj = 0; jj < CH; jj++) acc[jj] = 0.0;
   const long long stride = (long long)gridDim.x * TPB;
-  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-    const double xi = x[i];
+  if (vec2) {
+    // 16-byte loads: every pointer is 16-byte aligned and ldy is even (checked on the host)
+    const long long n2 = n >> 1;
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
+    for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n2; i += stride) {
+      const double2 xi = x2[i];
 #pragma unroll
-    for (int jj = 0; jj < CH; jj++)
-      if (jj < cnt) acc[jj] = fma(xi, Y[(long long)(j0 + jj) * ldy + i], acc[jj]);
+      for (int jj = 0; jj < CH; jj++)
+        if (jj < cnt) {
+          const double2 yv = reinterpret_cast<const double2*>(Y + (long long)(j0 + jj) * ldy)[i];
+          acc[jj] = fma(xi.x, yv.x, acc[jj]);
+          acc[jj] = fma(xi.y, yv.y, acc[jj]);
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const double xi = x[n - 1];
+#pragma unroll
+      for (int jj = 0; jj < CH; jj++)
+        if (jj < cnt) acc[jj] = fma(xi, Y[(long long)(j0 + jj) * ldy + n - 1], acc[jj]);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+      const double xi = x[i];
+#pragma unroll
+      for (int jj = 0; jj < CH; jj++)
+        if (jj < cnt) acc[jj] = fma(xi, Y[(long long)(j0 + jj) * ldy + i], acc[jj]);
+    }
   }
 #pragma unroll
   for (int jj = 0; jj < CH; jj++) {
@@ -59,11 +82,14 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
   }
   __syncthreads();
   if (last) {
+    // warp jj adds the per-block partials of vector j0+jj: lane-strided loads, then a shuffle tree (fixed order)
     __threadfence();
-    if (threadIdx.x < cnt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < cnt) {
       double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; b++) t += __ldcg(partial + (long long)(j0 + threadIdx.x) * gridDim.x + b);
-      out[j0 + threadIdx.x] = t;
+      for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (long long)(j0 + warp) * gridDim.x + b);
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) out[j0 + warp] = t;
     }
     if (threadIdx.x == 0) counters[blockIdx.y] = 0;
   }
@@ -72,7 +98,7 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
 // y[i] += sign * sum_j c[j] * Y[j*ldy + i];  optionally out_nrm2 = sum_i y[i]^2 (of the updated y).
 __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, const double* __restrict__ Y, long long ldy, int nv,
                                                     const double* __restrict__ c, double sign, long long n, double* __restrict__ partial,
-                                                    unsigned* counter, double* __restrict__ out_nrm2) {
+                                                    unsigned* counter, double* __restrict__ out_nrm2, int vec2) {
   __shared__ double sm[TPB / 32];
   __shared__ double cs[64];
   __shared__ bool last;
@@ -80,11 +106,34 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
   __syncthreads();
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * TPB;
-  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-    double v = y[i];
-    for (int j = 0; j < nv; j++) v = fma(cs[j], Y[(long long)j * ldy + i], v);
-    y[i] = v;
-    acc = fma(v, v, acc);
+  if (vec2) {
+    const long long n2 = n >> 1;
+    double2* __restrict__ y2 = reinterpret_cast<double2*>(y);
+    for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n2; i += stride) {
+      double2 v = y2[i];
+#pragma unroll 4
+      for (int j = 0; j < nv; j++) {
+        const double2 yv = reinterpret_cast<const double2*>(Y + (long long)j * ldy)[i];
+        v.x = fma(cs[j], yv.x, v.x);
+        v.y = fma(cs[j], yv.y, v.y);
+      }
+      y2[i] = v;
+      acc = fma(v.x, v.x, acc);
+      acc = fma(v.y, v.y, acc);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      double v = y[n - 1];
+      for (int j = 0; j < nv; j++) v = fma(cs[j], Y[(long long)j * ldy + n - 1], v);
+      y[n - 1] = v;
+      acc = fma(v, v, acc);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+      double v = y[i];
+      for (int j = 0; j < nv; j++) v = fma(cs[j], Y[(long long)j * ldy + i], v);
+      y[i] = v;
+      acc = fma(v, v, acc);
+    }
   }
   if (!out_nrm2) return;
   const double t = block_sum(acc, sm);
@@ -94,12 +143,15 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
     last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {
     __threadfence();
     double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(partial + b);
-    *out_nrm2 = s;
-    *counter = 0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += TPB) s += __ldcg(partial + b);
+    const double tot = block_sum(s, sm);
+    if (threadIdx.x == 0) {
+      *out_nrm2 = tot;
+      *counter = 0;
+    }
   }
 }
 
@@ -236,7 +288,9 @@ int KspCtx::create(long long n, int restart, int rank, int nranks, KspCtx** out)
 int KspCtx::init(long long n_, int restart_, int rank, int nranks) {
   n = n_;
   restart = restart_;
-  const size_t nb = (size_t)(n > 0 ? n : 1) * sizeof(double);
+  ldv = (n + 1) & ~1ll;  // even leading dimension: every basis vector starts 16-byte aligned
+  if (ldv < 2) ldv = 2;
+  const size_t nb = (size_t)ldv * sizeof(double);
   SB_CUDA(cudaMalloc((void**)&V, nb * (restart + 1)));
   SB_CUDA(cudaMalloc((void**)&Z, nb * restart));
   SB_CUDA(cudaMalloc((void**)&w, nb));
@@ -290,7 +344,8 @@ int KspCtx::allreduce(double* vals, int k, cudaStream_t s) {
 
 int KspCtx::dots(const double* x, const double* Y, long long ldy, int nv, double* out, cudaStream_t s) {
   dim3 grid(nblocks, (nv + CH - 1) / CH);
-  mdot_kernel<<<grid, TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out);
+  const int vec2 = (reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(Y) % 16 == 0 && ldy % 2 == 0) ? 1 : 0;
+  mdot_kernel<<<grid, TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return allreduce(out, nv, s);
@@ -302,7 +357,9 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
   SB_CHECK(op, SB200_ERR_USER, "KSP: no operator set (KSPSetOperators)");
   SB_CHECK(b && x && b != x, SB200_ERR_ARG, "KSPSolve: b and x must be distinct non-null vectors");
   const SmallPtrs sp = SmallPtrs::make(small, restart);
-  const long long ld = n;
+  const long long ld = ldv;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const int vx = al16(x) ? 1 : 0;  // V, Z, w are 256-byte aligned with an even leading dimension
   const int g1 = nblocks;
   its = 0;
   reason = 0;
@@ -355,7 +412,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
       SB_TRY(op(op_ctx, zk, w, (void*)s));
       SB_CUDA(cudaEventRecord(ev[2], s));
       SB_TRY(dots(w, V, ld, k + 1, sp.hcol, s));  // classical Gram-Schmidt: all projections at once
-      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, k + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (k + 1));
+      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, k + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (k + 1), 1);
       count_launch();
       SB_TRY(allreduce(sp.hcol + (k + 1), 1, s));
       hess_kernel<<<1, 1, 0, s>>>(sp, k, sp.scr + 3, d_rnorm);
@@ -392,7 +449,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
     // x += Z y with R y = g
     backsolve_kernel<<<1, 1, 0, s>>>(sp, k);
     count_launch();
-    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr);
+    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr, vx);
     count_launch();
     SB_CUDA(cudaGetLastError());
     if (done) break;

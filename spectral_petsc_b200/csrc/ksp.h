@@ -17,6 +17,7 @@ namespace sb200 {
 
 struct KspCtx {
   long long n = 0;     // local vector length
+  long long ldv = 0;   // leading dimension of the Krylov bases (n rounded up to even)
   int restart = 30;    // KSPGMRESSetRestart default
   double rtol = 1e-5, atol = 1e-50, dtol = 1e5;  // KSP defaults
   int maxits = 10000;

@@ -78,19 +78,25 @@ bool slab_deriv0_pencil_supported(const SymmArena& a, const DerivParams& p) {
 }
 
 // p: the slab-local description (x, y local arena arrays of this rank; O == 1; P = global extent; R columns).
-// Xp, Yp: arena arrays of at least P * R / nranks doubles.
-int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, double* Yp, cudaStream_t s) {
+// Xp, Yp: arena arrays of at least P * R / nranks doubles.  Split in two so that the caller can put independent local
+// work between the operand push and the point where the peers' planes are needed.
+int slab_deriv0_pencil_begin(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, cudaStream_t s) {
   SB_CHECK(a.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
   const int G = a.nranks;
   const long long R = p.R, Rp = R / G;
-  PushPtrs px, py;
-  for (int q = 0; q < SB200_MAX_RANKS; q++) {
-    px.dst[q] = q < G ? a.on(q, Xp) : nullptr;
-    py.dst[q] = q < G ? a.on(q, p.y) : nullptr;
-  }
+  PushPtrs px;
+  for (int q = 0; q < SB200_MAX_RANKS; q++) px.dst[q] = q < G ? a.on(q, Xp) : nullptr;
   push_to_pencils_kernel<<<blocks_for((long long)nloc * R), 256, 0, s>>>(p.x, p.xs, p.xoff, px, nloc, i0, R, Rp);
   count_launch();
   SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int slab_deriv0_pencil_finish(SymmArena& a, const DerivParams& p, int nloc, double* Xp, double* Yp, cudaStream_t s) {
+  const int G = a.nranks;
+  const long long R = p.R, Rp = R / G;
+  PushPtrs py;
+  for (int q = 0; q < SB200_MAX_RANKS; q++) py.dst[q] = q < G ? a.on(q, p.y) : nullptr;
   SB_TRY(a.barrier(s));
   DerivParams lp = p;  // the pencil: all P planes of Rp columns, unit stride
   lp.x = Xp;
@@ -106,6 +112,11 @@ int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, dou
   count_launch();
   SB_CUDA(cudaGetLastError());
   return a.barrier(s);
+}
+
+int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, double* Yp, cudaStream_t s) {
+  SB_TRY(slab_deriv0_pencil_begin(a, p, nloc, i0, Xp, s));
+  return slab_deriv0_pencil_finish(a, p, nloc, Xp, Yp, s);
 }
 
 }  // namespace sb200

@@ -561,9 +561,15 @@ bool StokesCtx::batchable() const {
 // goes through the pencils (two pushes over NVLink), the local axes run as one batch.
 int StokesCtx::run_jobs(DerivParams* jobs, int d, cudaStream_t s) {
   if (arena.nranks == 1) return deriv_eo_batch(jobs, d, sync, s);
-  SB_TRY(deriv_common(jobs[0], 0, s));
+  if (!slab_deriv0_pencil_supported(arena, jobs[0])) {
+    SB_TRY(deriv_common(jobs[0], 0, s));
+    if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
+    return 0;
+  }
+  // push the operand planes, do the local axes while they cross NVLink, then differentiate the pencil and push back
+  SB_TRY(slab_deriv0_pencil_begin(arena, jobs[0], gd.dim[0], gd.i0, Xp, s));
   if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
-  return 0;
+  return slab_deriv0_pencil_finish(arena, jobs[0], gd.dim[0], Xp, Yp, s);
 }
 
 int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s) {
