@@ -393,11 +393,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   load_matrices<P>(sm, p.Ae, p.Bo);
   if (SLAB && threadIdx.x == 0) tl_stamp(p, LASTPHASE ? 5 : 0);
 
+  // First ticket: static, strided over the CTAs first (warp w of CTA c takes w * gridDim.x + c), so that with fewer
+  // items than warps (a slab rank at 4 or 8 GPUs) every SM sub-partition gets at most one busy warp instead of the
+  // first CTAs taking everything.  Later tickets come from the global counter, which starts behind the static ones.
+  const unsigned nstatic = gridDim.x * NWARPS;
   auto grab = [&]() -> unsigned {
     unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(sync, 1u);
+    if (lane == 0) tk = atomicAdd(sync, 1u) + nstatic;
     return __shfl_sync(0xffffffffu, tk, 0);
   };
+  const unsigned first_ticket = warp * gridDim.x + blockIdx.x;
   bool peers_ready = false;
   auto issue_load = [&](unsigned tk) {
     if (tk >= total) return;
@@ -433,10 +438,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     // a first ticket may be a pencil item that waits for the peers: never hold the CTA barrier behind it
     cp_async_wait<0>();
     __syncthreads();
-    tk = grab();
+    tk = first_ticket;
     issue_load(tk);
   } else {
-    tk = grab();
+    tk = first_ticket;
     issue_load(tk);
     cp_async_wait<0>();
     __syncthreads();  // matrices visible to all warps (the only CTA-wide barrier)

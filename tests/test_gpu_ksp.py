@@ -93,7 +93,7 @@ def test_slab_ksp_two_ranks_in_process(cuda):
     the dot products go through the peer-memory all-reduce; counts and solution equal the single-domain solve."""
     import os
 
-    os.environ["SB200_MAX_CTAS"] = "12"
+    os.environ["SB200_MAX_CTAS"] = "6"
     try:
         dim, nr = [16, 16, 16], 2
         O = MatElliptic(dim, gamma=0.0)
