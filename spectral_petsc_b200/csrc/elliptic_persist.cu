@@ -209,6 +209,20 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     // last axis: phase A (all partials) must be complete and visible, then
     // V = crop(((0 - p_0) - p_1 ...) - D f)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (WAITDONE && p.merged) {
+      // same launch as the local axes: their partials are complete once every local item has checked in
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned*>(p.sync + 6) < p.nlocal_items) {
+          if (clock64() - t0 > SB200_SPIN_LIMIT) {
+            atomicAdd(p.sf.f[p.rank] + SYMM_TIMEOUT, 1ull);
+            break;
+          }
+        }
+        __threadfence();
+      }
+      __syncwarp();
+    }
     if (WAITDONE && !(p.xflags & 8)) {
       if (lane == 0) tl_stamp(p, 6);
       if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_DONE + lane, p.epoch, p.sf.f[p.rank]);
@@ -371,8 +385,14 @@ __global__ void __launch_bounds__(128, 6) stage_kernel(PersistParams p) {
   }
 }
 
+// Register budget: one CTA per SM.  The slab phase-A / merged kernel keeps ~9.7K registers of the SM free so that
+// the blocks of the stage kernel (128 threads x 76 registers) can share the SM with it (PDL overlap).
+constexpr int persist_maxreg(int nwarps, bool slab_a) {
+  return nwarps > 8 ? (65536 / (nwarps * 32)) / 8 * 8 : (slab_a ? 216 : 255);
+}
+
 template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
-__global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p) {
+__global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_kernel(PersistParams p) {
   using E = EO<P>;
   extern __shared__ double sm[];
   double* Ae = sm;
@@ -387,7 +407,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   // arrived (tickets [nlocal, total))
   const unsigned items0 = (SLAB && !LASTPHASE) ? (unsigned)(p.Rp / (8 * NT)) : 0u;
   const unsigned nlocal = LASTPHASE ? items_per_axis : items_per_axis * (p.d - 1 - p.first_axis);
-  const unsigned total = nlocal + items0;
+  const bool merged = SLAB && !LASTPHASE && p.merged;
+  const unsigned total = nlocal + items0 + (merged ? items_per_axis : 0u);  // merged: the last-axis items come last
   if (!LASTPHASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   load_matrices<P>(sm, p.Ae, p.Bo);
@@ -406,6 +427,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
   bool peers_ready = false;
   auto issue_load = [&](unsigned tk) {
     if (tk >= total) return;
+    if (SLAB && !LASTPHASE && tk >= nlocal + items0) {
+      load_item<P, NT, true>(Xw, p.U, p.d, p.d - 1, (long long)(tk - nlocal - items0) * (8 * NT), lane, p.sg);
+      return;
+    }
     if (SLAB && !LASTPHASE && tk >= nlocal) {
       if (!peers_ready && !(p.xflags & 4)) {
         // every rank must have pushed its planes of the padded input into this rank's pencil
@@ -468,7 +493,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     pencil_done = 0;
   };
   while (tk < total) {
-    if (SLAB && !LASTPHASE && tk >= nlocal) {
+    if (SLAB && !LASTPHASE && tk >= nlocal + items0) {
+      if (pencil_done) report_pencils();  // before this warp may block on the other ranks' DONE
+      run_item<P, NT, true, DEEP, false, true>(p, p.d - 1, (long long)(tk - nlocal - items0) * (8 * NT), Ae, Bo, Xw, lane);
+    } else if (SLAB && !LASTPHASE && tk >= nlocal) {
       run_item<P, NT, false, DEEP, true>(p, 0, (long long)(tk - nlocal) * (8 * NT), Ae, Bo, Xw, lane);
       pencil_done++;
     } else {
@@ -477,6 +505,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
       const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
       const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
       run_item<P, NT, LASTPHASE, DEEP, false, SLAB && LASTPHASE>(p, axis, n0, Ae, Bo, Xw, lane);
+      if (merged) {
+        __threadfence();  // this item's partial rows are visible device-wide before it checks in
+        __syncwarp();
+        if (lane == 0) atomicAdd(sync + 6, 1u);
+      }
     }
     tk = grab();
     issue_load(tk);  // run_item waits for it at its top
@@ -489,6 +522,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) persist_kernel(PersistParams p
     if (gone == gridDim.x * NWARPS - 1) {
       sync[0] = 0;
       sync[1] = 0;
+      if (merged) sync[6] = 0;
       if (SLAB) tl_stamp(p, LASTPHASE ? 9 : 8);
     }
   }
@@ -503,7 +537,7 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
     attr = true;
   }
   long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
-  if (SLAB && !LASTPHASE) items += p.Rp / (8 * NT);
+  if (SLAB && !LASTPHASE) items += p.Rp / (8 * NT) + (p.merged ? p.nlines / (8 * NT) : 0);
   if (items <= 0) return 0;
   // one persistent CTA per SM; with fewer items than warps spread them over all SMs (a warp alone on its
   // SM sub-partition issues DMMAs ~1.5x faster than two sharing it)
@@ -546,8 +580,9 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
       count_launch();
       SB_CUDA(cudaGetLastError());
     }
+    p.nlocal_items = (unsigned)(p.nlines / (8 * NT) * (p.d - 1 - p.first_axis));
     SB_TRY((launch_phase<P, NWARPS, NT, false, true>(p, smem, sms, s)));
-    SB_TRY((launch_phase<P, NWARPS, NT, true, true>(p, smem, sms, s)));
+    if (!p.merged) SB_TRY((launch_phase<P, NWARPS, NT, true, true>(p, smem, sms, s)));
     return 0;
   }
   SB_TRY((launch_phase<P, NWARPS, NT, false, false>(p, smem, sms, s)));

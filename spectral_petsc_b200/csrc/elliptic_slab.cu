@@ -128,6 +128,16 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   p.sf = sf;
   p.epoch = epoch;
   {
+    // one launch for all axes (the last axis waits for the local items by a counter and for the peers by DONE) or the
+    // two PDL-chained phases of the single-GPU kernel: SB200_SLAB_MERGED = 0 / 1, default merged
+    static int merged = -1;
+    if (merged < 0) {
+      const char* c = getenv("SB200_SLAB_MERGED");
+      merged = c ? atoi(c) : 1;
+    }
+    p.merged = merged;
+  }
+  {
     static long long tl = -1;
     if (tl < 0) {
       const char* c = getenv("SB200_TL_EPOCH");

@@ -41,6 +41,8 @@ struct PersistParams {
   long long R0, Rp;                     // lines per plane; lines per pencil (R0 / nranks)
   SymmFlags sf;
   unsigned long long epoch;             // READY / DONE flag value of this application
+  int merged;                           // slab: the last-axis items run in the same launch as phase A (no phase B launch)
+  unsigned nlocal_items;                // merged: local (non-pencil, non-last-axis) items whose partials the last axis reads
   unsigned long long tl_epoch;          // debug timeline: the application to stamp (SB200_TL_EPOCH)
   int stagger;       // start delay per warp group, in clocks
   int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
