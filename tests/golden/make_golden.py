@@ -1,9 +1,8 @@
 """Regenerates tests/golden/*.npz from the oracle (run from the repo root: python tests/golden/make_golden.py).
 
-The reference itself cannot be built in this image (needs FFTW, PETSc ~3.0, mpicxx, CppAD), so
-these vectors are outputs of the ORACLE restatement on seeded inputs - they pin the oracle against drift and give the
-CUDA path fixed vectors to hit, but they are not reference outputs: parity stays "unpinned" beyond the reference's own
-analytic known-answer tests (cheb.c, -exact 1/2), which tests/test_oracle_*.py check.
+These vectors are outputs of the ORACLE restatement on seeded inputs.  tests/test_oracle_ref*.py check them against the
+reference's own chebyshev.c / elliptic.C / stokes.C (compiled against FFTW / PETSc stand-ins, oracle/_ref):
+the cheb, elliptic and stokes vectors here equal what the reference source produces to 1e-12 or better.
 """
 import os
 import sys
