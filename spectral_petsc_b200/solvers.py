@@ -146,6 +146,35 @@ def newton(function, solve_jacobian, x0, rtol=1e-8, atol=1e-50, max_it=50, norm=
     return x, its, kits, hist
 
 
+def continuation_params(i, cont, exponent, regularization):
+    """Step i of the continuation loop (stokes.C:217-219): exponent_i = 1 + (i/cont)^0.8 (n - 1), eps_i = exp(log(eps) i/cont)."""
+    import math
+
+    t = 1.0 * i / cont
+    return 1.0 + math.pow(t, 0.8) * (exponent - 1.0), math.exp(math.log(regularization) * i / cont)
+
+
+def solve_stokes_continuation(function, set_rheology, make_saddle_pc, shells, d, krylov, x0, exponent, regularization, cont=1, cont0=0,
+                              ksp_rtol=1e-5, snes_rtol=1e-8, ksp_maxits=10000, snes_max_it=50):
+    """The solve loop of stokes.C:214-236: for i = cont0..cont set the rheology of step i, run SNES from the previous solution.
+    function(x): the residual (refreshes the Jacobian state); set_rheology(exponent_i, eps_i); make_saddle_pc(): a
+    StokesSaddlePC for the current state (the velocity-block PC matrix is assembled by the caller, PETSc's side).
+    Returns (x, [per-step dict with the parameters, SNES iterations, KSP iterations per Newton step, residual norms])."""
+    x, log = x0, []
+    for i in range(cont0, cont + 1):
+        e, r = continuation_params(i, cont, exponent, regularization)
+        set_rheology(e, r)
+
+        def solve_jacobian(rhs):
+            pc = make_saddle_pc()
+            dx, its, _ = solve_stokes_linear(shells, d, krylov, pc, rhs, rtol=ksp_rtol, maxits=ksp_maxits)
+            return dx, its
+
+        x, its, kits, hist = newton(function, solve_jacobian, x, rtol=snes_rtol, max_it=snes_max_it)
+        log.append({"step": i, "exponent": e, "regularization": r, "snes_its": its, "ksp_its": kits, "fnorm": hist})
+    return x, log
+
+
 def make_gpu_krylov():
     """krylov engine over the device FGMRES (spectral_petsc_b200.KSP); one solver object per (n, restart)."""
     from .capi import KSP

@@ -78,3 +78,43 @@ def test_newton_elliptic_nonlinear_matches_oracle(cuda):
     assert abs(its - its_o) <= 1  # SNES iteration count
     assert all(abs(a - b) <= 1 for a, b in zip(kits, kits_o))  # KSP iteration counts per Newton step
     assert np.abs(x.cpu().numpy() - u).max() < 1e-9 and abs(np.abs(x.cpu().numpy() - u).max() - np.abs(xo - u).max()) < 1e-10
+
+
+def test_config5_power_law_continuation_matches_oracle(cuda):
+    """./stokes -exact 2 -cont 4 -rheology 1 -eps 1e-4 -exponent 3 (README:55, BASELINE config 5) at a small extent: the five SNES
+    solves of the continuation take the same numbers of Newton and Krylov iterations on the CUDA shells as on the oracle."""
+    dim = [8, 8, 8]
+    kw = dict(rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0)
+    O = StokesCtx(dim, exact=2, **kw)
+    O.create_exact_solution()
+
+    def pc_o():
+        return solvers.StokesSaddlePC(O, 3, np_krylov, spla.splu(O.pc_velocity_matrix().tocsc()).solve, saddle_type=0)
+
+    xo, log_o = solvers.solve_stokes_continuation(O.function, O.set_rheology, pc_o, O, 3, np_krylov, np.zeros(O.g), 3.0, 1e-4, cont=4,
+                                                  ksp_rtol=1e-6, snes_rtol=1e-8, ksp_maxits=300)
+
+    S = sp.Stokes(dim, **kw)
+    S.set_dirichlet(torch.from_numpy(O.dirichlet.reshape(-1).copy()).to(cuda))
+    S.set_force(torch.from_numpy(O.force).to(cuda))
+    H = StokesCtx(dim, exact=2, **kw)  # host-side StokesPCSetUp0 input: the viscosity the GPU residual cached
+    gk = solvers.make_gpu_krylov()
+
+    def pc_g():
+        H.eta = S.get_state(0).cpu().numpy()
+        lu = spla.splu(H.pc_velocity_matrix().tocsc())
+        return solvers.StokesSaddlePC(S, 3, gk, lambda r: torch.from_numpy(lu.solve(r.cpu().numpy())).to(cuda), saddle_type=0)
+
+    x, log = solvers.solve_stokes_continuation(lambda v: S.function(v).clone(), lambda e, r: S.set_rheology(1, 1.0, e, r, 1.0), pc_g, S, 3, gk,
+                                               torch.zeros(S.g, dtype=torch.float64, device=cuda), 3.0, 1e-4, cont=4,
+                                               ksp_rtol=1e-6, snes_rtol=1e-8, ksp_maxits=300)
+    assert len(log) == len(log_o) == 5
+    for a, b in zip(log, log_o):
+        assert abs(a["snes_its"] - b["snes_its"]) <= 1, (a, b)
+        for ka, kb in zip(a["ksp_its"], b["ksp_its"]):
+            assert abs(ka - kb) <= 1 + kb // 10, (a, b)
+    xv, _ = solvers.split(x.cpu().numpy(), 3)
+    xov, _ = solvers.split(xo, 3)
+    assert np.abs(xv - xov).max() < 1e-6 * max(np.abs(xov).max(), 1.0)
+    mn, mx = S.eta_minmax()
+    assert mn == pytest.approx(O.min_eta, rel=1e-6) and mx == pytest.approx(O.max_eta, rel=1e-6)

@@ -66,3 +66,29 @@ def test_newton_elliptic_nonlinear():
     assert its <= 12 and hist[-1] <= 1e-12 * hist[0]
     assert np.abs(x - u).max() < 1e-9  # "Norm of error"
     assert all(h2 < h1 for h1, h2 in zip(hist, hist[1:]))
+
+
+def test_config5_power_law_continuation_small():
+    """./stokes -exact 2 -cont 4 -rheology 1 -eps 1e-4 -exponent 3 ... (README:55) at a small extent: five SNES solves, the first
+    one linear, each started from the previous solution; every step converges and the viscosity contrast grows."""
+    from oracle.stokes import continuation_params as oracle_params
+
+    dim = [8, 8, 8]
+    O = StokesCtx(dim, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0, exact=2)
+    O.create_exact_solution()
+    for i in range(5):  # the product-side formula equals the oracle's restatement of stokes.C:217-219
+        assert solvers.continuation_params(i, 4, 3.0, 1e-4) == pytest.approx(oracle_params(i, 4, 3.0, 1e-4), rel=1e-15)
+
+    def make_pc():
+        lu = spla.splu(O.pc_velocity_matrix().tocsc())
+        return solvers.StokesSaddlePC(O, 3, np_krylov, lu.solve, saddle_type=0)
+
+    x, log = solvers.solve_stokes_continuation(O.function, O.set_rheology, make_pc, O, 3, np_krylov, np.zeros(O.g), 3.0, 1e-4, cont=4,
+                                               ksp_rtol=1e-6, snes_rtol=1e-8, ksp_maxits=300)
+    assert [s["step"] for s in log] == [0, 1, 2, 3, 4]
+    assert log[0]["exponent"] == 1.0 and log[-1]["exponent"] == pytest.approx(3.0) and log[-1]["regularization"] == pytest.approx(1e-4)
+    assert log[0]["snes_its"] <= 2  # the linear problem
+    for s in log:
+        assert s["fnorm"][-1] <= 1e-8 * s["fnorm"][0] * 1.01 or s["fnorm"][-1] < 1e-10, s
+        assert s["snes_its"] <= 30
+    assert O.max_eta / O.min_eta > 3.0  # shear-thinning state at the end (stokes.C:731-734 prints these)
