@@ -27,4 +27,16 @@ def test_slab_multi_process(world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
     assert out.returncode == 0, out.stderr[-2000:]
-    assert len(lines) == 2 and all(l["ok"] and l["ranks"] == world for l in lines)
+    assert len(lines) == 3 and all(l["ok"] and l["ranks"] == world for l in lines)  # slab at 32 and 64, slab KSP at 32
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_stokes_slab_multi_process(world):
+    if _ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29720 + world), os.path.join(ROOT, "tools", "dist_stokes.py"), "16", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert len(lines) == 1 and lines[0]["ok"] and lines[0]["ranks"] == world

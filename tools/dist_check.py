@@ -57,6 +57,29 @@ def main():
         if rank == 0:
             print(json.dumps({"check": "slab", "P": P, "ranks": world, "function_rel": e[0], "matmult_fused_rel": e[1],
                               "matmult_generic_rel": e[2], "repeat_differs": e[3], "flag_timeouts": e[4], "ok": good}), flush=True)
+        if P <= 32:
+            # slab-partitioned FGMRES: dot products through the peer-memory all-reduce; counts equal the single-domain oracle solve
+            from oracle.fgmres import fgmres  # checker only
+
+            b = np.random.default_rng(3).standard_normal(O.g)
+            xo, its_o, hist_o, reason_o = fgmres(O.mat_mult, b, rtol=1e-6, maxits=60)
+            C.set_path(0)
+            K = sp.KSP(C.g, rank=rank, nranks=world)
+            spd.attach_peers(K)
+            K.set_operators(C)
+            K.set_tolerances(rtol=1e-6, maxits=60)
+            x = K.solve(torch.from_numpy(b[sl].copy()).to(dev)).cpu().numpy()
+            r = K.result
+            kerr = torch.tensor([rel(x, xo[sl]) if reason_o == 2 else 0.0, float(abs(r["its"] - its_o)), float(r["reason"] != reason_o)],
+                                dtype=torch.float64, device=dev)
+            dist.all_reduce(kerr, op=dist.ReduceOp.MAX)
+            ke = kerr.tolist()
+            kgood = ke[0] < 1e-5 and ke[1] <= 1 and ke[2] == 0
+            ok = ok and kgood
+            if rank == 0:
+                print(json.dumps({"check": "slab_ksp", "P": P, "ranks": world, "its": r["its"], "its_oracle": its_o, "x_rel": ke[0], "ok": kgood}), flush=True)
+            dist.barrier()
+            K.destroy()
         C.destroy()
     dist.barrier()
     dist.destroy_process_group()
