@@ -76,6 +76,17 @@ int sb200_elliptic_set_rhs(sb200_elliptic* e, const double* d_b, void* stream);
 /* MatMult_Elliptic(A, U, V) (elliptic.C:297-339): Jacobian action, U and V of g doubles. */
 int sb200_elliptic_matmult(sb200_elliptic* e, const double* d_U, double* d_V, void* stream);
 int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V);
+/* Queued host-buffer form of the same call for callers that apply the operator to a stream of host vectors
+ * (block Krylov right-hand sides, the bench's end-to-end leg): submit() enqueues copy-in -> MatMult_Elliptic ->
+ * copy-out on three streams of the context and returns at once; wait() blocks until the OLDEST submitted
+ * application has landed in its h_V.  At most SB200_HOST_QUEUE_DEPTH applications are in flight (submit() then
+ * fails with SB200_ERR_USER), each through its own device vectors, so the copy-in of one overlaps the kernels
+ * and the copy-out of its predecessors (PCIe is full duplex).  h_U / h_V should be pinned and must stay valid
+ * and untouched until the matching wait(); drain the queue before any other call on this context. */
+#define SB200_HOST_QUEUE_DEPTH 4
+int sb200_elliptic_matmult_host_submit(sb200_elliptic* e, const double* h_U, double* h_V);
+int sb200_elliptic_matmult_host_wait(sb200_elliptic* e);
+int sb200_elliptic_matmult_host_pending(const sb200_elliptic* e, int* pending);
 /* FormFunction(snes, U, rhs, ctx) (elliptic.C:481-533): residual; refreshes eta/deta/gradu caches. */
 int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream);
 int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F);

@@ -197,6 +197,31 @@ class Elliptic:
         _ck(lib().sb200_elliptic_function_host(self._h, _hptr(U), _hptr(F)))
         return F
 
+    HOST_QUEUE_DEPTH = 4  # SB200_HOST_QUEUE_DEPTH
+
+    def mat_mult_host_submit(self, U, V):
+        """Queued host-buffer MatMult (sb200_elliptic_matmult_host_submit): U, V are numpy views of (pinned) host
+        memory that must stay alive and untouched until the matching mat_mult_host_wait()."""
+        assert U.size == self.g and V.size == self.g
+        _ck(lib().sb200_elliptic_matmult_host_submit(self._h, _hptr(U), _hptr(V)))
+
+    def mat_mult_host_wait(self):
+        _ck(lib().sb200_elliptic_matmult_host_wait(self._h))
+
+    def mat_mult_host_pending(self):
+        n = ctypes.c_int()
+        _ck(lib().sb200_elliptic_matmult_host_pending(self._h, ctypes.byref(n)))
+        return n.value
+
+    def mat_mult_host_stream(self, Us, Vs):
+        """Apply the operator to every vector of Us (host arrays) into Vs, keeping the queue full."""
+        for U, V in zip(Us, Vs):
+            if self.mat_mult_host_pending() == self.HOST_QUEUE_DEPTH:
+                self.mat_mult_host_wait()
+            self.mat_mult_host_submit(U, V)
+        while self.mat_mult_host_pending():
+            self.mat_mult_host_wait()
+
     def get_state(self, which):
         import torch
 

@@ -40,6 +40,16 @@ struct sb200_elliptic {
   double* d_out = nullptr;
   double* h_pin_in = nullptr;
   double* h_pin_out = nullptr;
+  // host-buffer queue (sb200_elliptic_matmult_host_submit / _wait): SB200_HOST_QUEUE_DEPTH slots, each with its own
+  // device in / out vectors; copy-in, compute and copy-out run on three non-blocking streams chained by events
+  struct HostSlot {
+    double* d_in = nullptr;
+    double* d_out = nullptr;
+    cudaEvent_t in_done = nullptr, op_done = nullptr, out_done = nullptr;
+  };
+  HostSlot q[SB200_HOST_QUEUE_DEPTH];
+  cudaStream_t q_in = nullptr, q_op = nullptr, q_out = nullptr;
+  long long q_submitted = 0, q_waited = 0;
 };
 
 extern "C" {
@@ -321,6 +331,62 @@ int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_
   return 0;
 }
 
+static int elliptic_host_queue(sb200_elliptic* e) {
+  if (e->q_in) return 0;
+  const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  for (auto& s : e->q) {
+    SB_CUDA(cudaMalloc((void**)&s.d_in, bytes));
+    SB_CUDA(cudaMalloc((void**)&s.d_out, bytes));
+    SB_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&s.op_done, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+  }
+  SB_CUDA(cudaStreamCreateWithFlags(&e->q_op, cudaStreamNonBlocking));
+  SB_CUDA(cudaStreamCreateWithFlags(&e->q_out, cudaStreamNonBlocking));
+  SB_CUDA(cudaStreamCreateWithFlags(&e->q_in, cudaStreamNonBlocking));  // last: its presence marks the queue as built
+  return 0;
+}
+
+int sb200_elliptic_matmult_host_submit(sb200_elliptic* e, const double* h_U, double* h_V) {
+  SB_CHECK(e && h_U && h_V, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(h_U != h_V, SB200_ERR_ARG, "x must not alias y");
+  SB_CHECK(e->q_submitted - e->q_waited < SB200_HOST_QUEUE_DEPTH, SB200_ERR_USER, "host queue full: call sb200_elliptic_matmult_host_wait first");
+  SB_TRY(elliptic_host_queue(e));
+  const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  auto& s = e->q[e->q_submitted % SB200_HOST_QUEUE_DEPTH];
+  if (e->q_submitted == e->q_waited) {
+    // queue idle: order the first application behind whatever the caller enqueued before on the default stream
+    // (FormFunction refreshing eta / deta / gradu), which the non-blocking queue streams would otherwise not see
+    SB_CUDA(cudaEventRecord(s.op_done, 0));
+    SB_CUDA(cudaStreamWaitEvent(e->q_op, s.op_done, 0));
+  }
+  // the slot's previous application was waited for (queue-full check above), so its vectors are free
+  SB_CUDA(cudaMemcpyAsync(s.d_in, h_U, bytes, cudaMemcpyHostToDevice, e->q_in));
+  SB_CUDA(cudaEventRecord(s.in_done, e->q_in));
+  SB_CUDA(cudaStreamWaitEvent(e->q_op, s.in_done, 0));
+  SB_TRY(e->c->matmult(s.d_in, s.d_out, e->q_op));  // the context's scratch is shared: applications serialise on q_op
+  SB_CUDA(cudaEventRecord(s.op_done, e->q_op));
+  SB_CUDA(cudaStreamWaitEvent(e->q_out, s.op_done, 0));
+  SB_CUDA(cudaMemcpyAsync(h_V, s.d_out, bytes, cudaMemcpyDeviceToHost, e->q_out));
+  SB_CUDA(cudaEventRecord(s.out_done, e->q_out));
+  e->q_submitted++;
+  return 0;
+}
+
+int sb200_elliptic_matmult_host_wait(sb200_elliptic* e) {
+  SB_CHECK(e, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(e->q_waited < e->q_submitted, SB200_ERR_USER, "host queue empty: nothing was submitted");
+  SB_CUDA(cudaEventSynchronize(e->q[e->q_waited % SB200_HOST_QUEUE_DEPTH].out_done));
+  e->q_waited++;
+  return 0;
+}
+
+int sb200_elliptic_matmult_host_pending(const sb200_elliptic* e, int* pending) {
+  SB_CHECK(e && pending, SB200_ERR_ARG, "null pointer");
+  *pending = (int)(e->q_submitted - e->q_waited);
+  return 0;
+}
+
 int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F) {
   SB_CHECK(e && h_U && h_F, SB200_ERR_ARG, "null pointer");
   SB_TRY(elliptic_host_staging(e));
@@ -385,6 +451,17 @@ int sb200_elliptic_destroy(sb200_elliptic* e) {
   delete e->c;
   if (e->d_in) cudaFree(e->d_in);
   if (e->d_out) cudaFree(e->d_out);
+  if (e->q_out) cudaStreamSynchronize(e->q_out);  // applications still in flight write into the slots freed below
+  for (auto& s : e->q) {
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.in_done) cudaEventDestroy(s.in_done);
+    if (s.op_done) cudaEventDestroy(s.op_done);
+    if (s.out_done) cudaEventDestroy(s.out_done);
+  }
+  if (e->q_in) cudaStreamDestroy(e->q_in);
+  if (e->q_op) cudaStreamDestroy(e->q_op);
+  if (e->q_out) cudaStreamDestroy(e->q_out);
   delete e;
   return 0;
 }
