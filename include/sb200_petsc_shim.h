@@ -31,6 +31,7 @@ typedef int MPI_Comm;
 typedef struct _p_Vec* Vec;
 typedef struct _p_Mat* Mat;
 typedef struct _p_SNES* SNES;
+typedef struct _p_PC* PC;
 typedef enum { MATOP_MULT = 3, MATOP_GET_DIAGONAL = 17, MATOP_DESTROY = 250 } MatOperation;
 typedef enum { SAME_NONZERO_PATTERN, DIFFERENT_NONZERO_PATTERN } MatStructure;
 
@@ -45,6 +46,16 @@ struct _p_Mat {
   PetscErrorCode (*mult)(Mat, Vec, Vec);
   PetscErrorCode (*getdiagonal)(Mat, Vec);
   PetscErrorCode (*destroy)(Mat);
+  /* MATSEQAIJ created by MatCreateSeqAIJ: device CSR (the MATSEQAIJCUSPARSE layout), filled by FormJacobian /
+   * StokesPCSetUp0; the arrays are allocated at the first assembly, nz = entries stored */
+  int is_aij;
+  PetscInt nz;
+  PetscInt* d_rowptr;
+  PetscInt* d_colidx;
+  PetscScalar* d_vals;
+};
+struct _p_PC {
+  void* ctx; /* PCShell context (stokes.C:163) */
 };
 struct _p_SNES {
   void* appctx;
@@ -71,6 +82,17 @@ PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatGetDiagonal(Mat A, Vec y);
 PetscErrorCode MatGetSize(Mat A, PetscInt* m, PetscInt* n);
 PetscErrorCode MatDestroy(Mat A); /* PETSc 3.0 signature (elliptic.C:235) */
+
+/* SeqAIJ: the preconditioning matrices P (elliptic.C:167) and MatVVPC (stokes.C:326); nz / nnz are accepted and ignored
+ * (the assembling kernel knows the pattern in closed form).  GetCSRHost downloads whatever outputs are non-NULL. */
+PetscErrorCode MatCreateSeqAIJ(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt nz, const PetscInt* nnz, Mat* A);
+PetscErrorCode MatSeqAIJGetCSRHost(Mat A, PetscInt* nz, PetscInt* rowptr, PetscInt* colidx, PetscScalar* vals);
+
+/* PCShell: only the context plumbing StokesPCSetUp0 uses (stokes.C:163-166,1169) */
+PetscErrorCode PCCreate(MPI_Comm comm, PC* pc);
+PetscErrorCode PCShellSetContext(PC pc, void* ctx);
+PetscErrorCode PCShellGetContext(PC pc, void** ctx);
+PetscErrorCode PCDestroy(PC pc);
 
 /* SNES: only the application-context plumbing the callbacks use (elliptic.C:180,604) */
 PetscErrorCode SNESCreate(MPI_Comm comm, SNES* snes);

@@ -34,6 +34,9 @@ PetscErrorCode MatCreate_Elliptic(MPI_Comm comm, int d, int* dim, unsigned flag,
 PetscErrorCode MatMult_Elliptic(Mat A, Vec U, Vec V);
 PetscErrorCode MatDestroy_Elliptic(Mat A);
 PetscErrorCode FormFunction(SNES snes, Vec U, Vec rhs, void* void_ac);
+/* FormJacobian (elliptic.C:537-590): fills the SeqAIJ matrix *P (MatCreateSeqAIJ, elliptic.C:167) on the device from the
+ * eta / deta / gradu the last FormFunction cached; *flag = SAME_NONZERO_PATTERN (:588).  w is not read, as in the reference. */
+PetscErrorCode FormJacobian(SNES snes, Vec w, Mat* A, Mat* P, MatStructure* flag, void* void_ac);
 /* CreateExactSolution(snes, u, u2) (elliptic.C:594-677); -cos_scale is passed explicitly because the
  * reference reads it from the options database without a default (elliptic.C:607-609). */
 PetscErrorCode CreateExactSolution(SNES snes, Vec u, Vec u2, PetscReal cos_scale);
@@ -55,8 +58,12 @@ PetscErrorCode StokesMatMultVP(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y);
 PetscErrorCode StokesFunction(SNES snes, Vec xG, Vec yG, void* ctx);
 PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2);
-/* the inner shells created by StokesCreate (stokes.C:308-325) */
+/* the inner shells created by StokesCreate (stokes.C:308-325) and the SeqAIJ matrix MatVVPC (stokes.C:326) */
 PetscErrorCode StokesGetShells(StokesCtxB200* ctx, Mat* MatVV, Mat* MatPV, Mat* MatVP, Mat* MatSchur);
+PetscErrorCode StokesGetPCMatrix(StokesCtxB200* ctx, Mat* MatVVPC);
+/* StokesPCSetUp0 (stokes.C:1160-1240), the PCShell set-up routine of -pcvel 0 (stokes.C:166): assembles MatVVPC on the device
+ * from the eta the last StokesFunction cached.  The PC shell's context is the Stokes context (stokes.C:163). */
+PetscErrorCode StokesPCSetUp0(PC pc);
 PetscErrorCode StokesSetContinuation(StokesCtxB200* ctx, PetscReal exponent, PetscReal regularization); /* stokes.C:218-219 */
 
 #ifdef __cplusplus

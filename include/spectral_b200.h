@@ -93,6 +93,13 @@ int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h
 /* Cached state read by FormJacobian (elliptic.C:550-553): which = 0 eta, 1 deta, 2+k gradu[k];
  * copies m doubles device->device into d_out. */
 int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* d_out, void* stream);
+/* FormJacobian(snes, w, &A, &P, &flag, ctx) (elliptic.C:537-590): the finite-difference preconditioning matrix P
+ * about the state cached by the last FormFunction (eta, deta, gradu), assembled on the device as CSR with 32-bit
+ * indices (PetscInt): g rows in the global Vec order, columns increasing within a row, Dirichlet neighbours dropped
+ * like MatSetValues drops negative ids.  d_rowptr (nrows+1) and d_colidx (nnz) may both be NULL to refresh the values
+ * alone (the pattern never changes: SAME_NONZERO_PATTERN, elliptic.C:588).  What PC is built from P stays PETSc's. */
+int sb200_elliptic_jacobian_sizes(sb200_elliptic* e, long long* nrows, long long* nnz);
+int sb200_elliptic_jacobian_csr(sb200_elliptic* e, int* d_rowptr, int* d_colidx, double* d_vals, void* stream);
 /* Scatter helpers with the semantics of scatterGL+scatterDL / scatterLG (elliptic.C:426-434). */
 int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream);
 int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, void* stream);
@@ -163,6 +170,11 @@ int sb200_stokes_function_host(sb200_stokes* s, const double* h_x, double* h_y);
 int sb200_stokes_eta_minmax(sb200_stokes* s, double* h_min, double* h_max, void* stream);
 /* Cached state (stokes.C:766): which = 0 eta (m), 1 deta (m), 2+j strain[j] (m*d); device->device copy. */
 int sb200_stokes_get_state(sb200_stokes* s, int which, double* d_out, void* stream);
+/* StokesPCSetUp0 (stokes.C:1160-1240), Dirichlet rows (:1203-1224): the finite-difference velocity matrix MatVVPC about
+ * the eta cached by the last StokesFunction, as device CSR (gv rows, row = interior node * d + component, 32-bit
+ * indices, columns increasing); index arrays may be NULL to refresh the values alone. */
+int sb200_stokes_pc_velocity_sizes(sb200_stokes* s, long long* nrows, long long* nnz);
+int sb200_stokes_pc_velocity_csr(sb200_stokes* s, int* d_rowptr, int* d_colidx, double* d_vals, void* stream);
 /* StokesPressureReduceOrder (stokes.C:1029-1080) applied in place to a local pressure array of m doubles. */
 int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stream);
 /* Slab partition of the Stokes shells over the GPUs of one node (see sb200_elliptic_create_slab): rank r keeps the planes

@@ -73,6 +73,23 @@ def cheb_matrix(P):
     return D
 
 
+def _csr_call(sizes_fn, csr_fn, handle, pattern):
+    """Shared by Elliptic.jacobian_csr / Stokes.pc_velocity_csr: device CSR (int32 rowptr, int32 colidx, fp64 vals)."""
+    import torch
+
+    nrows, nnz = ctypes.c_longlong(), ctypes.c_longlong()
+    _ck(sizes_fn(handle, ctypes.byref(nrows), ctypes.byref(nnz)))
+    vals = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+    if pattern is None:
+        rowptr = torch.empty(nrows.value + 1, dtype=torch.int32, device="cuda")
+        colidx = torch.empty(nnz.value, dtype=torch.int32, device="cuda")
+        _ck(csr_fn(handle, ctypes.c_void_p(rowptr.data_ptr()), ctypes.c_void_p(colidx.data_ptr()), _ptr(vals), _stream()))
+    else:
+        rowptr, colidx = pattern
+        _ck(csr_fn(handle, None, None, _ptr(vals), _stream()))
+    return rowptr, colidx, vals
+
+
 class Cheb:
     """MatCreateCheb(comm, rank, tr, dims, flag, vx, vy, &A): y = ChebMult(A, x)."""
 
@@ -229,6 +246,11 @@ class Elliptic:
         _ck(lib().sb200_elliptic_get_state(self._h, ctypes.c_int(which), _ptr(out), _stream()))
         return out
 
+    def jacobian_csr(self, pattern=None):
+        """FormJacobian (elliptic.C:537-590): the FD preconditioning matrix about the state of the last form_function as
+        device CSR (rowptr, colidx, vals).  pattern=(rowptr, colidx) from an earlier call refreshes the values only."""
+        return _csr_call(lib().sb200_elliptic_jacobian_sizes, lib().sb200_elliptic_jacobian_csr, self._h, pattern)
+
     def pad(self, U, with_dirichlet=False):
         import torch
 
@@ -383,6 +405,10 @@ class Stokes:
         out = torch.empty(n, dtype=torch.float64, device="cuda")
         _ck(lib().sb200_stokes_get_state(self._h, ctypes.c_int(which), _ptr(out), _stream()))
         return out
+
+    def pc_velocity_csr(self, pattern=None):
+        """StokesPCSetUp0 (stokes.C:1160-1240): the FD velocity matrix MatVVPC about the eta of the last function() call."""
+        return _csr_call(lib().sb200_stokes_pc_velocity_sizes, lib().sb200_stokes_pc_velocity_csr, self._h, pattern)
 
     def pressure_reduce_order(self, pL):
         assert pL.numel() == self.m

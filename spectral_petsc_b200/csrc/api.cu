@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "deriv.h"
 #include "elliptic.h"
+#include "fd_assembly.h"
 
 namespace sb200 {
 
@@ -50,6 +51,7 @@ struct sb200_elliptic {
   HostSlot q[SB200_HOST_QUEUE_DEPTH];
   cudaStream_t q_in = nullptr, q_op = nullptr, q_out = nullptr;
   long long q_submitted = 0, q_waited = 0;
+  FdAssembler* fd = nullptr;  // FormJacobian's matrix (built on first use)
 };
 
 extern "C" {
@@ -409,6 +411,26 @@ int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* d_out, void* 
   return 0;
 }
 
+static int elliptic_fd(sb200_elliptic* e) {
+  SB_CHECK(e->c->arena.nranks == 1, SB200_ERR_SUP, "the finite-difference preconditioning matrix is assembled for single-GPU contexts only");
+  if (!e->fd) SB_TRY(FdAssembler::create(e->c->gd.d, e->c->gd.dim, 1, &e->fd));
+  return 0;
+}
+
+int sb200_elliptic_jacobian_sizes(sb200_elliptic* e, long long* nrows, long long* nnz) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  SB_TRY(elliptic_fd(e));
+  if (nrows) *nrows = e->fd->nrows;
+  if (nnz) *nnz = e->fd->nnz;
+  return 0;
+}
+
+int sb200_elliptic_jacobian_csr(sb200_elliptic* e, int* d_rowptr, int* d_colidx, double* d_vals, void* stream) {
+  SB_CHECK(e, SB200_ERR_ARG, "null context");
+  SB_TRY(elliptic_fd(e));
+  return e->fd->assemble(e->c->eta, e->c->deta, e->c->gradu, d_rowptr, d_colidx, d_vals, (cudaStream_t)stream);
+}
+
 int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream) {
   SB_CHECK(e && d_U && d_local, SB200_ERR_ARG, "null pointer");
   return e->c->pad(d_U, with_dirichlet != 0, d_local, (cudaStream_t)stream);
@@ -462,6 +484,7 @@ int sb200_elliptic_destroy(sb200_elliptic* e) {
   if (e->q_in) cudaStreamDestroy(e->q_in);
   if (e->q_op) cudaStreamDestroy(e->q_op);
   if (e->q_out) cudaStreamDestroy(e->q_out);
+  delete e->fd;
   delete e;
   return 0;
 }

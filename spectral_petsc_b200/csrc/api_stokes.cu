@@ -3,6 +3,7 @@
 
 #include "../../include/spectral_b200.h"
 #include "common.cuh"
+#include "fd_assembly.h"
 #include "stokes.h"
 
 using namespace sb200;
@@ -11,6 +12,7 @@ struct sb200_stokes {
   StokesCtx* c = nullptr;
   double* d_in = nullptr;  // staging for *_host
   double* d_out = nullptr;
+  FdAssembler* fd = nullptr;  // StokesPCSetUp0's MatVVPC (built on first use)
 };
 
 extern "C" {
@@ -202,8 +204,29 @@ int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* d_pL, void* stre
   return s->c->pressure_reduce_order(d_pL, (cudaStream_t)stream);
 }
 
+static int stokes_fd(sb200_stokes* s) {
+  SB_CHECK(s->c->arena.nranks == 1, SB200_ERR_SUP, "the finite-difference preconditioning matrix is assembled for single-GPU contexts only");
+  if (!s->fd) SB_TRY(FdAssembler::create(s->c->gd.d, s->c->gd.dim, s->c->gd.d, &s->fd));
+  return 0;
+}
+
+int sb200_stokes_pc_velocity_sizes(sb200_stokes* s, long long* nrows, long long* nnz) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  SB_TRY(stokes_fd(s));
+  if (nrows) *nrows = s->fd->nrows;
+  if (nnz) *nnz = s->fd->nnz;
+  return 0;
+}
+
+int sb200_stokes_pc_velocity_csr(sb200_stokes* s, int* d_rowptr, int* d_colidx, double* d_vals, void* stream) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  SB_TRY(stokes_fd(s));
+  return s->fd->assemble(s->c->eta, nullptr, nullptr, d_rowptr, d_colidx, d_vals, (cudaStream_t)stream);
+}
+
 int sb200_stokes_destroy(sb200_stokes* s) {
   if (!s) return 0;
+  delete s->fd;
   delete s->c;
   if (s->d_in) cudaFree(s->d_in);
   if (s->d_out) cudaFree(s->d_out);

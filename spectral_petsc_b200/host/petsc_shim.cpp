@@ -103,8 +103,48 @@ PetscErrorCode MatGetSize(Mat A, PetscInt* m, PetscInt* n) {
 PetscErrorCode MatDestroy(Mat A) {
   if (!A) return 0;
   PetscErrorCode rc = A->destroy ? A->destroy(A) : 0;
+  if (A->d_rowptr) sb200_free(A->d_rowptr);
+  if (A->d_colidx) sb200_free(A->d_colidx);
+  if (A->d_vals) sb200_free(A->d_vals);
   std::free(A);
   return rc;
+}
+
+PetscErrorCode MatCreateSeqAIJ(MPI_Comm, PetscInt m, PetscInt n, PetscInt, const PetscInt*, Mat* A) {
+  Mat a = (Mat)std::calloc(1, sizeof(_p_Mat));
+  a->m = m;
+  a->n = n;
+  a->is_aij = 1;
+  *A = a;
+  return 0;
+}
+
+PetscErrorCode MatSeqAIJGetCSRHost(Mat A, PetscInt* nz, PetscInt* rowptr, PetscInt* colidx, PetscScalar* vals) {
+  if (!A || !A->is_aij) return SB200_ERR_ARG;
+  if (nz) *nz = A->nz;
+  if ((rowptr || colidx || vals) && !A->d_vals) return SB200_ERR_USER;  // not assembled yet
+  PetscErrorCode rc = 0;
+  if (rowptr) rc = sb200_memcpy_d2h(rowptr, A->d_rowptr, (size_t)(A->m + 1) * sizeof(PetscInt), nullptr);
+  if (!rc && colidx) rc = sb200_memcpy_d2h(colidx, A->d_colidx, (size_t)A->nz * sizeof(PetscInt), nullptr);
+  if (!rc && vals) rc = sb200_memcpy_d2h(vals, A->d_vals, (size_t)A->nz * sizeof(PetscScalar), nullptr);
+  return rc ? rc : sb200_stream_sync(nullptr);
+}
+
+PetscErrorCode PCCreate(MPI_Comm, PC* pc) {
+  *pc = (PC)std::calloc(1, sizeof(_p_PC));
+  return 0;
+}
+PetscErrorCode PCShellSetContext(PC pc, void* ctx) {
+  pc->ctx = ctx;
+  return 0;
+}
+PetscErrorCode PCShellGetContext(PC pc, void** ctx) {
+  *ctx = pc->ctx;
+  return 0;
+}
+PetscErrorCode PCDestroy(PC pc) {
+  std::free(pc);
+  return 0;
 }
 
 PetscErrorCode SNESCreate(MPI_Comm, SNES* snes) {

@@ -16,6 +16,24 @@
 
 static const double PI_ = 3.14159265358979323846;  // chebyshev.h:10
 
+// Shared by FormJacobian and StokesPCSetUp0: the first assembly allocates the device CSR of the SeqAIJ matrix and writes
+// pattern + values, later ones refresh the values alone.
+template <class Ctx>
+static PetscErrorCode assemble_aij(Mat P, Ctx* h, int (*sizes)(Ctx*, long long*, long long*), int (*csr)(Ctx*, int*, int*, double*, void*)) {
+  if (!P || !P->is_aij) return SB200_ERR_ARG;
+  long long nrows = 0, nnz = 0;
+  CHK(sizes(h, &nrows, &nnz));
+  if (P->m != (PetscInt)nrows || P->n != (PetscInt)nrows) return SB200_ERR_USER;  // MatSetValues would fail on the row ids
+  if (!P->d_vals) {
+    CHK(sb200_malloc((void**)&P->d_rowptr, (size_t)(nrows + 1) * sizeof(PetscInt)));
+    CHK(sb200_malloc((void**)&P->d_colidx, (size_t)nnz * sizeof(PetscInt)));
+    CHK(sb200_malloc((void**)&P->d_vals, (size_t)nnz * sizeof(PetscScalar)));
+    P->nz = (PetscInt)nnz;
+    return csr(h, P->d_rowptr, P->d_colidx, P->d_vals, nullptr);
+  }
+  return csr(h, nullptr, nullptr, P->d_vals, nullptr);
+}
+
 extern "C" {
 
 // ---- chebyshev.c ---------------------------------------------------------------------------
@@ -127,6 +145,14 @@ PetscErrorCode FormFunction(SNES, Vec U, Vec rhs, void* void_ac) {  // elliptic.
   return 0;
 }
 
+PetscErrorCode FormJacobian(SNES, Vec, Mat* A, Mat* P, MatStructure* flag, void*) {  // elliptic.C:537-590
+  MatEllipticB200* c = nullptr;
+  CHK(MatShellGetContext(*A, (void**)&c));
+  CHK(assemble_aij<sb200_elliptic>(*P, c->e, sb200_elliptic_jacobian_sizes, sb200_elliptic_jacobian_csr));
+  if (flag) *flag = SAME_NONZERO_PATTERN;  // :588
+  return 0;
+}
+
 PetscErrorCode CreateExactSolution(SNES snes, Vec u, Vec u2, PetscReal cos_scale) {  // elliptic.C:594-677
   AppCtx* ac = nullptr;
   MatEllipticB200* c = nullptr;
@@ -207,7 +233,7 @@ struct StokesCtxB200 {
   sb200_stokes* s;
   StokesOptionsB200 opt;
   long long m, g, gp, gv, dv;
-  Mat MatVV, MatPV, MatVP, MatSchur;
+  Mat MatVV, MatPV, MatVP, MatSchur, MatVVPC;
 };
 
 static void stokes_exact(const StokesOptionsB200& o, const double* c, double* value, double* rhs) {
@@ -291,12 +317,14 @@ PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A,
   CHK(MatShellSetOperation(c->MatVP, MATOP_MULT, (void (*)(void))StokesMatMultVP));  // :323
   CHK(MatCreateShell(comm, (PetscInt)c->gv, (PetscInt)c->gv, 0, 0, c, &c->MatVV));
   CHK(MatShellSetOperation(c->MatVV, MATOP_MULT, (void (*)(void))StokesMatMultVV));  // :325
+  CHK(MatCreateSeqAIJ(comm, (PetscInt)c->gv, (PetscInt)c->gv, 1 + 2 * opt->numDims, PETSC_NULL, &c->MatVVPC));  // :326
   *ctx = c;
   return 0;
 }
 
 PetscErrorCode StokesDestroy(StokesCtxB200* c) {  // stokes.C:348-388
   if (!c) return 0;
+  MatDestroy(c->MatVVPC);
   MatDestroy(c->MatSchur);
   MatDestroy(c->MatPV);
   MatDestroy(c->MatVP);
@@ -356,6 +384,17 @@ PetscErrorCode StokesGetShells(StokesCtxB200* c, Mat* MatVV, Mat* MatPV, Mat* Ma
   if (MatVP) *MatVP = c->MatVP;
   if (MatSchur) *MatSchur = c->MatSchur;
   return 0;
+}
+
+PetscErrorCode StokesGetPCMatrix(StokesCtxB200* c, Mat* MatVVPC) {
+  *MatVVPC = c->MatVVPC;
+  return 0;
+}
+
+PetscErrorCode StokesPCSetUp0(PC pc) {  // stokes.C:1160-1240 (the KSPSetOperators calls at :1232-1234 stay with the caller's KSPs)
+  StokesCtxB200* c = nullptr;
+  CHK(PCShellGetContext(pc, (void**)&c));
+  return assemble_aij<sb200_stokes>(c->MatVVPC, c->s, sb200_stokes_pc_velocity_sizes, sb200_stokes_pc_velocity_csr);
 }
 
 PetscErrorCode StokesSetContinuation(StokesCtxB200* c, PetscReal exponent, PetscReal regularization) {

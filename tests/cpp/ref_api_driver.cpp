@@ -28,6 +28,46 @@ static double norm_inf(Vec v) {
   return m;
 }
 
+// The reference has no self-check for its preconditioning matrices beyond the solve converging, so use what the stencil
+// guarantees: with eta = 1, eta' = 0 the rows are the 3-point finite differences of -Laplace on the Chebyshev nodes, which are
+// exact for quadratics: (P q)_r = -2 for q = x_axis^2 on every row with a full stencil, and its row sum vanishes.
+static int check_fd_matrix(Mat P, int d, const int* dim, int ncomp, const char* tag) {
+  PetscInt nz = 0, rows = 0;
+  CHK(MatGetSize(P, &rows, PETSC_NULL));
+  CHK(MatSeqAIJGetCSRHost(P, &nz, PETSC_NULL, PETSC_NULL, PETSC_NULL));
+  std::vector<PetscInt> rp(rows + 1), ci(nz);
+  std::vector<double> v(nz);
+  CHK(MatSeqAIJGetCSRHost(P, PETSC_NULL, rp.data(), ci.data(), v.data()));
+  const double PI = 3.14159265358979323846;
+  const int axis = d - 2;  // an axis that is neither the slowest nor the fastest one in 3-D
+  long long istride = 1;
+  for (int j = d - 1; j > axis; j--) istride *= dim[j] - 2;
+  auto coord = [&](PetscInt row) {
+    const long long node = row / ncomp;
+    const int k = (int)((node / istride) % (dim[axis] - 2));
+    return cos((k + 1) * PI / (dim[axis] - 1));
+  };
+  double worst_q = 0, worst_sum = 0;
+  long long full = 0;
+  bool sorted = rp[0] == 0 && rp[rows] == nz;
+  for (PetscInt r = 0; r < rows; r++) {
+    for (PetscInt e = rp[r] + 1; e < rp[r + 1]; e++) sorted = sorted && ci[e] > ci[e - 1];
+    if (rp[r + 1] - rp[r] != 2 * d + 1) continue;
+    full++;
+    double q = 0, sum = 0;
+    for (PetscInt e = rp[r]; e < rp[r + 1]; e++) {
+      const double x = coord(ci[e]);
+      q += v[e] * x * x;
+      sum += v[e];
+    }
+    worst_q = fmax(worst_q, fabs(q + 2.0));
+    worst_sum = fmax(worst_sum, fabs(sum));
+  }
+  printf("%s P rows %d nz %d sorted %d full-stencil rows %lld  max |P x^2 + 2| = %.3e  max |row sum| = %.3e\n", tag, rows, nz, (int)sorted, full,
+         worst_q, worst_sum);
+  return 0;
+}
+
 static int test_cheb() {  // cheb.c:68-112 with the defaults m1=5, (m,n,p)=(8,7,6), all axes
   const double PI = 3.14159265358979323846;
   {
@@ -118,6 +158,21 @@ static int test_elliptic(int d, int* dim, int exact) {  // elliptic.C:159-209
   printf("%-25s: abs = %8e\n", "Norm of exact residual", norm_inf(r));
   CHK(MatMult(A, u, r));
   printf("elliptic |A u| = %8e\n", norm_inf(r));
+  {  // SNESSetJacobian(snes, A, P, FormJacobian, ac) (elliptic.C:167-178): P about the state FormFunction just cached
+    Mat P;
+    MatStructure flag = DIFFERENT_NONZERO_PATTERN;
+    CHK(MatCreateSeqAIJ(PETSC_COMM_SELF, m, n, 1 + 2 * d, PETSC_NULL, &P));
+    CHK(FormJacobian(snes, u, &A, &P, &flag, &ac));
+    CHK(check_fd_matrix(P, d, dim, 1, "elliptic"));
+    std::vector<double> v0(P->nz), v1(P->nz);
+    CHK(MatSeqAIJGetCSRHost(P, PETSC_NULL, PETSC_NULL, PETSC_NULL, v0.data()));
+    CHK(FormJacobian(snes, u, &A, &P, &flag, &ac));  // second Newton step: values refreshed into the same pattern
+    CHK(MatSeqAIJGetCSRHost(P, PETSC_NULL, PETSC_NULL, PETSC_NULL, v1.data()));
+    double diff = 0;
+    for (size_t i = 0; i < v0.size(); i++) diff = fmax(diff, fabs(v0[i] - v1[i]));
+    printf("elliptic P refresh flag %d max diff %.3e\n", (int)flag, diff);
+    CHK(MatDestroy(P));
+  }
   CHK(SNESDestroy(snes));
   CHK(MatDestroy(A));
   CHK(VecDestroy(u));
@@ -158,6 +213,16 @@ static int test_stokes(int n0) {  // stokes.C:139-212
   CHK(VecSetValuesHost(x, ns.data()));
   CHK(MatMult(A, x, r));
   printf("Null space test |A ns| = %9.3e\n", norm_inf(r));
+  {  // PCShellSetContext(pc, ctx); PCShellSetSetUp(pc, StokesPCSetUp0) (stokes.C:163-166)
+    PC pc;
+    Mat MatVVPC;
+    CHK(PCCreate(PETSC_COMM_SELF, &pc));
+    CHK(PCShellSetContext(pc, ctx));
+    CHK(StokesPCSetUp0(pc));
+    CHK(StokesGetPCMatrix(ctx, &MatVVPC));
+    CHK(check_fd_matrix(MatVVPC, 3, opt.dim, 3, "stokes"));
+    CHK(PCDestroy(pc));
+  }
   CHK(SNESDestroy(snes));
   CHK(StokesDestroy(ctx));
   CHK(MatDestroy(A));

@@ -29,3 +29,12 @@ def test_reference_api_driver(cuda):
     assert f(r"norm of residual\s+(\S+)") < 2e-11                                               # stokes 20^3 -exact 2
     assert f(r"Norm of solution\s+(\S+)") == pytest.approx(0.991, rel=1e-3)
     assert f(r"Null space test \|A ns\| =\s+(\S+)") < 1e-12                                     # stokes.C:206-212
+    # FormJacobian (elliptic.C:537-590) and StokesPCSetUp0 (stokes.C:1160-1240) through the reference's own names
+    fd = re.findall(r"(\w+) P rows (\d+) nz (\d+) sorted (\d) full-stencil rows (\d+)  max \|P x\^2 \+ 2\| = (\S+)  max \|row sum\| = (\S+)", txt)
+    assert [(t, int(r), int(z), int(s), int(n)) for t, r, z, s, n, _, _ in fd] == [
+        ("elliptic", 2744, 2744 + 3 * 2 * 13 * 14 * 14, 1, 12 ** 3),
+        ("elliptic", 100000, 100000 + 5 * 2 * 9 * 10 ** 4, 1, 8 ** 5),
+        ("stokes", 3 * 5832, 3 * (5832 + 3 * 2 * 17 * 18 * 18), 1, 3 * 16 ** 3)]
+    for row in fd:
+        assert float(row[5]) < 1e-8 and float(row[6]) < 1e-8    # 3-point differences are exact for quadratics; entries are O(1e3)
+    assert re.findall(r"elliptic P refresh flag (\d) max diff (\S+)", txt) == [("0", "0.000e+00")] * 2
