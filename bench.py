@@ -326,7 +326,7 @@ def run_cuda(args):
     Uq = [U_host.clone().pin_memory().numpy() for _ in range(depth)]
     Vq = [torch.empty(G.g, dtype=torch.float64).pin_memory().numpy() for _ in range(depth)]
     G.mat_mult_host_stream(Uq, Vq)  # warm-up: builds the queue's streams and device vectors
-    assert all(np.array_equal(v, Vh) for v in Vq), "queued host-buffer MatMult differs from the synchronous call"
+    queue_ok = all(np.array_equal(v, Vh) for v in Vq)  # reported, not asserted: a raise on one rank would hang the others' barrier
     e2e_steps = max(args.steps, 200)  # >= ~60 ms so the figure is a steady-state throughput, not the pipeline fill
     barrier()
     t0 = time.perf_counter()
@@ -362,7 +362,8 @@ def run_cuda(args):
                                  "frac": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9 / (hbm_peak * world), "algorithmic_bytes_per_step": alg_bytes(DIM)}},
             "e2e": {"value": ndof * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": G.gtotal * 8, "d2h_bytes_per_step": G.gtotal * 8,
                     "api": "sb200_elliptic_matmult_host_submit / _wait (pinned host buffers, <= %d applications in flight, %d steps timed)" % (depth, e2e_steps),
-                    "sync_call_value": ndof * args.steps / (e2e_sync_ms * 1e-3) / 1e9, "sync_call_api": "sb200_elliptic_matmult_host (one blocking call per step)"},
+                    "sync_call_value": ndof * args.steps / (e2e_sync_ms * 1e-3) / 1e9, "sync_call_api": "sb200_elliptic_matmult_host (one blocking call per step)",
+                    "queued_equals_sync_call_bitwise": bool(queue_ok)},
             "gpu_launches": launches,
             "clocks": clocks,
         }
