@@ -73,6 +73,12 @@ int sb200_elliptic_set_params(sb200_elliptic* e, double gamma, double exponent);
 /* c->dirichlet (nd doubles, lexicographic boundary order; elliptic.C:672) and ac->b (g doubles, :674). */
 int sb200_elliptic_set_dirichlet(sb200_elliptic* e, const double* d_values, void* stream);
 int sb200_elliptic_set_rhs(sb200_elliptic* e, const double* d_b, void* stream);
+/* CreateExactSolution(snes, u, u2) (elliptic.C:594-677) on the HOST (set-up work): -exact 0 (separable cosine, needs
+ * -cos_scale, which the reference reads without a default, :607-609), 1 (quadratics) or 2 (polynomials); writes the exact
+ * solution u (g), the forcing u2 (g, what the driver copies into ac->b, :674) and the Dirichlet values (nd), any of which
+ * may be NULL.  Needs no device; upload with sb200_elliptic_set_dirichlet / _set_rhs. */
+int sb200_elliptic_exact_solution(int d, const int* dim, int exact, double cos_scale, double gamma, double exponent, double* h_u,
+                                  double* h_u2, double* h_dirichlet);
 /* MatMult_Elliptic(A, U, V) (elliptic.C:297-339): Jacobian action, U and V of g doubles. */
 int sb200_elliptic_matmult(sb200_elliptic* e, const double* d_U, double* d_V, void* stream);
 int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V);
@@ -148,6 +154,10 @@ int sb200_stokes_set_rheology(sb200_stokes* s, int type, double hardness, double
 /* c->dirichlet (dv doubles: boundary nodes in walk order x d components, stokes.C:796-801) and c->force (g doubles). */
 int sb200_stokes_set_dirichlet(sb200_stokes* s, const double* d_values, void* stream);
 int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream);
+/* StokesCreateExactSolution (stokes.C:942-1003) on the HOST with StokesExact0..3 (:1948-2034): exact solution U and forcing
+ * U2 (g doubles each, AoS [v, p]) and the Dirichlet velocities StokesDirichlet gives the boundary nodes (dv doubles, :2039-2050);
+ * any output may be NULL.  -exact 3 is 2-D only (:2022).  Needs no device. */
+int sb200_stokes_exact_solution(int d, const int* dim, int exact, double* h_u, double* h_u2, double* h_dirichlet);
 /* StokesMatMult(A, x, y) (stokes.C:499-519): x, y of g doubles, AoS [v_0..v_{d-1}, p] per interior node. */
 int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y);

@@ -16,6 +16,8 @@ from .capi import (  # noqa: F401
     Stokes,
     KSP,
     cheb_matrix,
+    elliptic_exact_solution,
+    stokes_exact_solution,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution"]

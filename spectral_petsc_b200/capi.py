@@ -73,6 +73,28 @@ def cheb_matrix(P):
     return D
 
 
+def elliptic_exact_solution(dim, exact, cos_scale=0.0, gamma=0.0, exponent=2.0):
+    """CreateExactSolution (elliptic.C:594-677) on the host: (u, u2, dirichlet) as numpy arrays in the reference's Vec order."""
+    dim = [int(v) for v in dim]
+    g = int(np.prod([v - 2 for v in dim]))
+    m = int(np.prod(dim))
+    u, u2, dr = np.empty(g), np.empty(g), np.empty(m - g)
+    _ck(lib().sb200_elliptic_exact_solution(ctypes.c_int(len(dim)), (ctypes.c_int * len(dim))(*dim), ctypes.c_int(exact), ctypes.c_double(cos_scale),
+                                            ctypes.c_double(gamma), ctypes.c_double(exponent), _hptr(u), _hptr(u2), _hptr(dr)))
+    return u, u2, dr
+
+
+def stokes_exact_solution(dim, exact):
+    """StokesCreateExactSolution + StokesDirichlet (stokes.C:942-1003, 1948-2050) on the host: (U, U2, dirichlet velocities)."""
+    dim = [int(v) for v in dim]
+    d = len(dim)
+    gp = int(np.prod([v - 2 for v in dim]))
+    m = int(np.prod(dim))
+    U, U2, dr = np.empty(gp * (d + 1)), np.empty(gp * (d + 1)), np.empty((m - gp) * d)
+    _ck(lib().sb200_stokes_exact_solution(ctypes.c_int(d), (ctypes.c_int * d)(*dim), ctypes.c_int(exact), _hptr(U), _hptr(U2), _hptr(dr)))
+    return U, U2, dr
+
+
 def _csr_call(sizes_fn, csr_fn, handle, pattern):
     """Shared by Elliptic.jacobian_csr / Stokes.pc_velocity_csr: device CSR (int32 rowptr, int32 colidx, fp64 vals)."""
     import torch

@@ -14,8 +14,6 @@
     if (_e) return _e;       \
   } while (0)
 
-static const double PI_ = 3.14159265358979323846;  // chebyshev.h:10
-
 // Shared by FormJacobian and StokesPCSetUp0: the first assembly allocates the device CSR of the SeqAIJ matrix and writes
 // pattern + values, later ones refresh the values alone.
 template <class Ctx>
@@ -158,63 +156,8 @@ PetscErrorCode CreateExactSolution(SNES snes, Vec u, Vec u2, PetscReal cos_scale
   MatEllipticB200* c = nullptr;
   CHK(SNESGetApplicationContext(snes, (void**)&ac));
   CHK(MatShellGetContext(ac->A, (void**)&c));
-  const int d = c->d;
-  const double gamma = ac->gamma, exponent = ac->exponent;
-  double s = 0.5;
-  if (ac->exact == 0 || ac->exact == 3) s *= cos_scale;
-  if (ac->exact < 0 || ac->exact > 2) return 1;  // "Choose an exact solution." elliptic.C:657
   std::vector<double> hu((size_t)c->g), hu2((size_t)c->g), hd((size_t)c->nd);
-  std::vector<int> ind(d, 0);
-  std::vector<double> x(d);
-  long long gi = 0, di = 0;
-  for (long long node = 0; node < c->m; node++) {
-    bool bdy = false;
-    for (int j = 0; j < d; j++) {
-      x[j] = cos(ind[j] * M_PI / (c->dim[j] - 1));  // elliptic.C:279
-      bdy = bdy || ind[j] == 0 || ind[j] == c->dim[j] - 1;
-    }
-    double v = 1.0, w = 0.0;
-    switch (ac->exact) {
-      case 0: {  // elliptic.C:620-632
-        for (int j = 0; j < d; j++) v *= cos(s * PI_ * x[j]);
-        const double eta = 1.0 + gamma * pow(v, exponent);
-        const double deta = (fabs(exponent) < 1e-10) ? 0.0 : gamma * exponent * pow(v, exponent - 1.0);
-        for (int j = 0; j < d; j++) {
-          double dv = 1.0;
-          for (int k = 0; k < d; k++) dv *= (k == j) ? -s * PI_ * sin(s * PI_ * x[k]) : cos(s * PI_ * x[k]);
-          const double d2v = -(s * PI_) * (s * PI_) * v;
-          w += deta * dv * dv + eta * d2v;
-        }
-        w = -w;
-      } break;
-      case 1:  // elliptic.C:633-643
-        for (int j = 0; j < d; j++) {
-          v *= (1 - x[j]) * (1 + x[j]);
-          double z = 1.0;
-          for (int k = 0; k < d; k++)
-            if (k != j) z *= 2.0 * (1 - x[k]) * (1 + x[k]);
-          w += z;
-        }
-        break;
-      case 2:  // elliptic.C:644-655
-        for (int j = 0; j < d; j++) {
-          v *= pow(x[j], 4 + j);
-          double z = 1.0;
-          for (int k = 0; k < d; k++) z *= (k == j) ? (4 + k) * (3 + k) * pow(x[k], 2 + k) : pow(x[k], 4 + k);
-          w -= z;
-        }
-        break;
-    }
-    if (bdy) hd[di++] = v;
-    else {
-      hu[gi] = v;
-      hu2[gi++] = w;
-    }
-    for (int j = d - 1; j >= 0; j--) {  // BlockIt::next (elliptic.C:27-40)
-      if (++ind[j] < c->dim[j]) break;
-      ind[j] = 0;
-    }
-  }
+  CHK(sb200_elliptic_exact_solution(c->d, c->dim.data(), (int)ac->exact, cos_scale, ac->gamma, ac->exponent, hu.data(), hu2.data(), hd.data()));
   CHK(VecSetValuesHost(u, hu.data()));
   CHK(VecSetValuesHost(u2, hu2.data()));
   CHK(VecSetValuesHost(ac->b, hu2.data()));  // VecCopy(u2, ac->b) elliptic.C:674
@@ -236,51 +179,10 @@ struct StokesCtxB200 {
   Mat MatVV, MatPV, MatVP, MatSchur, MatVVPC;
 };
 
-static void stokes_exact(const StokesOptionsB200& o, const double* c, double* value, double* rhs) {
-  // StokesExact0..2 (stokes.C:1948-2012); value[d] for -exact 2 in 3-D is defined as 0
-  const int d = o.numDims;
-  for (int i = 0; i <= d; i++) value[i] = rhs[i] = 0.0;
-  if (o.exact == 0) return;
-  const double eta = 1.0;
-  const double u = sin(0.5 * M_PI * c[0]) * cos(0.5 * M_PI * c[1]);
-  const double v = -cos(0.5 * M_PI * c[0]) * sin(0.5 * M_PI * c[1]);
-  value[0] = u;
-  value[1] = v;
-  rhs[0] = (0.5 * M_PI) * (0.5 * M_PI) * eta * u;
-  rhs[1] = (0.5 * M_PI) * (0.5 * M_PI) * eta * v;
-  if (o.exact == 1) {
-    value[d] = 0.25 * (cos(M_PI * c[0]) + cos(M_PI * c[1])) + 10 * (c[0] + c[1]);
-    rhs[0] += -0.25 * M_PI * sin(M_PI * c[0]) + 10;
-    rhs[1] += -0.25 * M_PI * sin(M_PI * c[1]) + 10;
-  }
-}
-
 static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std::vector<double>* U2, std::vector<double>* D) {
-  const int d = c->opt.numDims;
-  int ind[3] = {0, 0, 0};
-  long long gi = 0, di = 0;
-  for (long long node = 0; node < c->m; node++) {
-    double x[3], val[4], rhs[4];
-    bool bdy = false;
-    for (int j = 0; j < d; j++) {
-      x[j] = cos(ind[j] * M_PI / (c->opt.dim[j] - 1));  // stokes.C:296
-      bdy = bdy || ind[j] == 0 || ind[j] == c->opt.dim[j] - 1;
-    }
-    stokes_exact(c->opt, x, val, rhs);
-    if (bdy) {
-      if (D) for (int k = 0; k < d; k++) (*D)[di * d + k] = val[k];
-      di++;
-    } else {
-      if (U) for (int k = 0; k <= d; k++) (*U)[gi * (d + 1) + k] = val[k];
-      if (U2) for (int k = 0; k <= d; k++) (*U2)[gi * (d + 1) + k] = rhs[k];
-      gi++;
-    }
-    for (int j = d - 1; j >= 0; j--) {
-      if (++ind[j] < c->opt.dim[j]) break;
-      ind[j] = 0;
-    }
-  }
-  return 0;
+  // StokesExact0..2 (stokes.C:1948-2012) at every node in walk order
+  return sb200_stokes_exact_solution((int)c->opt.numDims, c->opt.dim, (int)c->opt.exact, U ? U->data() : nullptr, U2 ? U2->data() : nullptr,
+                                     D ? D->data() : nullptr);
 }
 
 PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A, Vec* x, StokesCtxB200** ctx) {
