@@ -1,0 +1,84 @@
+"""The command-line drivers on the CUDA shells (spectral_petsc_b200.drivers with its own GpuElliptic / GpuStokes adapters:
+device FGMRES, device-assembled preconditioning matrices) against the SAME driver flow over the CPU oracle: identical SNES /
+KSP iteration counts (+-1), the same norms of error, the same stokes.vtk numbers."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from spectral_petsc_b200 import drivers
+from support.oracle_problems import OracleElliptic, OracleStokes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def both(main, cmd, oracle):
+    lo, lg = [], []
+    ro = main(cmd.split(), out=lo.append, make_problem=oracle)
+    rg = main(cmd.split(), out=lg.append)  # default adapters: the GPU
+    return ro, rg, lo, lg
+
+
+def test_elliptic_config1_and_nonlinear(cuda):
+    ro, rg, lo, lg = both(drivers.elliptic_main, "-dim 16,16,16 -exact 2 -ksp_rtol 1e-10", OracleElliptic)
+    assert lg[:2] == lo[:2]  # header and DOF distribution
+    assert rg["snes_its"] == ro["snes_its"] == 1 and rg["ksp_its"] == ro["ksp_its"] == [13]
+    assert rg["reason"] == ro["reason"] == "CONVERGED_FNORM_RELATIVE"
+    assert rg["exact_residual_abs"] < 5e-11 and abs(rg["error_abs"] - ro["error_abs"]) < 1e-11 + 1e-3 * ro["error_abs"]
+    assert np.abs(rg["x"] - ro["x"]).max() < 1e-9
+    # tests.sh: the nonlinear 2-D problem
+    ro, rg, _, _ = both(drivers.elliptic_main, "-dim 24,24 -exact 0 -cos_scale 3 -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12", OracleElliptic)
+    assert abs(rg["snes_its"] - ro["snes_its"]) <= 1 and all(abs(a - b) <= 1 for a, b in zip(rg["ksp_its"], ro["ksp_its"]))
+    assert abs(rg["error_abs"] - ro["error_abs"]) < 1e-9
+
+
+def test_stokes_continuation_and_vtk(cuda, tmp_path):
+    vo, vg = str(tmp_path / "o.vtk"), str(tmp_path / "g.vtk")
+    cmd = ("-exact 2 -cont 2 -rheology 1 -eps 1e-2 -exponent 3 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -dim 8,8,8 "
+           "-ksp_rtol 1e-6 -ksp_max_it 300 -output_vtk ")
+    lo, lg = [], []
+    ro = drivers.stokes_main((cmd + vo).split(), out=lo.append, make_problem=OracleStokes)
+    rg = drivers.stokes_main((cmd + vg).split(), out=lg.append)
+    assert lg[:3] == lo[:3]
+    assert rg["null_space"] < 1e-10
+    for a, b in zip(rg["steps"], ro["steps"]):
+        assert a["reason"] == b["reason"] == "CONVERGED_FNORM_RELATIVE"
+        assert abs(a["snes_its"] - b["snes_its"]) <= 1
+        assert all(abs(x - y) <= 1 + y // 10 for x, y in zip(a["ksp_its"], b["ksp_its"]))
+        assert abs(a["error"] - b["error"]) < 1e-6 * max(1.0, b["error"])
+    # the two files hold the same header lines and the same numbers
+    to, tg = open(vo).read().split("\n"), open(vg).read().split("\n")
+    assert len(to) == len(tg)
+    num = lambda line: [float(t) for t in line.split()]
+    for a, b in zip(to, tg):
+        if a[:1].isalpha() or a.startswith("#") or not a.strip():
+            assert a == b
+        else:
+            assert np.allclose(num(a), num(b), rtol=1e-5, atol=1e-6)
+
+
+def test_command_lines(cuda):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "spectral_petsc_b200.elliptic", "-dim", "10,10,10,10", "-pc_type", "hypre", "-exact", "2", "-ksp_monitor",
+                        "-ksp_rtol", "1e-10"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)  # README:21 in 4-D (the host LU standing in for hypre would fill 2 GB at 12^5)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.split("\n")
+    assert out[0] == "Elliptic problem  dims = [10,10,10,10]    gamma = 0.000000    exponent = 2.000000"
+    assert out[1] == "DOF distribution:    10000 local         4096 global         5904 dirichlet"
+    assert "Number of nonlinear iterations = 1" in out and "Reason for solver termination: CONVERGED_FNORM_RELATIVE" in out
+    err = float([l for l in out if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+    assert err < 1e-8
+    r = subprocess.run([sys.executable, "-m", "spectral_petsc_b200.stokes"] + ("-exact 2 -cont0 1 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -vel_pc_type hypre "
+                       "-svel_ksp_type preonly -svel_pc_type hypre -ksp_type fgmres -ksp_monitor -dim 20,20,20 -ksp_rtol 1e-10").split(),
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)  # README:44, BASELINE config 4
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.split("\n")
+    assert "DOF distribution: 23328 global   5832/8000 pressure    17496/24000 velocity    6504 dirichlet    0 mixed" in out  # SURVEY 8 header
+    assert "Reason for solver termination: CONVERGED_FNORM_RELATIVE" in out
+    err = float([l for l in out if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+    assert err < 1e-6  # 7.8e-08 over the oracle
+    r = subprocess.run([sys.executable, "-m", "spectral_petsc_b200.stokes", "-boundary", "2"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 83 and "Boundary type 2 not implemented" in r.stderr
