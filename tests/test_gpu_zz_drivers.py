@@ -1,4 +1,5 @@
-"""The command-line drivers on the CUDA shells (spectral_petsc_b200.drivers with its own GpuElliptic / GpuStokes adapters:
+"""(Named to run last in the GPU suite: it spawns the command lines as subprocesses.)
+The command-line drivers on the CUDA shells (spectral_petsc_b200.drivers with its own GpuElliptic / GpuStokes adapters:
 device FGMRES, device-assembled preconditioning matrices) against the SAME driver flow over the CPU oracle: identical SNES /
 KSP iteration counts (+-1), the same norms of error, the same stokes.vtk numbers."""
 import os
