@@ -228,6 +228,21 @@ int sb200_apply_elliptic_matmult(void* ctx, const double* d_x, double* d_y, void
 int sb200_apply_stokes_matmult(void* ctx, const double* d_x, double* d_y, void* stream);
 int sb200_apply_stokes_matmult_vv(void* ctx, const double* d_x, double* d_y, void* stream);
 
+/* ---- host stand-in for PETSc's PCILU (NOT part of the B200 path; the PC stays PETSc's own) --------------------------------
+ * The reference sets PCILU with 2 levels of fill on the finite-difference matrix in code (elliptic.C:183-184); PETSc's default
+ * PC for the Stokes matrix MatVVPC is ILU(0).  So that the command-line drivers and the solver-level parity tests can run those
+ * DEFAULT configurations without PETSc, this is the textbook level-of-fill ILU(k) on HOST CSR arrays (natural ordering, no
+ * pivoting, no shift; columns must increase within a row).  solve() applies (LU)^-1; refactor() takes new values on the same
+ * pattern (SAME_NONZERO_PATTERN). */
+typedef struct sb200_host_ilu sb200_host_ilu;
+int sb200_host_ilu_create(int n, const int* h_rowptr, const int* h_colidx, const double* h_vals, int levels, sb200_host_ilu** out);
+int sb200_host_ilu_refactor(sb200_host_ilu* f, const double* h_vals);
+int sb200_host_ilu_solve(const sb200_host_ilu* f, const double* h_b, double* h_x);
+int sb200_host_ilu_nnz(const sb200_host_ilu* f, long long* nnz);
+/* factor as CSR: rowptr (n+1), colidx / vals (nnz): strictly lower part = L (unit diagonal implied), diagonal and above = U */
+int sb200_host_ilu_get(const sb200_host_ilu* f, int* h_rowptr, int* h_colidx, double* h_vals);
+int sb200_host_ilu_destroy(sb200_host_ilu* f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ from .capi import (  # noqa: F401
     cheb_matrix,
     elliptic_exact_solution,
     stokes_exact_solution,
+    HostILU,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution", "HostILU"]

@@ -95,6 +95,54 @@ def stokes_exact_solution(dim, exact):
     return U, U2, dr
 
 
+class HostILU:
+    """ILU(levels) of a host CSR matrix: the stand-in for PETSc's PCILU (sb200_host_ilu_*; NOT part of the B200 path)."""
+
+    def __init__(self, P, levels=0):
+        P = P.tocsr().copy()
+        P.sort_indices()
+        self.n = P.shape[0]
+        self._rowptr = np.ascontiguousarray(P.indptr, dtype=np.int32)
+        self._colidx = np.ascontiguousarray(P.indices, dtype=np.int32)
+        self._h = ctypes.c_void_p()
+        vals = np.ascontiguousarray(P.data, dtype=np.float64)
+        ip = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _ck(lib().sb200_host_ilu_create(ctypes.c_int(self.n), ip(self._rowptr), ip(self._colidx), _hptr(vals), ctypes.c_int(levels), ctypes.byref(self._h)))
+
+    def refactor(self, P):
+        P = P.tocsr().copy()
+        P.sort_indices()
+        assert np.array_equal(P.indptr, self._rowptr) and np.array_equal(P.indices, self._colidx), "SAME_NONZERO_PATTERN required"
+        _ck(lib().sb200_host_ilu_refactor(self._h, _hptr(np.ascontiguousarray(P.data, dtype=np.float64))))
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        _ck(lib().sb200_host_ilu_solve(self._h, _hptr(b), _hptr(x)))
+        return x
+
+    @property
+    def nnz(self):
+        n = ctypes.c_longlong()
+        _ck(lib().sb200_host_ilu_nnz(self._h, ctypes.byref(n)))
+        return n.value
+
+    def factor(self):
+        """(rowptr, colidx, vals) of the combined factor: strictly lower = L (unit diagonal implied), rest = U."""
+        rp, ci, v = np.empty(self.n + 1, dtype=np.int32), np.empty(self.nnz, dtype=np.int32), np.empty(self.nnz)
+        ip = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _ck(lib().sb200_host_ilu_get(self._h, ip(rp), ip(ci), _hptr(v)))
+        return rp, ci, v
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().sb200_host_ilu_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
 def _csr_call(sizes_fn, csr_fn, handle, pattern):
     """Shared by Elliptic.jacobian_csr / Stokes.pc_velocity_csr: device CSR (int32 rowptr, int32 colidx, fp64 vals)."""
     import torch

@@ -142,7 +142,13 @@ int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb20
     delete c;
     return rc;
   }
-  if (cudaMalloc((void**)&c->sync, 64) == cudaSuccess) cudaMemset(c->sync, 0, 64);
+  cudaError_t ce = cudaMalloc((void**)&c->sync, 64);
+  if (ce == cudaSuccess) ce = cudaMemset(c->sync, 0, 64);
+  if (ce != cudaSuccess) {
+    set_last_error(std::string("MatCreateCheb: ") + cudaGetErrorString(ce));
+    sb200_cheb_destroy(c);
+    return SB200_ERR_CUDA;
+  }
   *out = c;
   return 0;
 }
@@ -170,10 +176,8 @@ int sb200_cheb_apply(sb200_cheb* c, const double* d_x, double* d_y, void* stream
 int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y) {
   SB_CHECK(c && h_x && h_y, SB200_ERR_ARG, "null pointer");
   const size_t bytes = (size_t)c->N * sizeof(double);
-  if (!c->d_x) {
-    SB_CUDA(cudaMalloc((void**)&c->d_x, bytes));
-    SB_CUDA(cudaMalloc((void**)&c->d_y, bytes));
-  }
+  if (!c->d_x) SB_CUDA(cudaMalloc((void**)&c->d_x, bytes));
+  if (!c->d_y) SB_CUDA(cudaMalloc((void**)&c->d_y, bytes));
   SB_CUDA(cudaMemcpyAsync(c->d_x, h_x, bytes, cudaMemcpyHostToDevice, 0));
   SB_TRY(sb200_cheb_apply(c, c->d_x, c->d_y, nullptr));
   SB_CUDA(cudaMemcpyAsync(h_y, c->d_y, bytes, cudaMemcpyDeviceToHost, 0));
@@ -315,10 +319,9 @@ int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, v
 }
 
 static int elliptic_host_staging(sb200_elliptic* e) {
-  if (e->d_in) return 0;
   const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
-  SB_CUDA(cudaMalloc((void**)&e->d_in, bytes));
-  SB_CUDA(cudaMalloc((void**)&e->d_out, bytes));
+  if (!e->d_in) SB_CUDA(cudaMalloc((void**)&e->d_in, bytes));
+  if (!e->d_out) SB_CUDA(cudaMalloc((void**)&e->d_out, bytes));
   return 0;
 }
 
@@ -336,15 +339,16 @@ int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_
 static int elliptic_host_queue(sb200_elliptic* e) {
   if (e->q_in) return 0;
   const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
+  // every piece is created only if missing, so a call that failed half way (out of memory) can be retried without leaking
   for (auto& s : e->q) {
-    SB_CUDA(cudaMalloc((void**)&s.d_in, bytes));
-    SB_CUDA(cudaMalloc((void**)&s.d_out, bytes));
-    SB_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
-    SB_CUDA(cudaEventCreateWithFlags(&s.op_done, cudaEventDisableTiming));
-    SB_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+    if (!s.d_in) SB_CUDA(cudaMalloc((void**)&s.d_in, bytes));
+    if (!s.d_out) SB_CUDA(cudaMalloc((void**)&s.d_out, bytes));
+    if (!s.in_done) SB_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+    if (!s.op_done) SB_CUDA(cudaEventCreateWithFlags(&s.op_done, cudaEventDisableTiming));
+    if (!s.out_done) SB_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
   }
-  SB_CUDA(cudaStreamCreateWithFlags(&e->q_op, cudaStreamNonBlocking));
-  SB_CUDA(cudaStreamCreateWithFlags(&e->q_out, cudaStreamNonBlocking));
+  if (!e->q_op) SB_CUDA(cudaStreamCreateWithFlags(&e->q_op, cudaStreamNonBlocking));
+  if (!e->q_out) SB_CUDA(cudaStreamCreateWithFlags(&e->q_out, cudaStreamNonBlocking));
   SB_CUDA(cudaStreamCreateWithFlags(&e->q_in, cudaStreamNonBlocking));  // last: its presence marks the queue as built
   return 0;
 }

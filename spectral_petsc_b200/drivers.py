@@ -88,26 +88,43 @@ def _is_number(s):
 
 
 class HostPC:
-    """Stand-in for PETSc's PC on a finite-difference matrix (scipy CSR on the host): -pc_type lu | ilu | jacobi | none;
-    `hypre` (README:12) has no counterpart here and maps to lu.  apply() takes and returns HOST arrays."""
+    """Stand-in for PETSc's PC on a finite-difference matrix (scipy CSR on the host), selected like PETSc's:
+    -pc_type ilu (level-of-fill ILU(k), -pc_factor_levels k: the C++ sb200_host_ilu_*, what the reference sets in code with
+    k = 2, elliptic.C:183-184) | lu (SuperLU) | ilut (scipy's threshold ILU) | jacobi | none; `hypre` (README:12) has no
+    counterpart here and maps to lu.  apply() takes and returns HOST arrays; update(P) refactors for a new matrix with
+    the same pattern (SAME_NONZERO_PATTERN)."""
 
-    TYPES = ("lu", "ilu", "jacobi", "none", "hypre")
+    TYPES = ("ilu", "lu", "ilut", "jacobi", "none", "hypre")
 
-    def __init__(self, P, pc_type="lu"):
-        import scipy.sparse.linalg as spla
-
+    def __init__(self, P, pc_type="ilu", levels=0):
         if pc_type not in self.TYPES:
             raise OptionsError("unknown PC type %r (have: %s)" % (pc_type, ", ".join(self.TYPES)))
         self.type = "lu" if pc_type == "hypre" else pc_type
-        if self.type == "lu":
+        self.levels = levels
+        self._ilu = None
+        self.update(P)
+
+    def update(self, P):
+        import scipy.sparse.linalg as spla
+
+        if self.type == "ilu":
+            if self._ilu is None:
+                from .capi import HostILU
+
+                self._ilu = HostILU(P, self.levels)
+            else:
+                self._ilu.refactor(P)
+            self.apply = self._ilu.solve
+        elif self.type == "lu":
             self.apply = spla.splu(P.tocsc()).solve
-        elif self.type == "ilu":  # scipy's threshold ILU, not PETSc's level-of-fill ILU(2): same role, different fill rule
+        elif self.type == "ilut":
             self.apply = spla.spilu(P.tocsc(), drop_tol=1e-4, fill_factor=10).solve
         elif self.type == "jacobi":
             dinv = 1.0 / P.diagonal()
             self.apply = lambda r: dinv * r
         else:
             self.apply = lambda r: r.copy()
+        return self
 
 
 # ---- problem adapters over the C-ABI library -------------------------------------------------------------------------
@@ -252,7 +269,8 @@ def elliptic_main(argv, out=print, make_problem=GpuElliptic):
     ksp_rtol, ksp_max_it = o.real("ksp_rtol", 1e-5), o.int("ksp_max_it", 10000)  # PETSc defaults
     restart = o.int("ksp_gmres_restart", 30)
     snes_rtol, snes_atol, snes_max_it = o.real("snes_rtol", 1e-8), o.real("snes_atol", 1e-50), o.int("snes_max_it", 50)
-    pc_type = o.string("pc_type", "lu")  # the reference's in-code default is PCILU with 2 levels (elliptic.C:183-184): PETSc's own
+    pc_type = o.string("pc_type", "ilu")  # PCSetType(pc, PCILU); PCFactorSetLevels(pc, 2) (elliptic.C:183-184)
+    pc_levels = o.int("pc_factor_levels", 2)
     ksp_type = o.string("ksp_type", "fgmres")  # KSPSetType(ksp, KSPFGMRES), elliptic.C:182
     if ksp_type != "fgmres":
         raise OptionsError("-ksp_type %s: only fgmres (the type the reference sets in code) is built" % ksp_type)
@@ -271,10 +289,12 @@ def elliptic_main(argv, out=print, make_problem=GpuElliptic):
         res["exact_residual_abs"], res["exact_residual_rel"] = float(np.abs(r).max()), float(np.nanmax(np.abs(r / u2)))
     out("%-25s: abs = %8e   rel = %8e" % ("Norm of exact residual", res["exact_residual_abs"], res["exact_residual_rel"]))
 
-    ksp_log = []
+    ksp_log, pcs = [], []
 
     def solve_jacobian(rhs):  # one KSPSolve of the SNES: FormJacobian -> PC set-up -> FGMRES on MatMult_Elliptic
-        pc = HostPC(prob.jacobian(), pc_type)
+        P = prob.jacobian()
+        pc = pcs[0].update(P) if pcs else HostPC(P, pc_type, pc_levels)
+        pcs[:] = [pc]
         x, its, reason = prob.krylov(prob.mat_mult, rhs, lambda v: prob.from_host(pc.apply(prob.to_host(v))), ksp_rtol, ksp_max_it, restart)
         ksp_log.append((its, reason))
         if ksp_monitor:
@@ -394,7 +414,9 @@ def stokes_main(argv, out=print, make_problem=GpuStokes):
     vel_max_it, vel_rtol = o.int("vel_ksp_max_it", 10000), o.real("vel_ksp_rtol", 1e-5)
     schur_max_it, schur_rtol = o.int("schur_ksp_max_it", 10000), o.real("schur_ksp_rtol", 1e-5)
     svel_preonly = o.string("svel_ksp_type", "gmres") == "preonly"
-    vel_pc, svel_pc = o.string("vel_pc_type", "lu"), o.string("svel_pc_type", "lu")
+    # PETSc's default PC for the SeqAIJ matrix MatVVPC is ILU(0); README:44 overrides it with hypre
+    vel_pc, svel_pc = o.string("vel_pc_type", "ilu"), o.string("svel_pc_type", "ilu")
+    vel_levels, svel_levels = o.int("vel_pc_factor_levels", 0), o.int("svel_pc_factor_levels", 0)
     ksp_monitor, snes_monitor = o.has("ksp_monitor"), o.has("snes_monitor")
     want_vtk = o.has("output_vtk")
     vtk_path = o.string("output_vtk", None) or "stokes.vtk"
@@ -429,8 +451,11 @@ def stokes_main(argv, out=print, make_problem=GpuStokes):
 
     def make_saddle_pc():  # StokesPCSetUp0 + the PCs PETSc builds on MatVVPC for KSPVelocity / KSPSchurVelocity
         P = prob.pc_velocity_matrix()
-        pcs["vel"] = HostPC(P, vel_pc)
-        pcs["svel"] = pcs["vel"] if svel_pc == vel_pc else HostPC(P, svel_pc)
+        pcs["vel"] = pcs["vel"].update(P) if "vel" in pcs else HostPC(P, vel_pc, vel_levels)
+        if (svel_pc, svel_levels) == (vel_pc, vel_levels):
+            pcs["svel"] = pcs["vel"]
+        else:
+            pcs["svel"] = pcs["svel"].update(P) if "svel" in pcs else HostPC(P, svel_pc, svel_levels)
         on_dev = lambda pc: (lambda v: prob.from_host(pc.apply(prob.to_host(v))))
         spc = solvers.StokesSaddlePC(prob, d, prob.krylov, on_dev(pcs["vel"]), saddle_type=saddle, vel_max_it=vel_max_it, schur_max_it=schur_max_it,
                                      vel_rtol=vel_rtol, schur_rtol=schur_rtol, svel_preonly=svel_preonly)

@@ -37,7 +37,11 @@ def test_elliptic_config1_lines_and_counts():
     assert re.match(r"Norm of exact residual   : abs = \S+   rel = \S+$", lines[2]) and res["exact_residual_abs"] < 5e-11  # K3
     assert lines[-3:-1] == ["Number of nonlinear iterations = 1", "Reason for solver termination: CONVERGED_FNORM_RELATIVE"]
     assert re.match(r"Norm of error            : abs = \S+   rel = \S+$", lines[-1])
-    assert res["ksp_its"] == [13] and res["error_abs"] < 1e-9
+    # the reference's in-code solver: FGMRES(30) preconditioned by ILU(2) of the finite-difference matrix (elliptic.C:181-184)
+    assert res["ksp_its"] == [16] and res["error_abs"] < 2e-9
+    res_lu, _ = run(drivers.elliptic_main, "-dim 16,16,16 -exact 2 -ksp_rtol 1e-10 -pc_type lu", OracleElliptic)
+    res_0, _ = run(drivers.elliptic_main, "-dim 16,16,16 -exact 2 -ksp_rtol 1e-10 -pc_factor_levels 0", OracleElliptic)
+    assert res_lu["ksp_its"] == [13] and res_0["ksp_its"] == [25]  # a stronger / weaker PC on the same matrix
 
 
 def test_elliptic_tests_sh_case_and_5d():
@@ -80,8 +84,8 @@ def test_stokes_readme_line_small():
 def test_stokes_continuation_and_vtk(tmp_path):
     """README:55 (BASELINE config 5) at a small extent, with -output_vtk."""
     vtk = str(tmp_path / "stokes.vtk")
-    cmd = ("-exact 2 -cont 2 -rheology 1 -eps 1e-2 -exponent 3 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -dim 8,8,8 "
-           "-ksp_rtol 1e-6 -ksp_max_it 300 -output_vtk " + vtk)
+    cmd = ("-exact 2 -cont 2 -rheology 1 -eps 1e-2 -exponent 3 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -vel_pc_type hypre -svel_ksp_type preonly "
+           "-svel_pc_type hypre -dim 8,8,8 -ksp_rtol 1e-6 -ksp_max_it 300 -output_vtk " + vtk)
     res, lines = run(drivers.stokes_main, cmd, OracleStokes)
     assert [s["step"] for s in res["steps"]] == [0, 1, 2]
     assert res["steps"][0]["exponent"] == 1.0 and res["steps"][2]["exponent"] == 3.0 and res["steps"][2]["regularization"] == pytest.approx(1e-2)
