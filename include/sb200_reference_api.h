@@ -10,7 +10,11 @@
 extern "C" {
 #endif
 
-/* chebyshev.h:31-34 */
+/* chebyshev.h:25-27: the 1-D operator (chebyshev.c:8-85), the same derivative as MatCreateCheb(rank 1, tr 0) */
+PetscErrorCode MatCreateChebD1(MPI_Comm comm, Vec vx, Vec vy, unsigned flag, Mat* A);
+PetscErrorCode ChebD1Mult(Mat A, Vec vx, Vec vy);
+PetscErrorCode ChebD1Destroy(Mat A);
+/* chebyshev.h:29-32 */
 PetscErrorCode MatCreateCheb(MPI_Comm comm, int rank, int tr, int* dims, unsigned flag, Vec vx, Vec vy, Mat* A);
 PetscErrorCode ChebMult(Mat A, Vec vx, Vec vy);
 PetscErrorCode ChebDestroy(Mat A);

@@ -69,6 +69,22 @@ PetscErrorCode ChebDestroy(Mat A) {
   return sb200_cheb_destroy(c);
 }
 
+// MatCreateChebD1 / ChebD1Mult / ChebD1Destroy (chebyshev.c:8-85): the 1-D operator; "n = %d but must be >= 2" and the
+// vx / vy size check are the reference's (chebyshev.c:18)
+PetscErrorCode MatCreateChebD1(MPI_Comm comm, Vec vx, Vec vy, unsigned flag, Mat* A) {
+  PetscInt n = 0, ny = 0;
+  CHK(VecGetSize(vx, &n));
+  CHK(VecGetSize(vy, &ny));
+  if (n != ny || n < 2) return SB200_ERR_USER;
+  int dims[1] = {(int)n};
+  CHK(MatCreateCheb(comm, 1, 0, dims, flag, vx, vy, A));
+  CHK(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))ChebD1Mult));
+  CHK(MatShellSetOperation(*A, MATOP_DESTROY, (void (*)(void))ChebD1Destroy));
+  return 0;
+}
+PetscErrorCode ChebD1Mult(Mat A, Vec vx, Vec vy) { return ChebMult(A, vx, vy); }
+PetscErrorCode ChebD1Destroy(Mat A) { return ChebDestroy(A); }
+
 // ---- elliptic.C ------------------------------------------------------------------------------
 struct MatEllipticB200 {  // MatElliptic (elliptic.C:78-86): the device state lives behind `e`
   sb200_elliptic* e;

@@ -86,6 +86,21 @@ static int test_cheb() {  // cheb.c:68-112 with the defaults m1=5, (m,n,p)=(8,7,
     double norm = 0;
     for (int i = 0; i < m1; i++) norm = fmax(norm, fabs(r[i] - a[i]));
     printf("cheb1d Norm of error %.12e\n", norm);
+    {  // cheb.c creates the 1-D operator with MatCreateChebD1(comm, u, b, FFTW_ESTIMATE, &A): same numbers
+      Mat A1;
+      CHK(MatCreateChebD1(PETSC_COMM_WORLD, u, b, FFTW_ESTIMATE, &A1));
+      CHK(MatMult(A1, u, b));
+      std::vector<double> r1(m1);
+      CHK(VecGetValuesHost(b, r1.data()));
+      double diff = 0;
+      for (int i = 0; i < m1; i++) diff = fmax(diff, fabs(r1[i] - r[i]));
+      printf("chebD1 vs cheb max diff %.3e\n", diff);
+      CHK(MatDestroy(A1));
+      Vec one;
+      CHK(VecCreateSeqCUDA(PETSC_COMM_WORLD, 1, &one));
+      printf("chebD1 n=1 -> %d\n", MatCreateChebD1(PETSC_COMM_WORLD, one, one, FFTW_ESTIMATE, &A1));  // chebyshev.c:18
+      CHK(VecDestroy(one));
+    }
     CHK(MatDestroy(A));
     CHK(VecDestroy(u));
     CHK(VecDestroy(b));

@@ -22,6 +22,7 @@ def test_reference_api_driver(cuda):
     assert f(r"cheb3d axis 0 Norm of error (\S+)") == pytest.approx(6.245e-06, rel=5e-3)
     assert f(r"cheb3d axis 1 Norm of error (\S+)") == pytest.approx(8.72e-05, rel=5e-3)
     assert f(r"cheb3d axis 2 Norm of error (\S+)") == pytest.approx(1.04e-03, rel=5e-3)
+    assert "chebD1 vs cheb max diff 0.000e+00" in txt and "chebD1 n=1 -> 83" in txt                # chebyshev.c:8-85, :18
     assert "cheb bad tr -> 83" in txt                                                           # chebyshev.c:106
     res = [float(x) for x in re.findall(r"Norm of exact residual\s*: abs = (\S+)", txt)]
     assert len(res) == 2 and res[0] < 5e-11 and res[1] < 5e-11                                  # 16^3 and 12^5, -exact 2
