@@ -185,38 +185,42 @@ def run_reference(args):
 
 def ksp_secondary(sp, torch, dev, G128, U128):
     """Secondary metric of BASELINE.json: 'KSP time to rtol 1e-10'.
-    (a) config 1, ./elliptic -dim 16,16,16 -exact 2 -ksp_rtol 1e-10: device FGMRES(30) on the MatShell with a host LU of
-        the finite-difference matrix as the PC stand-in (PETSc's PC is out of scope and timed separately);
-    (b) 128^3: one full FGMRES(30) cycle (30 iterations, no PC) on the benchmark operator: operator time vs KSP vector work."""
+    (a) config 1, ./elliptic -dim 16,16,16 -exact 2 -ksp_rtol 1e-10: device FGMRES(30) on the MatShell; the preconditioning
+        matrix is assembled on the device (FormJacobian = sb200_elliptic_jacobian_csr); the PC built from it is PETSc's own
+        and out of scope, so a HOST stand-in applies it and its time is reported separately: ILU(2), what the reference sets
+        in code (elliptic.C:183-184), and an exact LU;
+    (b) 128^3: one full FGMRES(30) cycle (30 iterations, no PC) on the benchmark operator: operator time vs KSP vector work.
+    Nothing here touches oracle/: exact solution and matrices come from the library itself."""
+    import scipy.sparse as sps
     import scipy.sparse.linalg as spla
-
-    from oracle.elliptic import MatElliptic  # checker-side input only: exact solution, FD matrix for the stand-in PC
 
     out = {}
     dim = [16, 16, 16]
-    O = MatElliptic(dim, gamma=0.0)
-    u, _ = O.create_exact_solution(2)
-    O.form_function(np.zeros(O.g))
-    lu = spla.splu(O.form_jacobian_matrix().tocsc())
+    u, u2, dirichlet = sp.elliptic_exact_solution(dim, 2)
     G = sp.Elliptic(dim, gamma=0.0)
-    G.set_dirichlet(torch.from_numpy(O.dirichlet).to(dev))
-    G.set_rhs(torch.from_numpy(O.b).to(dev))
+    G.set_dirichlet(torch.from_numpy(dirichlet).to(dev))
+    G.set_rhs(torch.from_numpy(u2).to(dev))
     F = G.form_function(torch.zeros(G.g, dtype=torch.float64, device=dev))
-    K = sp.KSP(G.g)
-    K.set_operators(G, pc=lambda r: torch.from_numpy(lu.solve(r.cpu().numpy())).to(dev))
-    K.set_tolerances(rtol=1e-10)
+    rowptr, colidx, vals = [t.cpu().numpy() for t in G.jacobian_csr()]
+    P = sps.csr_matrix((vals, colidx, rowptr), shape=(G.g, G.g))
     rhs = -F
-    K.solve(rhs)  # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    dx = K.solve(rhs)
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1e3
-    r, t = K.result, K.times_ms
-    out["config1_elliptic16_exact2"] = {"ksp_rtol": 1e-10, "iterations": r["its"], "reason": r["reason"], "time_ms_total": wall,
-                                        "time_ms_operator": t["operator"], "time_ms_pc_host_lu_standin": t["pc"], "time_ms_ksp_vector_work": t["ksp_vector_work"],
-                                        "time_ms_without_pc": wall - t["pc"], "norm_of_error": float((dx.cpu() - torch.from_numpy(u)).abs().max())}
-    K.destroy()
+    for name, solve in (("ilu2", sp.HostILU(P, 2).solve), ("lu", spla.splu(P.tocsc()).solve)):
+        K = sp.KSP(G.g)
+        K.set_operators(G, pc=lambda r, solve=solve: torch.from_numpy(solve(r.cpu().numpy())).to(dev))
+        K.set_tolerances(rtol=1e-10)
+        K.solve(rhs)  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dx = K.solve(rhs)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        r, t = K.result, K.times_ms
+        out["config1_elliptic16_exact2_pc_%s" % name] = {
+            "ksp_rtol": 1e-10, "pc": "host stand-in for PETSc's PC: " + ("ILU(2), the reference's in-code default" if name == "ilu2" else "exact LU (SuperLU)"),
+            "iterations": r["its"], "reason": r["reason"], "time_ms_total": wall, "time_ms_operator": t["operator"], "time_ms_pc_host_standin": t["pc"],
+            "time_ms_ksp_vector_work": t["ksp_vector_work"], "time_ms_without_pc": wall - t["pc"],
+            "norm_of_error": float((dx.cpu() - torch.from_numpy(u)).abs().max())}
+        K.destroy()
     G.destroy()
     K = sp.KSP(G128.g)
     K.set_operators(G128)
@@ -370,7 +374,10 @@ def run_cuda(args):
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_ksp:
-            line["ksp"] = ksp_secondary(sp, torch, dev, G, U)
+            try:
+                line["ksp"] = ksp_secondary(sp, torch, dev, G, U)
+            except Exception as e:  # the secondary metric must never cost the headline line
+                line["ksp"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
