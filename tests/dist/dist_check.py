@@ -1,7 +1,7 @@
 """Multi-process parity check of the slab partition: run under torchrun, one rank per GPU.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tools/dist_check.py 32 64 128
+      tests/dist/dist_check.py 32 64 128
 
 Every rank builds its slab context, the CUDA IPC handles are exchanged through torch.distributed, and
 FormFunction / MatMult_Elliptic (generic and fused slab paths) are compared with the oracle's
@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 import spectral_petsc_b200 as sp  # noqa: E402
 from spectral_petsc_b200 import dist as spd  # noqa: E402
 from oracle.elliptic import MatElliptic  # noqa: E402  (checker only)

@@ -1,7 +1,7 @@
 """Slab-partitioned Stokes shells under torchrun (one rank per GPU): parity against the oracle at a small extent and
 timing of StokesMatMult / StokesFunction at 128^3 (BASELINE config 5: -rheology 1 -exponent 3 -eps 1e-4).
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 tools/dist_stokes.py 24 128
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 tests/dist/dist_stokes.py 24 128
 """
 import json
 import os
@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 import spectral_petsc_b200 as sp  # noqa: E402
 from spectral_petsc_b200 import dist as spd  # noqa: E402
 

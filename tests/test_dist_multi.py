@@ -1,5 +1,5 @@
 """Multi-process slab partition on real GPUs (needs >= 2 devices; skipped on a 1-GPU box): torchrun launches
-tools/dist_check.py, which exchanges the CUDA IPC handles through torch.distributed and compares FormFunction /
+tests/dist/dist_check.py, which exchanges the CUDA IPC handles through torch.distributed and compares FormFunction /
 MatMult_Elliptic of every rank with the oracle's single-domain result (1e-12 max-norm relative)."""
 import json
 import os
@@ -23,7 +23,7 @@ def test_slab_multi_process(world):
     if _ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29700 + world), os.path.join(ROOT, "tools", "dist_check.py"), "32", "64"]
+           "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "dist", "dist_check.py"), "32", "64"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
     assert out.returncode == 0, out.stderr[-2000:]
@@ -35,7 +35,7 @@ def test_stokes_slab_multi_process(world):
     if _ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29720 + world), os.path.join(ROOT, "tools", "dist_stokes.py"), "16", "0"]
+           "--master-port", str(29720 + world), os.path.join(ROOT, "tests", "dist", "dist_stokes.py"), "16", "0"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
     assert out.returncode == 0, out.stderr[-2000:]
