@@ -86,3 +86,31 @@ def test_entry_count_closed_form(fdlib):
         assert nnz == g + sum(2 * (n[j] - 1) * g // n[j] for j in range(d))
     # 128^3: 2,000,376 rows (SURVEY 8 header), 7-point stencil
     assert nrows.value == 5832 and nnz == 5832 + 3 * 2 * 17 * 18 * 18
+
+
+def test_row_offsets_random_grids(fdlib):
+    """Property check of the closed-form CSR offsets on random grids up to 6-D (extents 3..7, i.e. interior extents 1..5):
+    rows tile [0, nnz) exactly, columns increase, every row holds its diagonal and only walk-order neighbours."""
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        d = int(rng.integers(1, 7))
+        dim = [int(v) for v in rng.integers(3, 8, size=d)]
+        m = int(np.prod(dim))
+        n = [v - 2 for v in dim]
+        g = int(np.prod(n))
+        eta = 1.0 + rng.random(m)
+        for ncomp in (1, 2):
+            rowptr, colidx, vals = host_csr(fdlib, dim, ncomp, eta, None, None, unrolled=int(rng.integers(0, 2)))
+            assert rowptr[0] == 0 and rowptr[-1] == colidx.size and (np.diff(rowptr) >= 1).all()
+            assert (colidx >= 0).all() and (colidx < g * ncomp).all() and not np.isnan(vals).any()
+            istr = [int(np.prod(n[j + 1:])) for j in range(d)]
+            for r in rng.integers(0, g * ncomp, size=min(50, g * ncomp)):
+                cols = colidx[rowptr[r]:rowptr[r + 1]]
+                assert (np.diff(cols) > 0).all() and r in cols
+                node, f = divmod(int(r), ncomp)
+                offs = sorted(set(abs(int(c) // ncomp - node) for c in cols if c != r))
+                assert all(int(c) % ncomp == f for c in cols) and all(o in istr for o in offs)
+            # symmetric positive weights: off-diagonals negative, diagonal = -(sum of ALL 2d neighbour weights) > |row sum of kept ones|
+            A = sps.csr_matrix((vals, colidx, rowptr), shape=(g * ncomp, g * ncomp))
+            assert (A.diagonal() > 0).all() and (A - sps.diags(A.diagonal())).max() <= 0
+            assert (np.asarray(A.sum(axis=1)).ravel() >= -1e-9 * A.diagonal()).all()
