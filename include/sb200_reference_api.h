@@ -60,6 +60,12 @@ PetscErrorCode StokesMatMultVV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultPV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultVP(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y);
+/* StokesMatMultSchur (stokes.C:523-535): y = -PV * KSPSolve(KSPSchurVelocity, VP * x).  The inner KSP is PETSc's; it is registered
+ * here as a callback on device Vecs (with PETSc: `return KSPSolve((KSP)ksp, rhs, sol);`).  Without one the shell's MULT fails
+ * with PETSC_ERR_ARG_*, like a KSPSolve on an unset KSP would. */
+typedef PetscErrorCode (*StokesVelocitySolve)(void* ksp, Vec rhs, Vec sol);
+PetscErrorCode StokesSetSchurVelocitySolve(StokesCtxB200* ctx, StokesVelocitySolve solve, void* ksp);
+PetscErrorCode StokesMatMultSchur(Mat S, Vec xG, Vec yG);
 PetscErrorCode StokesFunction(SNES snes, Vec xG, Vec yG, void* ctx);
 PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2);
 /* the inner shells created by StokesCreate (stokes.C:308-325) and the SeqAIJ matrix MatVVPC (stokes.C:326) */

@@ -46,6 +46,7 @@ int sb200_malloc(void** d_ptr, size_t bytes);
 int sb200_free(void* d_ptr);
 int sb200_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int sb200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int sb200_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int sb200_memset0(void* d_dst, size_t bytes, void* stream);
 int sb200_stream_sync(void* stream);
 

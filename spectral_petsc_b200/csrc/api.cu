@@ -99,6 +99,11 @@ int sb200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream)
   return 0;
 }
 
+int sb200_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+  SB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 int sb200_memset0(void* d_dst, size_t bytes, void* stream) {
   SB_CUDA(cudaMemsetAsync(d_dst, 0, bytes, (cudaStream_t)stream));
   return 0;

@@ -193,6 +193,8 @@ struct StokesCtxB200 {
   StokesOptionsB200 opt;
   long long m, g, gp, gv, dv;
   Mat MatVV, MatPV, MatVP, MatSchur, MatVVPC;
+  StokesVelocitySolve svel = nullptr;  // KSPSolve(KSPSchurVelocity, ., .) (stokes.C:531)
+  void* svel_ksp = nullptr;
 };
 
 static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std::vector<double>* U2, std::vector<double>* D) {
@@ -228,6 +230,7 @@ PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A,
   CHK(MatCreateShell(comm, (PetscInt)c->g, (PetscInt)c->g, 0, 0, c, A));
   CHK(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))StokesMatMult));  // stokes.C:309
   CHK(MatCreateShell(comm, (PetscInt)c->gp, (PetscInt)c->gp, 0, 0, c, &c->MatSchur));
+  CHK(MatShellSetOperation(c->MatSchur, MATOP_MULT, (void (*)(void))StokesMatMultSchur));                 // :318
   CHK(MatShellSetOperation(c->MatSchur, MATOP_GET_DIAGONAL, (void (*)(void))StokesMatGetDiagonalSchur));  // :319
   CHK(MatCreateShell(comm, (PetscInt)c->gp, (PetscInt)c->gv, 0, 0, c, &c->MatPV));
   CHK(MatShellSetOperation(c->MatPV, MATOP_MULT, (void (*)(void))StokesMatMultPV));  // :321
@@ -273,6 +276,35 @@ PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y) {  // stokes.C:542-553
   PetscScalar* a;
   CHK(VecCUDAGetArrayWrite(y, &a));
   return sb200_stokes_get_diagonal_schur(c->s, a, nullptr);
+}
+
+PetscErrorCode StokesSetSchurVelocitySolve(StokesCtxB200* c, StokesVelocitySolve solve, void* ksp) {
+  c->svel = solve;
+  c->svel_ksp = ksp;
+  return 0;
+}
+
+// the C ABI hands the inner solve raw device pointers; wrap them as Vecs for the PETSc-side callback
+static int schur_velocity_trampoline(void* vctx, const double* d_rhs, double* d_sol, void*) {
+  StokesCtxB200* c = (StokesCtxB200*)vctx;
+  Vec rhs = nullptr, sol = nullptr;
+  PetscErrorCode rc = VecCreateSeqCUDAWithArray(PETSC_COMM_SELF, (PetscInt)c->gv, (double*)d_rhs, &rhs);
+  if (!rc) rc = VecCreateSeqCUDAWithArray(PETSC_COMM_SELF, (PetscInt)c->gv, d_sol, &sol);
+  if (!rc) rc = c->svel(c->svel_ksp, rhs, sol);
+  if (rhs) VecDestroy(rhs);
+  if (sol) VecDestroy(sol);
+  return rc;
+}
+
+PetscErrorCode StokesMatMultSchur(Mat S, Vec xG, Vec yG) {  // stokes.C:523-535
+  StokesCtxB200* c = nullptr;
+  CHK(MatShellGetContext(S, (void**)&c));
+  if (!c->svel) return SB200_ERR_ARG;
+  const PetscScalar* x;
+  PetscScalar* y;
+  CHK(VecCUDAGetArrayRead(xG, &x));
+  CHK(VecCUDAGetArrayWrite(yG, &y));
+  return sb200_stokes_matmult_schur(c->s, x, y, schur_velocity_trampoline, c, nullptr);
 }
 
 PetscErrorCode StokesFunction(SNES, Vec xG, Vec yG, void* ctx) {  // stokes.C:680-758
