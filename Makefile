@@ -13,10 +13,14 @@ OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 DRIVER    := tests/cpp/ref_api_driver
+DRIVER2   := tests/cpp/ref_api_driver2
 
-all: $(LIB) $(DRIVER)
+all: $(LIB) $(DRIVER) $(DRIVER2)
 
 $(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
+	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
+
+$(DRIVER2): tests/cpp/ref_api_driver2.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
@@ -35,6 +39,6 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(DRIVER)
+	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2)
 
 .PHONY: all clean

@@ -86,21 +86,6 @@ static int test_cheb() {  // cheb.c:68-112 with the defaults m1=5, (m,n,p)=(8,7,
     double norm = 0;
     for (int i = 0; i < m1; i++) norm = fmax(norm, fabs(r[i] - a[i]));
     printf("cheb1d Norm of error %.12e\n", norm);
-    {  // cheb.c creates the 1-D operator with MatCreateChebD1(comm, u, b, FFTW_ESTIMATE, &A): same numbers
-      Mat A1;
-      CHK(MatCreateChebD1(PETSC_COMM_WORLD, u, b, FFTW_ESTIMATE, &A1));
-      CHK(MatMult(A1, u, b));
-      std::vector<double> r1(m1);
-      CHK(VecGetValuesHost(b, r1.data()));
-      double diff = 0;
-      for (int i = 0; i < m1; i++) diff = fmax(diff, fabs(r1[i] - r[i]));
-      printf("chebD1 vs cheb max diff %.3e\n", diff);
-      CHK(MatDestroy(A1));
-      Vec one;
-      CHK(VecCreateSeqCUDA(PETSC_COMM_WORLD, 1, &one));
-      printf("chebD1 n=1 -> %d\n", MatCreateChebD1(PETSC_COMM_WORLD, one, one, FFTW_ESTIMATE, &A1));  // chebyshev.c:18
-      CHK(VecDestroy(one));
-    }
     CHK(MatDestroy(A));
     CHK(VecDestroy(u));
     CHK(VecDestroy(b));
@@ -197,18 +182,6 @@ static int test_elliptic(int d, int* dim, int exact) {  // elliptic.C:159-209
   return 0;
 }
 
-// stands for KSPSolve(KSPSchurVelocity, rhs, sol) with -svel_ksp_type preonly -svel_pc_type none: sol = rhs
-static PetscErrorCode identity_solve(void* calls, Vec rhs, Vec sol) {
-  ++*(int*)calls;
-  PetscInt n;
-  VecGetSize(rhs, &n);
-  const PetscScalar* a;
-  PetscScalar* b;
-  VecCUDAGetArrayRead(rhs, &a);
-  VecCUDAGetArrayWrite(sol, &b);
-  return sb200_memcpy_d2d(b, a, (size_t)n * sizeof(double), nullptr);
-}
-
 static int test_stokes(int n0) {  // stokes.C:139-212
   StokesOptionsB200 opt;
   opt.numDims = 3;
@@ -240,38 +213,6 @@ static int test_stokes(int n0) {  // stokes.C:139-212
   CHK(VecSetValuesHost(x, ns.data()));
   CHK(MatMult(A, x, r));
   printf("Null space test |A ns| = %9.3e\n", norm_inf(r));
-  {  // the Schur shell (stokes.C:318, 523-535): with the inner solve replaced by the identity, S p = -PV (VP p)
-    Mat MatVV, MatPV, MatVP, MatSchur;
-    CHK(StokesGetShells(ctx, &MatVV, &MatPV, &MatVP, &MatSchur));
-    PetscInt gp, gv;
-    CHK(MatGetSize(MatPV, &gp, &gv));
-    Vec p, sp, v, q;
-    CHK(VecCreateSeqCUDA(PETSC_COMM_SELF, gp, &p));
-    CHK(VecDuplicate(p, &sp));
-    CHK(VecDuplicate(p, &q));
-    CHK(VecCreateSeqCUDA(PETSC_COMM_SELF, gv, &v));
-    std::vector<double> hp(gp), hs(gp), hq(gp);
-    for (PetscInt i = 0; i < gp; i++) hp[i] = sin(0.37 * i) + 0.01 * (i % 7);
-    CHK(VecSetValuesHost(p, hp.data()));
-    printf("Schur without an inner solve -> %d\n", MatMult(MatSchur, p, sp));
-    int calls = 0;
-    CHK(StokesSetSchurVelocitySolve(ctx, identity_solve, &calls));
-    CHK(MatMult(MatSchur, p, sp));
-    CHK(MatMult(MatVP, p, v));
-    CHK(MatMult(MatPV, v, q));
-    CHK(VecGetValuesHost(sp, hs.data()));
-    CHK(VecGetValuesHost(q, hq.data()));
-    double diff = 0, big = 0;
-    for (PetscInt i = 0; i < gp; i++) {
-      diff = fmax(diff, fabs(hs[i] + hq[i]));
-      big = fmax(big, fabs(hq[i]));
-    }
-    printf("Schur identity-solve calls %d  max |S p + PV VP p| / max |PV VP p| = %.3e\n", calls, diff / big);
-    CHK(VecDestroy(p));
-    CHK(VecDestroy(sp));
-    CHK(VecDestroy(q));
-    CHK(VecDestroy(v));
-  }
   {  // PCShellSetContext(pc, ctx); PCShellSetSetUp(pc, StokesPCSetUp0) (stokes.C:163-166)
     PC pc;
     Mat MatVVPC;
