@@ -1,0 +1,74 @@
+"""Per-P table SURVEY 8d asks for: ChebMult (one axis derivative) and MatMult_Elliptic at P in {16, 32, 48, 64, 96, 128, 129} on
+every kernel path that supports the extent, timed with CUDA events (L2 flushed between steps), with both rooflines beside each
+number: t_hbm = algorithmic bytes / measured copy bandwidth, t_fp64 = algorithmic flops / measured DMMA peak.  Also times the
+device assembly of the finite-difference preconditioning matrix.  One JSON line per row; nothing here reads oracle/.
+
+usage: python tools/p_sweep.py [steps] > gpurun_out/p_sweep.jsonl
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spectral_petsc_b200 as sp  # noqa: E402
+from tools.time_ops import timeit  # noqa: E402
+
+FP64_TFLOPS = 37.1  # tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.jsonl)
+
+
+def hbm_gbs():
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("hbm_gbs", 6452.2))
+    except Exception:
+        return 6452.2
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    bw = hbm_gbs()
+    rng = np.random.default_rng(0)
+    for P in (16, 32, 48, 64, 96, 128, 129):
+        m = P ** 3
+        x = torch.from_numpy(rng.standard_normal(m)).to(dev)
+        y = torch.empty_like(x)
+        for tr in (0, 2):  # strided and contiguous axis
+            C = sp.Cheb(3, tr, [P] * 3)
+            ms = timeit(lambda: C.mult(x, y), steps, flush)
+            fl, by = 2.0 * P * m, 16.0 * m
+            print(json.dumps({"op": "ChebMult", "P": P, "axis": tr, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6, "t_fp64_ms": fl / FP64_TFLOPS / 1e9,
+                              "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}), flush=True)
+            C.destroy()
+        E = sp.Elliptic([P] * 3, gamma=4.0, exponent=2.0)
+        us = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(E.g)).to(dev)
+        E.form_function(us)
+        U = torch.from_numpy(rng.standard_normal(E.g)).to(dev)
+        V = torch.empty_like(U)
+        fl, by = 6 * 2.0 * P * m, 8.0 * (2 * E.g + 5 * m)  # 2d derivatives; U, V, eta, deta, gradu[3] once each
+        for path, name in ((1, "generic"), (2, "chain per axis"), (3, "persistent chain")):
+            if path > 1 and P not in (32, 64, 128):
+                continue
+            E.set_path(path)
+            l0 = sp.launch_count()
+            E.mat_mult(U, V)
+            nl = sp.launch_count() - l0
+            ms = timeit(lambda: E.mat_mult(U, V), steps, flush)
+            print(json.dumps({"op": "MatMult_Elliptic", "P": P, "path": name, "launches": nl, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6,
+                              "t_fp64_ms": fl / FP64_TFLOPS / 1e9, "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}), flush=True)
+        E.set_path(0)
+        csr = E.jacobian_csr()
+        ms_full = timeit(lambda: E.jacobian_csr(), steps, flush)  # includes the torch.empty of the three output arrays
+        ms_vals = timeit(lambda: E.jacobian_csr(pattern=csr[:2]), steps, flush)
+        nnz = csr[2].numel()
+        by_vals = 8.0 * 5 * m + 8.0 * nnz  # eta, deta, gradu[3] once; values written
+        print(json.dumps({"op": "FormJacobian (device CSR)", "P": P, "rows": E.g, "nnz": nnz, "ms_pattern_and_values": ms_full, "ms_values_only": ms_vals,
+                          "t_hbm_ms_values_only": by_vals / bw / 1e6, "frac_of_hbm_roofline": by_vals / bw / 1e6 / ms_vals}), flush=True)
+        E.destroy()
+
+
+if __name__ == "__main__":
+    main()
