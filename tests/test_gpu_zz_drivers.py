@@ -34,9 +34,9 @@ def test_elliptic_config1_and_nonlinear(cuda):
     assert rg["ksp_its"] == ro["ksp_its"] == [13] and abs(rg["error_abs"] - ro["error_abs"]) < 1e-11 + 1e-3 * ro["error_abs"]
     assert np.abs(rg["x"] - ro["x"]).max() < 1e-9
     # tests.sh: the nonlinear 2-D problem
-    ro, rg, _, _ = both(drivers.elliptic_main, "-dim 24,24 -exact 0 -cos_scale 3 -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12", OracleElliptic)
-    assert abs(rg["snes_its"] - ro["snes_its"]) <= 1 and all(abs(a - b) <= 1 for a, b in zip(rg["ksp_its"], ro["ksp_its"]))
-    assert abs(rg["error_abs"] - ro["error_abs"]) < 1e-9
+    ro, rg, _, _ = both(drivers.elliptic_main, "-dim 24,24 -exact 0 -cos_scale 3 -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12 -pc_type lu", OracleElliptic)
+    assert abs(rg["snes_its"] - ro["snes_its"]) <= 1 and all(abs(a - b) <= 2 for a, b in zip(rg["ksp_its"], ro["ksp_its"]))
+    assert rg["reason"] == ro["reason"] == "CONVERGED_FNORM_RELATIVE" and abs(rg["error_abs"] - ro["error_abs"]) < 1e-9
 
 
 def test_stokes_continuation_and_vtk(cuda, tmp_path):
