@@ -14,14 +14,18 @@ HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 DRIVER    := tests/cpp/ref_api_driver
 DRIVER2   := tests/cpp/ref_api_driver2
+APP_ELL   := apps/elliptic
 
-all: $(LIB) $(DRIVER) $(DRIVER2)
+all: $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL)
 
 $(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
 
 $(DRIVER2): tests/cpp/ref_api_driver2.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
+
+$(APP_ELL): apps/elliptic.cpp $(LIB) $(HDRS)
+	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -39,6 +43,6 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2)
+	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL)
 
 .PHONY: all clean

@@ -151,3 +151,22 @@ def test_command_line_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, "-m", "spectral_petsc_b200.stokes", "-pcvel", "2"], capture_output=True, text=True, timeout=300,
                        cwd=root, env=dict(os.environ, PYTHONPATH=root))
     assert r.returncode == 83 and "pcvel type number 2 not implemented" in r.stderr
+
+
+def test_native_executable_option_errors_and_no_fallback():
+    """apps/elliptic (C++): option errors are PETSC_ERR_USER before any device work; without a GPU the run fails loudly."""
+    import os
+    import subprocess
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "apps", "elliptic")
+    assert os.path.exists(exe), "run `make` first"
+    for bad in (["-dim", "8,8", "-exact", "0"], ["dim"], ["-dim", "1,2,3,4,5,6,7,8,9,10,11"], ["-pc_type", "sor", "-exact", "1"], ["-ksp_type", "cg", "-exact", "1"]):
+        r = subprocess.run([exe] + bad, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 83 and r.stderr.startswith("error:"), (bad, r.stderr)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "-dim", "8,8", "-exact", "1"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 97 and "error 97" in r.stderr  # SB200_ERR_CUDA: no device, no CPU path
+        assert r.stdout.startswith("Elliptic problem  dims = [8,8]    gamma = 0.000000    exponent = 2.000000")

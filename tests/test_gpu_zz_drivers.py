@@ -86,3 +86,34 @@ def test_command_lines(cuda):
     assert err < 1e-6  # 7.8e-08 over the oracle
     r = subprocess.run([sys.executable, "-m", "spectral_petsc_b200.stokes", "-boundary", "2"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 83 and "Boundary type 2 not implemented" in r.stderr
+
+
+def test_native_elliptic_executable(cuda):
+    """apps/elliptic: the reference's ./elliptic in C++ over the reference-API layer, the device FGMRES and the host ILU(2)
+    stand-in - no Python in the solve.  Same lines and the same counts as the Python flow over the oracle."""
+    exe = os.path.join(ROOT, "apps", "elliptic")
+    assert os.path.exists(exe), "run `make` (or __graft_entry__.build()) first"
+    cmd = "-dim 16,16,16 -exact 2 -ksp_rtol 1e-10"  # BASELINE.json configs[0]
+    r = subprocess.run([exe] + cmd.split(), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    out = r.stdout.split("\n")
+    lo = []
+    ro = drivers.elliptic_main(cmd.split(), out=lo.append, make_problem=OracleElliptic)
+    assert out[:2] == lo[:2]  # header, DOF distribution
+    assert out[2].startswith("Norm of exact residual   : abs = ") and float(out[2].split("abs =")[1].split()[0]) < 5e-11
+    assert "Number of nonlinear iterations = 1" in out and "Reason for solver termination: CONVERGED_FNORM_RELATIVE" in out
+    kits = [int(t) for t in [l for l in out if l.startswith("KSP iterations per Newton step:")][0].split(":")[1].split()]
+    assert len(kits) == 1 and abs(kits[0] - ro["ksp_its"][0]) <= 1  # 16 with ILU(2)
+    err = float([l for l in out if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+    assert err < 5e-9
+    # the nonlinear problem of tests.sh: same number of Newton steps as the Python flow
+    cmd = "-dim 24,24 -exact 0 -cos_scale 3 -gamma 4 -ksp_rtol 1e-10 -snes_rtol 1e-10 -snes_monitor"
+    r = subprocess.run([exe] + cmd.split(), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    ro = drivers.elliptic_main(cmd.split(), out=lo.append, make_problem=OracleElliptic)
+    its = int([l for l in r.stdout.split("\n") if l.startswith("Number of nonlinear iterations")][0].split("=")[1])
+    assert abs(its - ro["snes_its"]) <= 1 and "CONVERGED_FNORM_RELATIVE" in r.stdout
+    err = float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+    assert abs(err - ro["error_abs"]) < 1e-8
+    # errors follow the reference: unknown exact solution, missing -cos_scale
+    assert subprocess.run([exe, "-dim", "8,8", "-exact", "0"], capture_output=True, text=True).returncode == 83
