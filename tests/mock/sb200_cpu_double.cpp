@@ -1,12 +1,13 @@
 // TEST DOUBLE - never built into libspectral_b200.so, never shipped, never used by bench.py or the package.
 //
-// A plain-CPU stand-in for the DEVICE-side entry points of include/spectral_b200.h (memory helpers, the elliptic shells, the
-// FGMRES), so that the HOST layer of the product - host/reference_api.cpp, host/petsc_shim.cpp, host/host_ilu.cpp,
+// A plain-CPU stand-in for the DEVICE-side entry points of include/spectral_b200.h (memory helpers, the elliptic and Stokes shells,
+// the FGMRES), so that the HOST layer of the product - host/reference_api.cpp, host/petsc_shim.cpp, host/host_ilu.cpp,
 // csrc/exact.cpp, csrc/fd_rows.h and the native executable apps/elliptic.cpp - can be linked UNCHANGED against it and driven
 // end to end in the CPU test suite (tests/test_native_cpu_double.py): option handling, Newton loop, PC refresh, printed lines,
 // iteration counts.  "Device" pointers are host pointers here.  The arithmetic follows the same definitions as the oracle
 // (dense CGL differentiation matrix per axis, reference operation order), which is all a host-logic test needs; GPU parity
 // is tested on the GPU (tests/test_gpu_*.py), never through this file.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,17 @@ struct sb200_elliptic {
   double gamma = 0.0, exponent = 2.0;
 };
 
+struct sb200_stokes {
+  int d;
+  std::vector<int> dim;
+  long long m, gp;
+  std::vector<long long> stride, ixI, ixB;  // interior / boundary nodes in walk order
+  std::vector<std::vector<double>> D, xnode, strain;
+  std::vector<double> eta, deta, dirichlet, force;
+  int rheology = 0;
+  double hardness = 1.0, exponent = 1.0, reg = 1.0, gamma0 = 1.0, min_eta = 1.0, max_eta = 1.0;
+};
+
 struct sb200_ksp {
   long long n;
   int restart;
@@ -80,11 +92,132 @@ void pad(const sb200_elliptic* e, const double* U, bool with_dirichlet, double* 
   for (size_t q = 0; q < e->ixD.size(); q++) w0[e->ixD[q]] = with_dirichlet ? e->dirichlet[q] : 0.0;
 }
 
+// ---- Stokes helpers ---------------------------------------------------------------------------------------------------------
+// derivative along `axis` of a field with nc interleaved components per node
+void st_deriv(const sb200_stokes* s, int axis, const double* x, int nc, double* y) {
+  const int P = s->dim[axis];
+  const long long R = s->stride[axis], O = s->m / (R * P);
+  const double* D = s->D[axis].data();
+  for (long long o = 0; o < O; o++)
+    for (long long r = 0; r < R; r++)
+      for (int c = 0; c < nc; c++)
+        for (int i = 0; i < P; i++) {
+          double acc = 0;
+          for (int j = 0; j < P; j++) acc += D[(size_t)i * P + j] * x[((o * P + j) * R + r) * nc + c];
+          y[((o * P + i) * R + r) * nc + c] = acc;
+        }
+}
+
+std::vector<double> st_vel_local(const sb200_stokes* s, const double* vG, bool with_dirichlet) {
+  const int d = s->d;
+  std::vector<double> xL(s->m * d, 0.0);
+  for (long long q = 0; q < s->gp; q++)
+    for (int k = 0; k < d; k++) xL[s->ixI[q] * d + k] = vG[q * d + k];
+  if (with_dirichlet)
+    for (size_t q = 0; q < s->ixB.size(); q++)
+      for (int k = 0; k < d; k++) xL[s->ixB[q] * d + k] = s->dirichlet[q * d + k];
+  return xL;
+}
+
+// Neville evaluation of the interpolant through (x_i, f_i), i < n, at the two points t0 and t1 (util.C:129-144 computes the same)
+void neville2(int n, const double* x, const double* f, double t0, double t1, double* f0, double* f1) {
+  std::vector<double> a(f, f + n), b(f, f + n);
+  for (int lvl = 1; lvl < n; lvl++)
+    for (int i = 0; i < n - lvl; i++) {
+      const double den = x[i] - x[i + lvl];
+      a[i] = ((t0 - x[i + lvl]) * a[i] + (x[i] - t0) * a[i + 1]) / den;
+      b[i] = ((t1 - x[i + lvl]) * b[i] + (x[i] - t1) * b[i + 1]) / den;
+    }
+  *f0 = a[0];
+  *f1 = b[0];
+}
+
+// StokesPressureReduceOrder (stokes.C:1029-1080): extend the interior pressure to the boundary nodes, z lines then y lines
+// (planes i >= 1), then x lines; later passes read what earlier ones wrote
+void st_reduce_order(const sb200_stokes* s, double* pres) {
+  const int d = s->d, m = s->dim[0], n = s->dim[1], p = d == 2 ? 1 : s->dim[2];
+  std::vector<double> f(std::max(std::max(m, n), p));
+  for (int i = 1; i < m; i++) {
+    if (p > 1)
+      for (int j = 1; j < n; j++) {
+        double* line = pres + ((long long)i * n + j) * p;
+        for (int k = 1; k < p - 1; k++) f[k - 1] = line[k];
+        neville2(p - 2, s->xnode[2].data() + 1, f.data(), s->xnode[2][0], s->xnode[2][p - 1], &line[0], &line[p - 1]);
+      }
+    for (int k = 0; k < p; k++) {
+      double* line = pres + (long long)i * n * p + k;
+      for (int j = 1; j < n - 1; j++) f[j - 1] = line[(long long)j * p];
+      neville2(n - 2, s->xnode[1].data() + 1, f.data(), s->xnode[1][0], s->xnode[1][n - 1], &line[0], &line[(long long)(n - 1) * p]);
+    }
+  }
+  for (int j = 0; j < n; j++)
+    for (int k = 0; k < p; k++) {
+      double* line = pres + (long long)j * p + k;
+      const long long st = (long long)n * p;
+      for (int i = 1; i < m - 1; i++) f[i - 1] = line[i * st];
+      neville2(m - 2, s->xnode[0].data() + 1, f.data(), s->xnode[0][0], s->xnode[0][m - 1], &line[0], &line[(m - 1) * st]);
+    }
+}
+
+std::vector<double> st_vv(const sb200_stokes* s, const double* xG) {  // StokesMatMultVV (stokes.C:623-676)
+  const int d = s->d;
+  const long long m = s->m;
+  const std::vector<double> xL = st_vel_local(s, xG, false);
+  std::vector<std::vector<double>> V(d, std::vector<double>(m * d)), W(d, std::vector<double>(m * d));
+  for (int j = 0; j < d; j++) st_deriv(s, j, xL.data(), d, V[j].data());
+  for (long long i = 0; i < m; i++) {
+    double e[3][3], z = 0;
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) {
+        e[j][k] = 0.5 * (V[j][i * d + k] + V[k][i * d + j]);
+        z += e[j][k] * s->strain[j][i * d + k];
+      }
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) W[j][i * d + k] = s->eta[i] * e[j][k] + s->deta[i] * s->strain[j][i * d + k] * z;
+  }
+  std::vector<double> yL(m * d, 0.0), t(m * d), y(s->gp * d);
+  for (int j = 0; j < d; j++) {
+    st_deriv(s, j, W[j].data(), d, t.data());
+    for (long long i = 0; i < m * d; i++) yL[i] -= t[i];
+  }
+  for (long long q = 0; q < s->gp; q++)
+    for (int k = 0; k < d; k++) y[q * d + k] = yL[s->ixI[q] * d + k];
+  return y;
+}
+
+std::vector<double> st_div(const sb200_stokes* s, const double* vG, bool with_dirichlet) {  // StokesDivergence (stokes.C:570-595)
+  const int d = s->d;
+  const long long m = s->m;
+  const std::vector<double> xL = st_vel_local(s, vG, with_dirichlet);
+  std::vector<double> comp(m), t(m), acc(m, 0.0), y(s->gp);
+  for (int k = 0; k < d; k++) {
+    for (long long i = 0; i < m; i++) comp[i] = xL[i * d + k];
+    st_deriv(s, k, comp.data(), 1, t.data());
+    for (long long i = 0; i < m; i++) acc[i] += t[i];
+  }
+  for (long long q = 0; q < s->gp; q++) y[q] = acc[s->ixI[q]];
+  return y;
+}
+
+std::vector<double> st_grad(const sb200_stokes* s, const double* pG) {  // StokesMatMultVP (stokes.C:599-619)
+  const int d = s->d;
+  const long long m = s->m;
+  std::vector<double> pL(m, 0.0), t(m), y(s->gp * d);
+  for (long long q = 0; q < s->gp; q++) pL[s->ixI[q]] = pG[q];
+  st_reduce_order(s, pL.data());
+  for (int k = 0; k < d; k++) {
+    st_deriv(s, k, pL.data(), 1, t.data());
+    for (long long q = 0; q < s->gp; q++) y[q * d + k] = t[s->ixI[q]];
+  }
+  return y;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* sb200_last_error(void) { return g_err.c_str(); }
+long long sb200_launch_count(void) { return 0; }  // nothing is launched here
 int sb200_malloc(void** p, size_t bytes) {
   *p = std::calloc(bytes ? bytes : 8, 1);
   return *p ? 0 : SB200_ERR_CUDA;
@@ -373,23 +506,214 @@ int sb200_ksp_destroy(sb200_ksp* k) {
   return 0;
 }
 
-// ---- the Stokes shells are not doubled: the host layer links, a call reports "not supported" --------------------------------
-#define NOSTOKES(name, ...) \
-  int name(__VA_ARGS__) { FAIL(SB200_ERR_SUP, #name ": not provided by the CPU test double"); }
-NOSTOKES(sb200_stokes_create, int, const int*, sb200_stokes**)
-NOSTOKES(sb200_stokes_destroy, sb200_stokes*)
-NOSTOKES(sb200_stokes_sizes, const sb200_stokes*, long long*, long long*, long long*, long long*, long long*)
-NOSTOKES(sb200_stokes_set_rheology, sb200_stokes*, int, double, double, double, double)
-NOSTOKES(sb200_stokes_set_dirichlet, sb200_stokes*, const double*, void*)
-NOSTOKES(sb200_stokes_set_force, sb200_stokes*, const double*, void*)
-NOSTOKES(sb200_stokes_matmult, sb200_stokes*, const double*, double*, void*)
-NOSTOKES(sb200_stokes_matmult_vv, sb200_stokes*, const double*, double*, void*)
-NOSTOKES(sb200_stokes_matmult_pv, sb200_stokes*, const double*, double*, void*)
-NOSTOKES(sb200_stokes_matmult_vp, sb200_stokes*, const double*, double*, void*)
-NOSTOKES(sb200_stokes_get_diagonal_schur, sb200_stokes*, double*, void*)
-NOSTOKES(sb200_stokes_matmult_schur, sb200_stokes*, const double*, double*, sb200_velocity_solve_fn, void*, void*)
-NOSTOKES(sb200_stokes_function, sb200_stokes*, const double*, double*, void*)
-NOSTOKES(sb200_stokes_pc_velocity_sizes, sb200_stokes*, long long*, long long*)
-NOSTOKES(sb200_stokes_pc_velocity_csr, sb200_stokes*, int*, int*, double*, void*)
+// ---- Stokes shells (stokes.C:499-758, 1029-1080, 1160-1240, 1920-1944), -boundary 0 ------------------------------------------
+int sb200_stokes_create(int d, const int* dim, sb200_stokes** out) {
+  *out = nullptr;
+  if (d != 2 && d != 3) FAIL(SB200_ERR_USER, "the Stokes shells need 2 or 3 dimensions (stokes.C:1036)");
+  for (int j = 0; j < d; j++)
+    if (dim[j] < 3) FAIL(SB200_ERR_USER, "each extent must be >= 3");
+  sb200_stokes* s = new sb200_stokes();
+  s->d = d;
+  s->dim.assign(dim, dim + d);
+  s->stride.assign(d, 1);
+  s->m = 1;
+  for (int j = d - 1; j >= 0; j--) {
+    s->stride[j] = s->m;
+    s->m *= dim[j];
+  }
+  std::vector<int> ind(d, 0);
+  for (long long node = 0; node < s->m; node++) {  // StokesSetupDomain walk (stokes.C:791-879)
+    bool bdy = false;
+    for (int j = 0; j < d; j++) bdy = bdy || ind[j] == 0 || ind[j] == dim[j] - 1;
+    (bdy ? s->ixB : s->ixI).push_back(node);
+    for (int j = d - 1; j >= 0; j--) {
+      if (++ind[j] < dim[j]) break;
+      ind[j] = 0;
+    }
+  }
+  s->gp = (long long)s->ixI.size();
+  for (int j = 0; j < d; j++) {
+    s->D.push_back(cgl_diff_matrix(dim[j]));
+    std::vector<double> x(dim[j]);
+    for (int i = 0; i < dim[j]; i++) x[i] = cos(i * M_PI / (dim[j] - 1));
+    s->xnode.push_back(x);
+  }
+  s->eta.assign(s->m, 1.0);
+  s->deta.assign(s->m, 0.0);
+  s->strain.assign(d, std::vector<double>(s->m * d, 0.0));
+  s->dirichlet.assign(s->ixB.size() * d, 0.0);
+  s->force.assign(s->gp * (d + 1), 0.0);
+  *out = s;
+  return 0;
+}
+int sb200_stokes_destroy(sb200_stokes* s) {
+  delete s;
+  return 0;
+}
+int sb200_stokes_sizes(const sb200_stokes* s, long long* m, long long* g, long long* gp, long long* gv, long long* dv) {
+  if (m) *m = s->m;
+  if (g) *g = s->gp * (s->d + 1);
+  if (gp) *gp = s->gp;
+  if (gv) *gv = s->gp * s->d;
+  if (dv) *dv = (long long)s->ixB.size() * s->d;
+  return 0;
+}
+int sb200_stokes_set_rheology(sb200_stokes* s, int type, double hardness, double exponent, double regularization, double gamma0) {
+  if (type != 0 && type != 1) FAIL(SB200_ERR_SUP, "Rheology type not implemented");
+  s->rheology = type;
+  s->hardness = hardness;
+  s->exponent = exponent;
+  s->reg = regularization;
+  s->gamma0 = gamma0;
+  return 0;
+}
+int sb200_stokes_set_dirichlet(sb200_stokes* s, const double* v, void*) {
+  s->dirichlet.assign(v, v + s->dirichlet.size());
+  return 0;
+}
+int sb200_stokes_set_force(sb200_stokes* s, const double* f, void*) {
+  s->force.assign(f, f + s->force.size());
+  return 0;
+}
+int sb200_stokes_matmult_vv(sb200_stokes* s, const double* x, double* y, void*) {
+  std::vector<double> v = st_vv(s, x);
+  std::copy(v.begin(), v.end(), y);
+  return 0;
+}
+int sb200_stokes_matmult_pv(sb200_stokes* s, const double* x, double* y, void*) {
+  std::vector<double> p = st_div(s, x, false);
+  std::copy(p.begin(), p.end(), y);
+  return 0;
+}
+int sb200_stokes_matmult_vp(sb200_stokes* s, const double* x, double* y, void*) {
+  std::vector<double> v = st_grad(s, x);
+  std::copy(v.begin(), v.end(), y);
+  return 0;
+}
+int sb200_stokes_matmult(sb200_stokes* s, const double* x, double* y, void*) {  // stokes.C:499-519
+  const int d = s->d;
+  std::vector<double> v(s->gp * d), p(s->gp);
+  for (long long q = 0; q < s->gp; q++) {
+    for (int k = 0; k < d; k++) v[q * d + k] = x[q * (d + 1) + k];
+    p[q] = x[q * (d + 1) + d];
+  }
+  const std::vector<double> vv = st_vv(s, v.data()), pv = st_div(s, v.data(), false), vp = st_grad(s, p.data());
+  for (long long q = 0; q < s->gp; q++) {
+    for (int k = 0; k < d; k++) y[q * (d + 1) + k] = vv[q * d + k] + vp[q * d + k];
+    y[q * (d + 1) + d] = pv[q];
+  }
+  return 0;
+}
+int sb200_stokes_get_diagonal_schur(sb200_stokes* s, double* y, void*) {
+  for (long long q = 0; q < s->gp; q++) y[q] = 1.0 / s->eta[s->ixI[q]];
+  return 0;
+}
+int sb200_stokes_matmult_schur(sb200_stokes* s, const double* x, double* y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream) {
+  if (!solve) FAIL(SB200_ERR_ARG, "StokesMatMultSchur needs the inner velocity solve");
+  std::vector<double> v0 = st_grad(s, x), v1(v0.size());
+  if (int rc = solve(solve_ctx, v0.data(), v1.data(), stream)) return rc;
+  std::vector<double> p = st_div(s, v1.data(), false);
+  for (long long q = 0; q < s->gp; q++) y[q] = -p[q];
+  return 0;
+}
+int sb200_stokes_function(sb200_stokes* s, const double* x, double* y, void*) {  // stokes.C:680-758
+  const int d = s->d;
+  const long long m = s->m;
+  std::vector<double> v(s->gp * d), p(s->gp);
+  for (long long q = 0; q < s->gp; q++) {
+    for (int k = 0; k < d; k++) v[q * d + k] = x[q * (d + 1) + k];
+    p[q] = x[q * (d + 1) + d];
+  }
+  std::vector<double> xL = st_vel_local(s, v.data(), true);
+  std::vector<std::vector<double>> raw(d, std::vector<double>(m * d)), V(d, std::vector<double>(m * d));
+  for (int j = 0; j < d; j++) st_deriv(s, j, xL.data(), d, raw[j].data());
+  s->min_eta = 1e300;
+  s->max_eta = -1e300;
+  for (long long i = 0; i < m; i++) {
+    double gamma = 0;
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) {
+        const double e = 0.5 * (raw[j][i * d + k] + raw[k][i * d + j]);
+        s->strain[j][i * d + k] = e;
+        gamma += 0.5 * (e * e);
+      }
+    if (s->rheology == 0) {
+      s->eta[i] = 1.0;
+      s->deta[i] = 0.0;
+    } else {  // StokesRheologyPower (stokes.C:1930-1944)
+      const double n = s->exponent, pw = (1.0 - n) / (2.0 * n), base = s->reg + gamma / s->gamma0;
+      s->eta[i] = s->hardness * pow(base, pw);
+      s->deta[i] = fabs(n) > 1.0e-5 ? s->hardness * pw / s->gamma0 * pow(base, pw - 1.0) : 0.0;
+    }
+    s->min_eta = fmin(s->min_eta, s->eta[i]);
+    s->max_eta = fmax(s->max_eta, s->eta[i]);
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) V[j][i * d + k] = s->eta[i] * s->strain[j][i * d + k];
+  }
+  std::vector<double> yL(m * d, 0.0), t(m * d);
+  for (int j = 0; j < d; j++) {
+    st_deriv(s, j, V[j].data(), d, t.data());
+    for (long long i = 0; i < m * d; i++) yL[i] -= t[i];
+  }
+  const std::vector<double> pv = st_div(s, v.data(), true), vp = st_grad(s, p.data());
+  for (long long q = 0; q < s->gp; q++) {
+    for (int k = 0; k < d; k++) y[q * (d + 1) + k] = yL[s->ixI[q] * d + k] + vp[q * d + k] - s->force[q * (d + 1) + k];
+    y[q * (d + 1) + d] = pv[q] - s->force[q * (d + 1) + d];
+  }
+  return 0;
+}
+int sb200_stokes_eta_minmax(sb200_stokes* s, double* mn, double* mx, void*) {
+  *mn = s->min_eta;
+  *mx = s->max_eta;
+  return 0;
+}
+int sb200_stokes_get_state(sb200_stokes* s, int which, double* out, void*) {
+  if (which == 0) std::copy(s->eta.begin(), s->eta.end(), out);
+  else if (which == 1) std::copy(s->deta.begin(), s->deta.end(), out);
+  else if (which >= 2 && which < 2 + s->d) std::copy(s->strain[which - 2].begin(), s->strain[which - 2].end(), out);
+  else FAIL(SB200_ERR_USER, "state selector out of range");
+  return 0;
+}
+int sb200_stokes_pressure_reduce_order(sb200_stokes* s, double* pL, void*) {
+  st_reduce_order(s, pL);
+  return 0;
+}
+int sb200_stokes_pc_velocity_sizes(sb200_stokes* s, long long* nrows, long long* nnz) {
+  FdGrid G;
+  fd_grid_init(&G, s->d, s->dim.data());
+  if (nrows) *nrows = G.g * s->d;
+  if (nnz) *nnz = fd_total_entries(G) * s->d;
+  return 0;
+}
+int sb200_stokes_pc_velocity_csr(sb200_stokes* s, int* rowptr, int* colidx, double* vals, void*) {
+  FdGrid G;
+  fd_grid_init(&G, s->d, s->dim.data());
+  const int nc = s->d;
+  std::vector<double> x;
+  for (int j = 0; j < s->d; j++) x.insert(x.end(), s->xnode[j].begin(), s->xnode[j].end());
+  FdFields F;
+  F.xtab = x.data();
+  F.eta = s->eta.data();
+  F.deta = nullptr;
+  for (int j = 0; j < SB200_FD_MAX_DIM; j++) F.gradu[j] = nullptr;
+  for (long long r = 0; r < G.g; r++) {
+    int k[SB200_FD_MAX_DIM];
+    long long cols[2 * SB200_FD_MAX_DIM + 1];
+    double v[2 * SB200_FD_MAX_DIM + 1];
+    const long long node = fd_decode(G, r, k);
+    const int n = fd_row(G, F, r, k, node, cols, v);
+    const long long base = fd_row_offset(G, k, r) * nc;
+    for (int f = 0; f < nc; f++) {
+      const long long o = base + (long long)f * n;
+      if (rowptr) rowptr[r * nc + f] = (int)o;
+      for (int q = 0; q < n; q++) {
+        if (colidx) colidx[o + q] = (int)(cols[q] * nc + f);
+        vals[o + q] = v[q];
+      }
+    }
+  }
+  if (rowptr) rowptr[G.g * nc] = (int)(fd_total_entries(G) * nc);
+  return 0;
+}
 
 }  // extern "C"
