@@ -24,7 +24,7 @@ $(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
 $(DRIVER2): tests/cpp/ref_api_driver2.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
 
-$(APP_ELL): apps/elliptic.cpp $(LIB) $(HDRS)
+$(APP_ELL): apps/elliptic.cpp apps/common.h $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)

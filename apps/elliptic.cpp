@@ -11,73 +11,13 @@
 //   * SNES: full Newton steps with the step halved while the residual norm does not decrease (PETSc's cubic line search is
 //     PETSc's); its vector updates are done on the host copy of x (one 8 g-byte transfer per Newton step).
 // The Python command line (python -m spectral_petsc_b200.elliptic) runs the identical flow; tests compare the two.
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
+#include "common.h"
 
-#include "../include/sb200_reference_api.h"
-#include "../include/spectral_b200.h"
-
-#define CHK(expr)                                                                          \
-  do {                                                                                     \
-    PetscErrorCode _e = (expr);                                                            \
-    if (_e) {                                                                              \
-      fprintf(stderr, "%s:%d error %d: %s\n", __FILE__, __LINE__, _e, sb200_last_error()); \
-      return _e;                                                                           \
-    }                                                                                      \
-  } while (0)
+using app::HostPc;
+using app::norm2;
+using app::Options;
 
 namespace {
-
-// ---- the slice of the PETSc options database the driver reads ------------------------------------------------------------
-struct Options {
-  std::map<std::string, std::string> kv;
-  std::map<std::string, bool> used;
-  static bool number(const char* s) {
-    char* end = nullptr;
-    strtod(s, &end);
-    return end != s && *end == 0;
-  }
-  int parse(int argc, char** argv) {
-    for (int i = 1; i < argc;) {
-      const char* a = argv[i];
-      if (a[0] != '-' || number(a)) {
-        fprintf(stderr, "error: expected an option name, got '%s'\n", a);
-        return 83;
-      }
-      if (i + 1 < argc && (argv[i + 1][0] != '-' || number(argv[i + 1]))) {
-        kv[a + 1] = argv[i + 1];
-        i += 2;
-      } else {
-        kv[a + 1] = "";
-        i += 1;
-      }
-    }
-    return 0;
-  }
-  const std::string* get(const char* name) {
-    used[name] = true;
-    auto it = kv.find(name);
-    return it == kv.end() ? nullptr : &it->second;
-  }
-  bool has(const char* name) { return get(name) != nullptr; }
-  int integer(const char* name, int dflt) {
-    const std::string* v = get(name);
-    return v && !v->empty() ? atoi(v->c_str()) : dflt;
-  }
-  double real(const char* name, double dflt) {
-    const std::string* v = get(name);
-    return v && !v->empty() ? atof(v->c_str()) : dflt;
-  }
-  std::string str(const char* name, const char* dflt) {
-    const std::string* v = get(name);
-    return v && !v->empty() ? *v : std::string(dflt);
-  }
-};
 
 // ---- KSP callbacks ---------------------------------------------------------------------------------------------------------
 // MatMult(A, x, y) on raw device arrays, the way PETSc's KSP calls the MatShell
@@ -94,66 +34,7 @@ int op_matmult(void* ctx, const double* d_x, double* d_y, void*) {
   return rc;
 }
 
-struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
-  std::string type;
-  int levels = 2;
-  sb200_host_ilu* ilu = nullptr;
-  std::vector<int> rowptr, colidx;
-  std::vector<double> vals, dinv, hx, hy;
-  int n = 0;
-};
-
-int pc_apply(void* ctx, const double* d_x, double* d_y, void* stream) {
-  HostPc* pc = (HostPc*)ctx;
-  const size_t bytes = (size_t)pc->n * sizeof(double);
-  if (pc->type == "none") return sb200_memcpy_d2d(d_y, d_x, bytes, stream);
-  int rc = sb200_memcpy_d2h(pc->hx.data(), d_x, bytes, stream);
-  if (!rc) rc = sb200_stream_sync(stream);
-  if (rc) return rc;
-  if (pc->type == "jacobi") {
-    for (int i = 0; i < pc->n; i++) pc->hy[i] = pc->dinv[i] * pc->hx[i];
-  } else {
-    rc = sb200_host_ilu_solve(pc->ilu, pc->hx.data(), pc->hy.data());
-    if (rc) return rc;
-  }
-  rc = sb200_memcpy_h2d(d_y, pc->hy.data(), bytes, stream);
-  return rc ? rc : sb200_stream_sync(stream);  // hy is reused by the next application
-}
-
-// PCSetUp: bring the values of P down (pattern once) and (re)factor
-int pc_setup(HostPc* pc, Mat P) {
-  PetscInt n, nz;
-  CHK(MatGetSize(P, &n, PETSC_NULL));
-  CHK(MatSeqAIJGetCSRHost(P, &nz, PETSC_NULL, PETSC_NULL, PETSC_NULL));
-  const bool first = pc->rowptr.empty();
-  if (first) {
-    pc->n = n;
-    pc->rowptr.resize(n + 1);
-    pc->colidx.resize(nz);
-    pc->vals.resize(nz);
-    pc->hx.resize(n);
-    pc->hy.resize(n);
-    CHK(MatSeqAIJGetCSRHost(P, PETSC_NULL, pc->rowptr.data(), pc->colidx.data(), pc->vals.data()));
-  } else {
-    CHK(MatSeqAIJGetCSRHost(P, PETSC_NULL, PETSC_NULL, PETSC_NULL, pc->vals.data()));
-  }
-  if (pc->type == "ilu") {
-    if (first) CHK(sb200_host_ilu_create(n, pc->rowptr.data(), pc->colidx.data(), pc->vals.data(), pc->levels, &pc->ilu));
-    else CHK(sb200_host_ilu_refactor(pc->ilu, pc->vals.data()));
-  } else if (pc->type == "jacobi") {
-    pc->dinv.assign(n, 1.0);
-    for (int i = 0; i < n; i++)
-      for (int p = pc->rowptr[i]; p < pc->rowptr[i + 1]; p++)
-        if (pc->colidx[p] == i) pc->dinv[i] = 1.0 / pc->vals[p];
-  }
-  return 0;
-}
-
-double norm2(const std::vector<double>& v) {
-  double s = 0;
-  for (double x : v) s += x * x;
-  return sqrt(s);
-}
+int pc_apply(void* ctx, const double* d_x, double* d_y, void* stream) { return ((HostPc*)ctx)->apply_device(d_x, d_y, stream); }
 
 }  // namespace
 
@@ -164,24 +45,12 @@ int main(int argc, char** argv) {
   AppCtx ac;
   int dim[10] = {8, 6};
   ac.d = 2;
-  if (const std::string* v = o.get("dim")) {
-    ac.d = 0;
-    const char* p = v->c_str();
-    while (*p) {
-      char* end = nullptr;
-      const long x = strtol(p, &end, 10);
-      if (end == p) break;
-      if (ac.d == 10) {
-        fprintf(stderr, "error: -dim takes at most 10 extents (elliptic.C:138)\n");
-        return 83;
-      }
-      dim[ac.d++] = (int)x;
-      p = (*end == ',') ? end + 1 : end;
-    }
-    if (ac.d == 0) {
-      fprintf(stderr, "error: -dim takes comma-separated integers\n");
+  if (const int nd = o.int_array("dim", dim, 10)) {
+    if (nd < 0) {
+      fprintf(stderr, "error: -dim takes 1..10 comma-separated integers (elliptic.C:138)\n");
       return 83;
     }
+    ac.d = nd;
   }
   ac.dim = dim;
   ac.debug = o.integer("debug", 0);
@@ -199,7 +68,7 @@ int main(int argc, char** argv) {
   HostPc pc;
   pc.type = o.str("pc_type", "ilu");  // PCSetType(pc, PCILU); PCFactorSetLevels(pc, 2): elliptic.C:183-184
   pc.levels = o.integer("pc_factor_levels", 2);
-  if (pc.type != "ilu" && pc.type != "jacobi" && pc.type != "none") {
+  if (!HostPc::known(pc.type)) {
     fprintf(stderr, "error: unknown PC type '%s' (have: ilu, jacobi, none)\n", pc.type.c_str());
     return 83;
   }
@@ -277,7 +146,7 @@ int main(int argc, char** argv) {
     MatStructure flag;
     CHK(FormJacobian(snes, x, &A, &P, &flag, &ac));  // about the state the last FormFunction(x) cached
     pc.n = m;
-    if (pc.type != "none") CHK(pc_setup(&pc, P));
+    CHK(pc.setup(P));
     for (int i = 0; i < m; i++) hr[i] = -hF[i];
     CHK(VecSetValuesHost(rhs, hr.data()));
     CHK(sb200_memset0(dx->d_array, (size_t)m * sizeof(double), nullptr));
@@ -320,11 +189,9 @@ int main(int argc, char** argv) {
   printf("KSP iterations per Newton step:");
   for (int k : kits) printf(" %d", k);
   printf("\n");
-  for (auto& kvp : o.kv)
-    if (!o.used.count(kvp.first)) printf("WARNING! There are options you set that were not used: -%s\n", kvp.first.c_str());
+  o.warn_unused();
 
   sb200_ksp_destroy(ksp);
-  if (pc.ilu) sb200_host_ilu_destroy(pc.ilu);
   CHK(SNESDestroy(snes));
   CHK(MatDestroy(A));
   CHK(MatDestroy(P));

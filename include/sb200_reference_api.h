@@ -75,6 +75,13 @@ PetscErrorCode StokesGetPCMatrix(StokesCtxB200* ctx, Mat* MatVVPC);
  * from the eta the last StokesFunction cached.  The PC shell's context is the Stokes context (stokes.C:163). */
 PetscErrorCode StokesPCSetUp0(PC pc);
 PetscErrorCode StokesSetContinuation(StokesCtxB200* ctx, PetscReal exponent, PetscReal regularization); /* stokes.C:218-219 */
+/* StokesPressureReduceOrder(pL, ctx) (stokes.C:1029-1080) on a local pressure Vec of m doubles, in place */
+PetscErrorCode StokesPressureReduceOrder(Vec pL, StokesCtxB200* ctx);
+/* what the driver reads out of the context: VecMin / VecMax of c->eta (stokes.C:731-734), the DOF counts printed at :891, and
+ * the cached fields StokesStateView dumps (:1821-1894): which = 0 eta (m), 1 deta (m), 2+j strain[j] (m*d) */
+PetscErrorCode StokesGetEtaMinMax(StokesCtxB200* ctx, PetscReal* minEta, PetscReal* maxEta);
+PetscErrorCode StokesGetSizes(StokesCtxB200* ctx, PetscInt* m, PetscInt* g, PetscInt* gp, PetscInt* gv, PetscInt* dv);
+PetscErrorCode StokesGetState(StokesCtxB200* ctx, PetscInt which, Vec out);
 
 #ifdef __cplusplus
 }

@@ -347,6 +347,34 @@ PetscErrorCode StokesPCSetUp0(PC pc) {  // stokes.C:1160-1240 (the KSPSetOperato
   return assemble_aij<sb200_stokes>(c->MatVVPC, c->s, sb200_stokes_pc_velocity_sizes, sb200_stokes_pc_velocity_csr);
 }
 
+PetscErrorCode StokesPressureReduceOrder(Vec pL, StokesCtxB200* c) {  // stokes.C:1029-1080
+  PetscScalar* p;
+  if (pL->n != (PetscInt)c->m) return SB200_ERR_USER;
+  CHK(VecCUDAGetArrayWrite(pL, &p));
+  return sb200_stokes_pressure_reduce_order(c->s, p, nullptr);
+}
+
+PetscErrorCode StokesGetEtaMinMax(StokesCtxB200* c, PetscReal* minEta, PetscReal* maxEta) {  // stokes.C:731-734
+  return sb200_stokes_eta_minmax(c->s, minEta, maxEta, nullptr);
+}
+
+PetscErrorCode StokesGetSizes(StokesCtxB200* c, PetscInt* m, PetscInt* g, PetscInt* gp, PetscInt* gv, PetscInt* dv) {  // stokes.C:891
+  if (m) *m = (PetscInt)c->m;
+  if (g) *g = (PetscInt)c->g;
+  if (gp) *gp = (PetscInt)c->gp;
+  if (gv) *gv = (PetscInt)c->gv;
+  if (dv) *dv = (PetscInt)c->dv;
+  return 0;
+}
+
+PetscErrorCode StokesGetState(StokesCtxB200* c, PetscInt which, Vec out) {  // the fields StokesStateView writes (stokes.C:1868-1885)
+  const long long need = which < 2 ? c->m : c->m * c->opt.numDims;
+  if (out->n != (PetscInt)need) return SB200_ERR_USER;
+  PetscScalar* a;
+  CHK(VecCUDAGetArrayWrite(out, &a));
+  return sb200_stokes_get_state(c->s, (int)which, a, nullptr);
+}
+
 PetscErrorCode StokesSetContinuation(StokesCtxB200* c, PetscReal exponent, PetscReal regularization) {
   c->opt.exponent = exponent;
   c->opt.regularization = regularization;
