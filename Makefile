@@ -15,8 +15,9 @@ HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 DRIVER    := tests/cpp/ref_api_driver
 DRIVER2   := tests/cpp/ref_api_driver2
 APP_ELL   := apps/elliptic
+APP_STK   := apps/stokes
 
-all: $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL)
+all: $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK)
 
 $(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
@@ -25,6 +26,9 @@ $(DRIVER2): tests/cpp/ref_api_driver2.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
 
 $(APP_ELL): apps/elliptic.cpp apps/common.h $(LIB) $(HDRS)
+	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
+
+$(APP_STK): apps/stokes.cpp apps/common.h $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
@@ -43,6 +47,6 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL)
+	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK)
 
 .PHONY: all clean

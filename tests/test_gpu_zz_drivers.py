@@ -117,3 +117,46 @@ def test_native_elliptic_executable(cuda):
     assert abs(err - ro["error_abs"]) < 1e-8
     # errors follow the reference: unknown exact solution, missing -cos_scale
     assert subprocess.run([exe, "-dim", "8,8", "-exact", "0"], capture_output=True, text=True).returncode == 83
+
+
+def test_native_stokes_executable(cuda, tmp_path):
+    """apps/stokes: the reference's ./stokes in C++ (reference-API layer, device FGMRES for every Krylov solve, host ILU stand-in,
+    saddle-point PC / Newton / continuation orchestrated in C++) - same counts, errors and stokes.vtk as the Python flow over the oracle."""
+    exe = os.path.join(ROOT, "apps", "stokes")
+    assert os.path.exists(exe), "run `make` (or __graft_entry__.build()) first"
+    vn, vp = str(tmp_path / "native.vtk"), str(tmp_path / "python.vtk")
+    cmd = ("-exact 2 -cont 2 -rheology 1 -eps 1e-2 -exponent 3 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -dim 8,8,8 "
+           "-ksp_rtol 1e-6 -ksp_max_it 300 -output_vtk ")
+    r = subprocess.run([exe] + (cmd + vn).split(), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr + r.stdout
+    out = r.stdout.strip().split("\n")
+    lo = []
+    ro = drivers.stokes_main((cmd + vp).split(), out=lo.append, make_problem=OracleStokes)
+    assert out[:3] == lo[:3]
+    assert [l for l in out if l.startswith("## [")] == [l for l in lo if l.startswith("## [")]
+    steps = []
+    for i, l in enumerate(out):
+        if l.startswith("Number of nonlinear iterations"):
+            steps.append((int(l.split("=")[1]), out[i + 1].split(": ")[1], float(out[i + 2].split("abs =")[1]), [int(t) for t in out[i + 3].split(":")[1].split()]))
+    assert len(steps) == len(ro["steps"]) == 3
+    for (its, reason, err, kits), b in zip(steps, ro["steps"]):
+        assert reason == b["reason"] == "CONVERGED_FNORM_RELATIVE" and abs(its - b["snes_its"]) <= 1
+        assert all(abs(x - y) <= 1 + y // 10 for x, y in zip(kits, b["ksp_its"]))
+        assert abs(err - b["error"]) <= 1e-3 * b["error"] + 1e-8
+    tn, tp = open(vn).read().split("\n"), open(vp).read().split("\n")
+    assert len(tn) == len(tp)
+    for a, b in zip(tn, tp):
+        if a[:1].isalpha() or a.startswith("#") or not a.strip():
+            assert a == b
+        else:
+            assert np.allclose([float(t) for t in a.split()], [float(t) for t in b.split()], rtol=1e-5, atol=1e-6)
+    # BASELINE config 4 (README:44) with ILU(2) where the README asks for hypre: 26 outer iterations over the oracle (245 with ILU(0), 11 with LU)
+    r = subprocess.run([exe] + ("-exact 2 -cont0 1 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_type fgmres -dim 20,20,20 -ksp_rtol 1e-10 "
+                                "-ksp_max_it 400 -vel_pc_factor_levels 2 -svel_pc_factor_levels 2").split(),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "DOF distribution: 23328 global   5832/8000 pressure    17496/24000 velocity    6504 dirichlet    0 mixed" in r.stdout
+    assert "Reason for solver termination: CONVERGED_FNORM_RELATIVE" in r.stdout
+    assert float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1]) < 1e-6
+    kits = [int(t) for t in [l for l in r.stdout.split("\n") if l.startswith("KSP iterations per Newton step:")][0].split(":")[1].split()]
+    assert len(kits) == 1 and abs(kits[0] - 26) <= 2

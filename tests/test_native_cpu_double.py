@@ -9,9 +9,20 @@ import subprocess
 import pytest
 
 from spectral_petsc_b200 import drivers
-from support.oracle_problems import OracleElliptic
+from support.oracle_problems import OracleElliptic, OracleStokes
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+HOST = ["tests/mock/sb200_cpu_double.cpp", "spectral_petsc_b200/host/reference_api.cpp", "spectral_petsc_b200/host/petsc_shim.cpp",
+        "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
+
+
+@pytest.fixture(scope="module")
+def stokes_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("native") / "stokes_cpu_double")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out, os.path.join(ROOT, "apps", "stokes.cpp")] + [os.path.join(ROOT, s) for s in HOST])
+    return out
 
 
 @pytest.fixture(scope="module")
@@ -58,3 +69,62 @@ def test_monitors_and_unused_option_warning(exe):
     out, its, kits, _, _, _ = native(exe, "-dim 12,12 -exact 0 -cos_scale 1 -gamma 4 -snes_monitor -ksp_monitor -typo 3")
     assert sum("SNES Function norm" in l for l in out) == its + 1 and sum(l.startswith("    KSP iterations") for l in out) == its
     assert out[-1] == "WARNING! There are options you set that were not used: -typo"
+
+
+# ---- apps/stokes.cpp ------------------------------------------------------------------------------------------------------------
+def native_stokes(exe, cmd):
+    r = subprocess.run([exe] + cmd.split(), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr + r.stdout
+    out = r.stdout.strip().split("\n")
+    steps = []
+    for i, l in enumerate(out):
+        if l.startswith("Number of nonlinear iterations"):
+            steps.append({"snes_its": int(l.split("=")[1]), "reason": out[i + 1].split(": ")[1], "error": float(out[i + 2].split("abs =")[1]),
+                          "ksp_its": [int(t) for t in out[i + 3].split(":")[1].split()]})
+    return out, steps
+
+
+BASE = "-schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly"
+STOKES_CASES = [
+    "-exact 2 -cont0 1 " + BASE + " -ksp_type fgmres -dim 10,10,10 -ksp_rtol 1e-10 -ksp_max_it 200",                                   # README:44 shape, ILU(0) for hypre
+    "-exact 2 -cont 2 -rheology 1 -eps 1e-2 -exponent 3 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-6 -ksp_max_it 300",       # README:55 shape (BASELINE config 5)
+    "-exact 2 -cont0 1 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 1 -vel_pc_factor_levels 2 -svel_pc_factor_levels 2",
+    "-exact 2 -cont0 1 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 2 -svel_pc_type jacobi",
+    "-exact 2 -cont0 1 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 3 -vel_pc_factor_levels 1",  # svel: GMRES, not preonly
+]
+
+
+@pytest.mark.parametrize("cmd", STOKES_CASES)
+def test_native_stokes_flow_equals_python_flow(stokes_exe, cmd):
+    out, steps = native_stokes(stokes_exe, cmd)
+    lines = []
+    ro = drivers.stokes_main(cmd.split(), out=lines.append, make_problem=OracleStokes)
+    assert out[:3] == lines[:3]  # problem header (2 lines), DOF distribution
+    assert [l for l in out if l.startswith("## [")] == [l for l in lines if l.startswith("## [")]  # continuation banners
+    assert len(steps) == len(ro["steps"])
+    for a, b in zip(steps, ro["steps"]):
+        assert (a["snes_its"], a["reason"]) == (b["snes_its"], b["reason"])
+        assert len(a["ksp_its"]) == len(b["ksp_its"]) and all(abs(x - y) <= 1 for x, y in zip(a["ksp_its"], b["ksp_its"]))
+        assert abs(a["error"] - b["error"]) <= 1e-3 * b["error"] + 1e-8  # the solves stop at their tolerances on both sides
+
+
+def test_native_stokes_vtk_equals_python_vtk(stokes_exe, tmp_path):
+    import numpy as np
+
+    cmd = "-exact 2 -cont 1 -rheology 1 -eps 1e-2 -exponent 2 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -snes_max_it 10 -output_vtk "
+    vn, vp = str(tmp_path / "native.vtk"), str(tmp_path / "python.vtk")
+    native_stokes(stokes_exe, cmd + vn)
+    drivers.stokes_main((cmd + vp).split(), out=lambda s: None, make_problem=OracleStokes)
+    tn, tp = open(vn).read().split("\n"), open(vp).read().split("\n")
+    assert len(tn) == len(tp)
+    for a, b in zip(tn, tp):
+        if a[:1].isalpha() or a.startswith("#") or not a.strip():
+            assert a == b
+        else:
+            assert np.allclose([float(t) for t in a.split()], [float(t) for t in b.split()], rtol=1e-5, atol=1e-7)
+
+
+def test_native_stokes_option_errors(stokes_exe):
+    for bad in ("-boundary 1", "-rheology 2", "-pcvel 1", "-pc_saddle_type 4", "-ksp_type gmres", "-dim 8,8,8,8", "-exact 3", "-vel_pc_type hypre"):
+        r = subprocess.run([stokes_exe, "-exact", "2"] + bad.split(), capture_output=True, text=True, timeout=60)
+        assert r.returncode == 83 and r.stderr.startswith("error:"), (bad, r.stderr)
