@@ -11,8 +11,10 @@
 
 #ifdef __CUDACC__
 #define SB_FD_HD __host__ __device__ __forceinline__
+#define SB_FD_UNROLL _Pragma("unroll")
 #else
 #define SB_FD_HD inline
+#define SB_FD_UNROLL
 #endif
 
 #define SB200_FD_MAX_DIM 10  // elliptic.C:138
@@ -72,7 +74,7 @@ template <int D = 0>
 SB_FD_HD long long fd_decode(const FdGrid& G, long long r, int* k) {
   const int d = D > 0 ? D : G.d;
   long long node = 0;
-#pragma unroll
+SB_FD_UNROLL
   for (int j = 0; j < d; j++) {
     const long long q = r / G.istride[j];
     r -= q * G.istride[j];
@@ -87,7 +89,7 @@ template <int D = 0>
 SB_FD_HD int fd_row_entries(const FdGrid& G, const int* k) {
   const int d = D > 0 ? D : G.d;
   int n = 1;
-#pragma unroll
+SB_FD_UNROLL
   for (int j = 0; j < d; j++) n += (k[j] > 0) + (k[j] < G.dim[j] - 3);
   return n;
 }
@@ -99,18 +101,18 @@ template <int D = 0>
 SB_FD_HD long long fd_row_offset(const FdGrid& G, const int* k, long long r) {
   const int d = D > 0 ? D : G.d;
   long long missing = 0;
-#pragma unroll
+SB_FD_UNROLL
   for (int j = 0; j < d; j++) {
     const int n = G.dim[j] - 2;
-#pragma unroll
+SB_FD_UNROLL
     for (int side = 0; side < 2; side++) {
       const int v = side ? n - 1 : 0;
       long long c = 0;
-#pragma unroll
+SB_FD_UNROLL
       for (int a = 0; a < j; a++) c += (long long)k[a] * (G.istride[a] / n);  // differs before j: k'_j free -> pinned to v
       if (v < k[j]) c += G.istride[j];                                        // differs at j with k'_j = v
       if (k[j] == v)
-#pragma unroll
+SB_FD_UNROLL
         for (int a = j + 1; a < d; a++) c += (long long)k[a] * G.istride[a];  // agrees through j, differs after
       missing += c;
     }
@@ -125,7 +127,7 @@ template <int D = 0>
 SB_FD_HD int fd_row(const FdGrid& G, const FdFields& F, long long r, const int* k, long long node, long long* cols, double* vals) {
   const int d = D > 0 ? D : G.d;
   int nM = 0;
-#pragma unroll
+SB_FD_UNROLL
   for (int j = 0; j < d; j++) nM += (k[j] > 0);
   const int n = fd_row_entries<D>(G, k);
   // sorted layout: M neighbours of axes 0..d-1 (columns r - istride[j], increasing with j), the diagonal, then the P
@@ -134,7 +136,7 @@ SB_FD_HD int fd_row(const FdGrid& G, const FdFields& F, long long r, const int* 
   double diag = 0.0;
   const double e0 = F.eta[node];
   const double de0 = F.deta ? F.deta[node] : 0.0;
-#pragma unroll
+SB_FD_UNROLL
   for (int j = 0; j < d; j++) {
     const long long iM = node - G.stride[j], iP = node + G.stride[j];
     const double* X = F.xtab + G.xoff[j];
