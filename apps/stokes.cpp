@@ -47,6 +47,11 @@ struct Pool {
     return VecCreateSeqCUDA(PETSC_COMM_SELF, n, &v) ? nullptr : v;
   }
   void put(Vec v) { free_[v->n].push_back(v); }
+  void clear() {  // before main returns: static destructors run after the CUDA runtime has begun to unload
+    for (auto& kv : free_)
+      for (Vec v : kv.second) VecDestroy(v);
+    free_.clear();
+  }
 };
 Pool g_pool;
 struct Tmp {  // RAII lease of a pooled device vector
@@ -563,6 +568,7 @@ int main(int argc, char** argv) {
   }
   o.warn_unused();
 
+  g_pool.clear();
   CHK(SNESDestroy(snes));
   CHK(StokesDestroy(F.ctx));
   CHK(MatDestroy(F.A));
