@@ -373,6 +373,23 @@ def run_cuda(args):
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_extras:
+            # per-P table of SURVEY 8d and the set-up kernels (tools/p_sweep.py), after and outside every timed region above;
+            # bounded in time and never allowed to cost the headline line
+            try:
+                import itertools
+
+                from tools.p_sweep import rows, stokes_rows
+
+                t_ex, extra = time.perf_counter(), []
+                for row in itertools.chain(stokes_rows(steps=5, dev=dev, flush=flush), rows(steps=5, dev=dev, flush=flush)):
+                    extra.append({k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()})
+                    if time.perf_counter() - t_ex > 60.0:
+                        extra.append({"truncated": "60 s budget reached"})
+                        break
+                line["p_sweep"] = extra
+            except Exception as e:
+                line["p_sweep"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_ksp:
             try:
                 line["ksp"] = ksp_secondary(sp, torch, dev, G, U)
@@ -392,6 +409,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--path", type=int, default=None, help="kernel path override (1 generic, 2 fused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-P sweep (ChebMult, MatMult_Elliptic on every path, device FormJacobian)")
     ap.add_argument("--no-ksp", action="store_true", help="skip the secondary 'KSP time to rtol 1e-10' measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -26,13 +26,14 @@ def hbm_gbs():
         return 6452.2
 
 
-def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-    dev = torch.device("cuda:0")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def rows(steps=10, Ps=(16, 32, 48, 64, 96, 128, 129), dev=None, flush=None):
+    """Yields one dict per measured row (see the module docstring)."""
+    dev = dev or torch.device("cuda:0")
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     bw = hbm_gbs()
     rng = np.random.default_rng(0)
-    for P in (16, 32, 48, 64, 96, 128, 129):
+    for P in Ps:
         m = P ** 3
         x = torch.from_numpy(rng.standard_normal(m)).to(dev)
         y = torch.empty_like(x)
@@ -40,8 +41,8 @@ def main():
             C = sp.Cheb(3, tr, [P] * 3)
             ms = timeit(lambda: C.mult(x, y), steps, flush)
             fl, by = 2.0 * P * m, 16.0 * m
-            print(json.dumps({"op": "ChebMult", "P": P, "axis": tr, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6, "t_fp64_ms": fl / FP64_TFLOPS / 1e9,
-                              "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}), flush=True)
+            yield {"op": "ChebMult", "P": P, "axis": tr, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6, "t_fp64_ms": fl / FP64_TFLOPS / 1e9,
+                   "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}
             C.destroy()
         E = sp.Elliptic([P] * 3, gamma=4.0, exponent=2.0)
         us = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(E.g)).to(dev)
@@ -57,17 +58,62 @@ def main():
             E.mat_mult(U, V)
             nl = sp.launch_count() - l0
             ms = timeit(lambda: E.mat_mult(U, V), steps, flush)
-            print(json.dumps({"op": "MatMult_Elliptic", "P": P, "path": name, "launches": nl, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6,
-                              "t_fp64_ms": fl / FP64_TFLOPS / 1e9, "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}), flush=True)
+            yield {"op": "MatMult_Elliptic", "P": P, "path": name, "launches": nl, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6,
+                   "t_fp64_ms": fl / FP64_TFLOPS / 1e9, "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}
         E.set_path(0)
         csr = E.jacobian_csr()
         ms_full = timeit(lambda: E.jacobian_csr(), steps, flush)  # includes the torch.empty of the three output arrays
         ms_vals = timeit(lambda: E.jacobian_csr(pattern=csr[:2]), steps, flush)
         nnz = csr[2].numel()
         by_vals = 8.0 * 5 * m + 8.0 * nnz  # eta, deta, gradu[3] once; values written
-        print(json.dumps({"op": "FormJacobian (device CSR)", "P": P, "rows": E.g, "nnz": nnz, "ms_pattern_and_values": ms_full, "ms_values_only": ms_vals,
-                          "t_hbm_ms_values_only": by_vals / bw / 1e6, "frac_of_hbm_roofline": by_vals / bw / 1e6 / ms_vals}), flush=True)
+        yield {"op": "FormJacobian (device CSR)", "P": P, "rows": E.g, "nnz": nnz, "ms_pattern_and_values": ms_full, "ms_values_only": ms_vals,
+               "t_hbm_ms_values_only": by_vals / bw / 1e6, "frac_of_hbm_roofline": by_vals / bw / 1e6 / ms_vals}
         E.destroy()
+
+
+def stokes_rows(steps=10, P=128, dev=None, flush=None):
+    """The Stokes shells at P^3 (BASELINE config 5 state: -rheology 1 -exponent 3 -eps 1e-4) and the device assembly of MatVVPC."""
+    dev = dev or torch.device("cuda:0")
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    bw = hbm_gbs()
+    rng = np.random.default_rng(0)
+    S = sp.Stokes([P] * 3, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0)
+    xs = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(S.g)).to(dev)
+    S.set_dirichlet(torch.zeros(S.dv, dtype=torch.float64, device=dev))
+    S.set_force(torch.zeros(S.g, dtype=torch.float64, device=dev))
+    S.function(xs)
+    x = torch.from_numpy(rng.standard_normal(S.g)).to(dev)
+    xv = torch.from_numpy(rng.standard_normal(S.gv)).to(dev)
+    xp = torch.from_numpy(rng.standard_normal(S.gp)).to(dev)
+    y, yv, yp = torch.empty_like(x), torch.empty_like(xv), torch.empty_like(xp)
+    m = S.m
+    # scalar axis derivatives per application (SURVEY 8d): VV 18, VP 3, PV 3, MatMult / Function 24
+    ops = (("StokesMatMult", lambda: S.mat_mult(x, y), 4 * m, 24), ("StokesMatMultVV", lambda: S.mat_mult_vv(xv, yv), 3 * m, 18),
+           ("StokesMatMultVP", lambda: S.mat_mult_vp(xp, yv), m, 3), ("StokesMatMultPV", lambda: S.mat_mult_pv(xv, yp), 3 * m, 3),
+           ("StokesFunction", lambda: S.function(xs, y), 4 * m, 24))
+    for name, fn, ndof, nder in ops:
+        l0 = sp.launch_count()
+        fn()
+        nl = sp.launch_count() - l0
+        ms = timeit(fn, steps, flush)
+        t_fp64 = nder * 2.0 * P * m / FP64_TFLOPS / 1e9
+        yield {"op": name, "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64, "frac_of_fp64_roofline": t_fp64 / ms}
+    csr = S.pc_velocity_csr()
+    ms_vals = timeit(lambda: S.pc_velocity_csr(pattern=csr[:2]), steps, flush)
+    nnz = csr[2].numel()
+    by_vals = 8.0 * m + 8.0 * nnz  # eta once, values written
+    yield {"op": "StokesPCSetUp0 (device CSR)", "P": P, "rows": S.gv, "nnz": nnz, "ms_values_only": ms_vals, "t_hbm_ms_values_only": by_vals / bw / 1e6,
+           "frac_of_hbm_roofline": by_vals / bw / 1e6 / ms_vals}
+    S.destroy()
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    for row in rows(steps):
+        print(json.dumps(row), flush=True)
+    for row in stokes_rows(steps):
+        print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":
