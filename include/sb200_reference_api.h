@@ -67,6 +67,8 @@ typedef PetscErrorCode (*StokesVelocitySolve)(void* ksp, Vec rhs, Vec sol);
 PetscErrorCode StokesSetSchurVelocitySolve(StokesCtxB200* ctx, StokesVelocitySolve solve, void* ksp);
 PetscErrorCode StokesMatMultSchur(Mat S, Vec xG, Vec yG);
 PetscErrorCode StokesFunction(SNES snes, Vec xG, Vec yG, void* ctx);
+/* StokesJacobian (stokes.C:761-769): the Jacobian state was fixed up by StokesFunction; only reports DIFFERENT_NONZERO_PATTERN */
+PetscErrorCode StokesJacobian(SNES snes, Vec w, Mat* Ashell, Mat* Pshell, MatStructure* flag, void* ctx);
 PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2);
 /* the inner shells created by StokesCreate (stokes.C:308-325) and the SeqAIJ matrix MatVVPC (stokes.C:326) */
 PetscErrorCode StokesGetShells(StokesCtxB200* ctx, Mat* MatVV, Mat* MatPV, Mat* MatVP, Mat* MatSchur);

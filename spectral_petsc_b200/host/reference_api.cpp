@@ -278,6 +278,11 @@ PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y) {  // stokes.C:542-553
   return sb200_stokes_get_diagonal_schur(c->s, a, nullptr);
 }
 
+PetscErrorCode StokesJacobian(SNES, Vec, Mat*, Mat*, MatStructure* flag, void*) {  // stokes.C:761-769
+  *flag = DIFFERENT_NONZERO_PATTERN;  // "The nonlinear term has already been fixed up by StokesFunction() so we do nothing here."
+  return 0;
+}
+
 PetscErrorCode StokesSetSchurVelocitySolve(StokesCtxB200* c, StokesVelocitySolve solve, void* ksp) {
   c->svel = solve;
   c->svel_ksp = ksp;
