@@ -60,6 +60,15 @@ PetscErrorCode StokesMatMultVV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultPV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultVP(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y);
+/* StokesDivergence(ctx, withDirichlet, xG, yG) (stokes.C:570-595) */
+PetscErrorCode StokesDivergence(StokesCtxB200* ctx, PetscTruth withDirichlet, Vec xG, Vec yG);
+/* The rheologies as the host callbacks StokesOptions stores (stokes.C:1920-1944); ctx = the StokesOptionsB200 holding hardness,
+ * exponent, regularization, gamma0.  The kernels evaluate the same expressions per node on the device. */
+PetscErrorCode StokesRheologyLinear(PetscInt d, PetscReal gamma, PetscReal* eta, PetscReal* deta, void* ctx);
+PetscErrorCode StokesRheologyPower(PetscInt d, PetscReal gamma, PetscReal* eta, PetscReal* deta, void* ctx);
+/* polyInterp (util.C:129-144): Neville evaluation at x0 and x1 of the interpolant through (x[i], w[4*i]) / (x[i], w[4*i+1]),
+ * i < n; w is the reference's width-4 work array and is overwritten like there. */
+PetscErrorCode polyInterp(const PetscInt n, const PetscReal* x, PetscScalar* w, const PetscReal x0, const PetscReal x1, PetscScalar* f0, PetscScalar* f1);
 /* StokesMatMultSchur (stokes.C:523-535): y = -PV * KSPSolve(KSPSchurVelocity, VP * x).  The inner KSP is PETSc's; it is registered
  * here as a callback on device Vecs (with PETSc: `return KSPSolve((KSP)ksp, rhs, sol);`).  Without one the shell's MULT fails
  * with PETSC_ERR_ARG_*, like a KSPSolve on an unset KSP would. */

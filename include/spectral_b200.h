@@ -166,6 +166,9 @@ int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y);
 int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 /* StokesMatMultPV (stokes.C:557-566): divergence, gv -> gp. */
 int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
+/* StokesDivergence(ctx, withDirichlet, xG, yG) (stokes.C:570-595): the same with the Dirichlet velocities inserted on the boundary
+ * when with_dirichlet != 0 (what the residual uses, :746); with_dirichlet = 0 is StokesMatMultPV. */
+int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d_x, double* d_y, void* stream);
 /* StokesMatMultVP (stokes.C:599-619): pressure gradient with P_N - P_{N-2} extrapolation, gp -> gv. */
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 /* StokesMatGetDiagonalSchur (stokes.C:542-553): y = 1/eta at pressure nodes (gp doubles). */

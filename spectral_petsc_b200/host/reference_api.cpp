@@ -278,6 +278,43 @@ PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y) {  // stokes.C:542-553
   return sb200_stokes_get_diagonal_schur(c->s, a, nullptr);
 }
 
+PetscErrorCode StokesDivergence(StokesCtxB200* c, PetscTruth withDirichlet, Vec xG, Vec yG) {  // stokes.C:570-595
+  const PetscScalar* x;
+  PetscScalar* y;
+  if (xG->n != (PetscInt)c->gv || yG->n != (PetscInt)c->gp) return SB200_ERR_USER;
+  CHK(VecCUDAGetArrayRead(xG, &x));
+  CHK(VecCUDAGetArrayWrite(yG, &y));
+  return sb200_stokes_divergence(c->s, withDirichlet ? 1 : 0, x, y, nullptr);
+}
+
+PetscErrorCode StokesRheologyLinear(PetscInt, PetscReal, PetscReal* eta, PetscReal* deta, void*) {  // stokes.C:1920-1926
+  *eta = 1.0;
+  *deta = 0.0;
+  return 0;
+}
+
+PetscErrorCode StokesRheologyPower(PetscInt, PetscReal gamma, PetscReal* eta, PetscReal* deta, void* ctx) {  // stokes.C:1930-1944
+  const StokesOptionsB200* o = (const StokesOptionsB200*)ctx;
+  const double n = o->exponent, p = (1.0 - n) / (2.0 * n), base = o->regularization + gamma / o->gamma0;
+  *eta = o->hardness * pow(base, p);
+  *deta = fabs(n) > 1.0e-5 ? o->hardness * p / o->gamma0 * pow(base, p - 1.0) : 0.0;  // "Avoid a singularity for the special case"
+  return 0;
+}
+
+PetscErrorCode polyInterp(const PetscInt n, const PetscReal* x, PetscScalar* w, const PetscReal x0, const PetscReal x1, PetscScalar* f0, PetscScalar* f1) {
+  // util.C:129-144.  Columns 0 / 1 of the width-4 table hold the values; each level combines neighbours in place.
+  if (n < 1) return SB200_ERR_USER;
+  for (PetscInt lvl = 1; lvl < n; lvl++)
+    for (PetscInt i = 0; i < n - lvl; i++) {
+      const double den = x[i] - x[i + lvl];
+      w[4 * i] = ((x0 - x[i + lvl]) * w[4 * i] + (x[i] - x0) * w[4 * (i + 1)]) / den;
+      w[4 * i + 1] = ((x1 - x[i + lvl]) * w[4 * i + 1] + (x[i] - x1) * w[4 * (i + 1) + 1]) / den;
+    }
+  *f0 = w[0];
+  *f1 = w[1];
+  return 0;
+}
+
 PetscErrorCode StokesJacobian(SNES, Vec, Mat*, Mat*, MatStructure* flag, void*) {  // stokes.C:761-769
   *flag = DIFFERENT_NONZERO_PATTERN;  // "The nonlinear term has already been fixed up by StokesFunction() so we do nothing here."
   return 0;

@@ -585,6 +585,11 @@ int sb200_stokes_matmult_pv(sb200_stokes* s, const double* x, double* y, void*) 
   std::copy(p.begin(), p.end(), y);
   return 0;
 }
+int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* x, double* y, void*) {
+  std::vector<double> p = st_div(s, x, with_dirichlet != 0);
+  std::copy(p.begin(), p.end(), y);
+  return 0;
+}
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* x, double* y, void*) {
   std::vector<double> v = st_grad(s, x);
   std::copy(v.begin(), v.end(), y);

@@ -34,3 +34,7 @@ def check_driver2(txt):
     assert "Schur without an inner solve -> 62" in txt
     m = re.search(r"Schur identity-solve calls (\d+)  max \|S p \+ PV VP p\| / max \|PV VP p\| = (\S+)", txt)
     assert int(m.group(1)) == 1 and float(m.group(2)) < 1e-14
+    m = re.search(r"StokesDivergence: \|div\(no bc\) - PV\| = (\S+)  \|div\(exact, with bc\)\| = (\S+)  \|div\(exact, zero bc\)\| = (\S+)", txt)
+    assert float(m.group(1)) == 0.0         # withDirichlet = PETSC_FALSE is StokesMatMultPV (stokes.C:557-566)
+    assert float(m.group(2)) < 1e-5         # the manufactured velocity is divergence free once its boundary values are in
+    assert float(m.group(3)) > 1e-2         # ... and is not when the boundary is zeroed
