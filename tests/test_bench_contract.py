@@ -43,3 +43,15 @@ def test_ksp_and_slab_argument_validation_before_cuda():
     assert b"divisible" in L.sb200_last_error()
     assert L.sb200_slab_geometry(3, dims, 0, 4, None, None, None, None, None, None) == 0
     assert L.sb200_ipc_handle_bytes() == 64
+
+
+def test_secondary_measurements_are_isolated_in_child_processes():
+    """The per-P sweep and the KSP metric run as `bench.py --child NAME`; a child that fails (here: no CUDA device) or overruns its
+    limit yields an error record for the JSON line instead of an exception in the process that holds the headline numbers."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    r = bench.run_child("ksp", limit_s=300)
+    assert set(r) == {"error"} and "no CUDA device" in r["error"]
+    r = bench.run_child("p_sweep", limit_s=0.01)
+    assert set(r) == {"error"} and "exceeded" in r["error"]
