@@ -116,7 +116,8 @@ struct Krylov {
   }
   // x = solve(op, b) from a zero initial guess; op is a host-level callback, or the MatShell `native` applied on the device;
   // pc may be null (PCNONE)
-  int solve(PetscInt n, const HostOp* op, Mat native, const HostOp* pc, const Vecd& b, Vecd& x, double rtol, int maxits, int restart, int* its, int* reason) {
+  int solve(PetscInt n, const HostOp* op, Mat native, const HostOp* pc, const Vecd& b, Vecd& x, double rtol, int maxits, int restart, int* its, int* reason,
+            sb200_apply_fn native_pc = nullptr, void* native_pc_ctx = nullptr) {
     auto key = std::make_pair(n, restart);
     if (!cache.count(key)) {
       sb200_ksp* k = nullptr;
@@ -125,7 +126,10 @@ struct Krylov {
     }
     sb200_ksp* k = cache[key];
     Callback cop{op, n, {}, {}}, cpc{pc, n, {}, {}};
-    CHK(sb200_ksp_set_operators(k, native ? native_matmult : trampoline, native ? (void*)native : (void*)&cop, pc ? trampoline : nullptr, &cpc));
+    if (native_pc)  // the preconditioner works on the device vectors themselves (sb200_apply_saddle)
+      CHK(sb200_ksp_set_operators(k, native ? native_matmult : trampoline, native ? (void*)native : (void*)&cop, native_pc, native_pc_ctx));
+    else
+      CHK(sb200_ksp_set_operators(k, native ? native_matmult : trampoline, native ? (void*)native : (void*)&cop, pc ? trampoline : nullptr, &cpc));
     CHK(sb200_ksp_set_tolerances(k, rtol, 1e-50, 1e5, maxits));
     Tmp db(n), dx(n);
     if (!db.v || !dx.v) return SB200_ERR_CUDA;
@@ -149,6 +153,23 @@ struct Flow {
   int saddle = 0, vel_max_it = 10000, schur_max_it = 10000;
   double vel_rtol = 1e-5, schur_rtol = 1e-5;
   Vecd diag;  // StokesMatGetDiagonalSchur: 1/eta at the pressure nodes
+  // StokesPCApply{saddle} on the device (sb200_saddle_*, host/saddle.cpp): the default; -saddle_on_host 1 runs the same
+  // composition in this file on host copies instead (kept as the cross-check of the device-resident one)
+  sb200_saddle* dev_saddle = nullptr;
+  bool saddle_on_host = false;
+  ~Flow() {
+    if (dev_saddle) sb200_saddle_destroy(dev_saddle);
+  }
+  static int pc_device(void* ctx, const double* d_x, double* d_y, void* stream) { return ((HostPc*)ctx)->apply_device(d_x, d_y, stream); }
+  int setup_device_saddle() {
+    if (saddle_on_host) return 0;
+    if (!dev_saddle) CHK(sb200_saddle_create(StokesGetHandle(ctx), saddle, &dev_saddle));
+    CHK(sb200_saddle_set_inner(dev_saddle, vel_rtol, vel_max_it, schur_rtol, schur_max_it, svel_preonly ? 1 : 0));
+    sb200_apply_fn fv = vel.type == "none" ? nullptr : pc_device;
+    HostPc& sp = svel_is_vel ? vel : svel;
+    sb200_apply_fn fs = sp.type == "none" ? nullptr : pc_device;
+    return sb200_saddle_set_velocity_pc(dev_saddle, fv, &vel, fs, &sp, 0);
+  }
 
   // scatterGV / scatterGP and back (stokes.C:867-877): global AoS [v_0..v_{d-1}, p] per interior node
   void split(const Vecd& x, Vecd& v, Vecd& p) const {
@@ -346,6 +367,7 @@ int main(int argc, char** argv) {
   F.schur_max_it = o.integer("schur_ksp_max_it", 10000);
   F.schur_rtol = o.real("schur_ksp_rtol", 1e-5);
   F.svel_preonly = o.str("svel_ksp_type", "gmres") == "preonly";
+  F.saddle_on_host = o.integer("saddle_on_host", 0) != 0;
   F.vel.type = o.str("vel_pc_type", "ilu");  // PETSc's default PC for the SeqAIJ matrix MatVVPC is ILU(0); README:44 overrides it with hypre
   F.svel.type = o.str("svel_pc_type", "ilu");
   F.vel.levels = o.integer("vel_pc_factor_levels", 0);
@@ -446,7 +468,11 @@ int main(int argc, char** argv) {
         return rc;
       };
       int k = 0, kreason = 0;
-      CHK(F.krylov.solve(F.g, nullptr, F.A, &pc_outer, rhs, dx, ksp_rtol, ksp_max_it, 30, &k, &kreason));
+      CHK(F.setup_device_saddle());
+      if (F.saddle_on_host)
+        CHK(F.krylov.solve(F.g, nullptr, F.A, &pc_outer, rhs, dx, ksp_rtol, ksp_max_it, 30, &k, &kreason));
+      else
+        CHK(F.krylov.solve(F.g, nullptr, F.A, nullptr, rhs, dx, ksp_rtol, ksp_max_it, 30, &k, &kreason, sb200_apply_saddle, F.dev_saddle));
       kits.push_back(k);
       if (ksp_monitor) printf("    KSP iterations %d reason %d\n", k, kreason);
       double lam = 1.0, fnn = 0;

@@ -85,6 +85,23 @@ PetscErrorCode StokesGetPCMatrix(StokesCtxB200* ctx, Mat* MatVVPC);
 /* StokesPCSetUp0 (stokes.C:1160-1240), the PCShell set-up routine of -pcvel 0 (stokes.C:166): assembles MatVVPC on the device
  * from the eta the last StokesFunction cached.  The PC shell's context is the Stokes context (stokes.C:163). */
 PetscErrorCode StokesPCSetUp0(PC pc);
+/* StokesPCApply0..3 (stokes.C:1714-1817), the PCShell apply routines -pc_saddle_type selects (stokes.C:171-185); the PC shell's
+ * context is the Stokes context (stokes.C:163).  x, y: device Vecs of g doubles.  The three inner KSPs of stokes.C:328-341 run on
+ * the device (sb200_saddle_*); what stays with the caller is the preconditioner PETSc builds on MatVVPC for KSPVelocity /
+ * KSPSchurVelocity, registered here as callbacks on device Vecs (with PETSc: `return PCApply((PC)pc, r, z);`; NULL = PCNONE),
+ * and the inner tolerances the options database would supply (-vel_ksp_rtol, -vel_ksp_max_it, -schur_ksp_rtol,
+ * -schur_ksp_max_it, -svel_ksp_type preonly). */
+PetscErrorCode StokesSetVelocityPC(StokesCtxB200* ctx, StokesVelocitySolve vel_pc, void* vel_pc_ctx, StokesVelocitySolve svel_pc, void* svel_pc_ctx);
+PetscErrorCode StokesSetInnerSolves(StokesCtxB200* ctx, PetscReal vel_rtol, PetscInt vel_max_it, PetscReal schur_rtol, PetscInt schur_max_it, PetscTruth svel_preonly);
+PetscErrorCode StokesPCApply0(PC pc, Vec x, Vec y);
+PetscErrorCode StokesPCApply1(PC pc, Vec x, Vec y);
+PetscErrorCode StokesPCApply2(PC pc, Vec x, Vec y);
+PetscErrorCode StokesPCApply3(PC pc, Vec x, Vec y);
+/* the null space StokesRemoveConstantPressure attaches to the outer KSP (stokes.C:1006-1025), applied to a global Vec in place */
+PetscErrorCode StokesNullSpaceRemove(StokesCtxB200* ctx, Vec x);
+PetscErrorCode StokesGetInnerIterations(StokesCtxB200* ctx, PetscInt* velocity, PetscInt* schur);
+/* the C-ABI handle behind the context (for sb200_saddle_create / sb200_ksp_set_operators without going through Vecs) */
+struct sb200_stokes* StokesGetHandle(StokesCtxB200* ctx);
 PetscErrorCode StokesSetContinuation(StokesCtxB200* ctx, PetscReal exponent, PetscReal regularization); /* stokes.C:218-219 */
 /* StokesPressureReduceOrder(pL, ctx) (stokes.C:1029-1080) on a local pressure Vec of m doubles, in place */
 PetscErrorCode StokesPressureReduceOrder(Vec pL, StokesCtxB200* ctx);

@@ -232,6 +232,42 @@ int sb200_apply_elliptic_matmult(void* ctx, const double* d_x, double* d_y, void
 int sb200_apply_stokes_matmult(void* ctx, const double* d_x, double* d_y, void* stream);
 int sb200_apply_stokes_matmult_vv(void* ctx, const double* d_x, double* d_y, void* stream);
 
+/* ---- vector helpers: what the saddle-point preconditioners are composed from besides shells and inner solves -------------
+ * scatterGV / scatterGP and scatterVG / scatterPG (stokes.C:867-877): the global Stokes vector holds [v_0..v_{d-1}, p] per
+ * interior node; split / merge move the velocity (nodes*d) and pressure (nodes) parts out and back.  A NULL part is skipped
+ * (merge then leaves those entries of d_x untouched). */
+int sb200_vec_split(long long nodes, int d, const double* d_x, double* d_v, double* d_p, void* stream);
+int sb200_vec_merge(long long nodes, int d, const double* d_v, const double* d_p, double* d_x, void* stream);
+/* VecAXPBY: y = a x + b y (b == 0 does not read y; a == 0 is VecScale and does not read x) */
+int sb200_vec_axpby(long long n, double a, const double* d_x, double b, double* d_y, void* stream);
+/* VecPointwiseDivide: y = x / diag (PCJacobi on the "diagonal" of StokesMatGetDiagonalSchur, stokes.C:328-333) */
+int sb200_vec_pointwise_divide(long long n, const double* d_x, const double* d_diag, double* d_y, void* stream);
+/* MatNullSpaceRemove with the constant vector on the n entries x[offset + i*stride] (stokes.C:1013-1023: the pressure slots of
+ * the global vector are stride d+1, offset d).  d_scratch: SB200_REDUCE_SCRATCH_DOUBLES doubles of device memory. */
+#define SB200_REDUCE_SCRATCH_DOUBLES 1024
+int sb200_vec_remove_mean(long long n, int stride, int offset, double* d_x, double* d_scratch, void* stream);
+
+/* ---- StokesPCApply0..3 (stokes.C:1714-1817): the saddle-point preconditioners, device resident -----------------------------
+ * Composition of the PV / VP / VV shells with the three inner Krylov solves of stokes.C:328-341 - KSPVelocity, KSPSchur (on the
+ * Schur shell, Jacobi from StokesMatGetDiagonalSchur, constant null space) and KSPSchurVelocity - each PETSc's default GMRES(30)
+ * with LEFT preconditioning, run as sb200_ksp on M^-1 A.  Every vector stays on the device; only the preconditioner of the
+ * velocity block (PETSc's PC on MatVVPC, out of scope) is a callback.  type = -pc_saddle_type (stokes.C:171-185): 0 block LU,
+ * 1 upper triangular, 2 diagonal, 3 lower triangular. */
+typedef struct sb200_saddle sb200_saddle;
+int sb200_saddle_create(sb200_stokes* s, int type, sb200_saddle** out);
+/* -vel_pc_* / -svel_pc_*: z = M^-1 r on device vectors of gv doubles; NULL = PCNONE.  svel_pc NULL with svel_same != 0 reuses vel_pc. */
+int sb200_saddle_set_velocity_pc(sb200_saddle* p, sb200_apply_fn vel_pc, void* vel_ctx, sb200_apply_fn svel_pc, void* svel_ctx, int svel_same);
+/* -vel_ksp_rtol / -vel_ksp_max_it, -schur_ksp_rtol / -schur_ksp_max_it, -svel_ksp_type preonly (PETSc defaults: 1e-5, 10000, gmres) */
+int sb200_saddle_set_inner(sb200_saddle* p, double vel_rtol, int vel_maxits, double schur_rtol, int schur_maxits, int svel_preonly);
+int sb200_saddle_apply(sb200_saddle* p, const double* d_x, double* d_y, void* stream); /* y = StokesPCApply{type}(x), g doubles */
+/* StokesRemoveConstantPressure's null space (stokes.C:1006-1025) applied to a global vector in place */
+int sb200_saddle_remove_constant_pressure(sb200_saddle* p, double* d_x, void* stream);
+/* sb200_apply_fn form for the pc slot of the outer KSP: PCApply followed by the null-space removal KSPSetNullSpace adds */
+int sb200_apply_saddle(void* ctx, const double* d_x, double* d_y, void* stream);
+/* inner iterations accumulated since creation (KSPVelocity, KSPSchur) */
+int sb200_saddle_get_inner_its(const sb200_saddle* p, long long* velocity, long long* schur);
+int sb200_saddle_destroy(sb200_saddle* p);
+
 /* ---- host stand-in for PETSc's PCILU (NOT part of the B200 path; the PC stays PETSc's own) --------------------------------
  * The reference sets PCILU with 2 levels of fill on the finite-difference matrix in code (elliptic.C:183-184); PETSc's default
  * PC for the Stokes matrix MatVVPC is ILU(0).  So that the command-line drivers and the solver-level parity tests can run those

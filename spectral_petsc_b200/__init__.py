@@ -19,6 +19,12 @@ from .capi import (  # noqa: F401
     elliptic_exact_solution,
     stokes_exact_solution,
     HostILU,
+    StokesSaddle,
+    vec_split,
+    vec_merge,
+    vec_axpby,
+    vec_pointwise_divide,
+    vec_remove_mean,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution", "HostILU"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution", "HostILU", "StokesSaddle", "vec_split", "vec_merge", "vec_axpby", "vec_pointwise_divide", "vec_remove_mean"]

@@ -541,7 +541,11 @@ class KSP:
         else:
             fn, ctx = self._as_fn(op)
         self._keep.append(op)
-        pfn, pctx = (None, None) if pc is None else self._as_fn(pc)
+        if isinstance(pc, StokesSaddle):  # StokesPCApply + null-space removal natively on the device vectors
+            pfn, pctx = pc.as_ksp_pc()
+            self._keep.append(pc)
+        else:
+            pfn, pctx = (None, None) if pc is None else self._as_fn(pc)
         _ck(L.sb200_ksp_set_operators(self._h, fn, ctx, pfn, pctx))
 
     def set_tolerances(self, rtol=1e-5, atol=1e-50, dtol=1e5, maxits=10000):
@@ -598,6 +602,119 @@ class KSP:
             self.destroy()
         except Exception:
             pass
+
+
+class StokesSaddle:
+    """StokesPCApply0..3 (stokes.C:1714-1817) composed on the device (sb200_saddle_*, host/saddle.cpp): the PV / VP / VV shells,
+    KSPVelocity / KSPSchur / KSPSchurVelocity as device GMRES, the index scatters and the null-space projection.
+    velocity_pc / svel_pc: callables z = M^-1 r on torch tensors of gv doubles (None = PCNONE); svel_pc defaults to velocity_pc."""
+
+    def __init__(self, stokes, saddle_type=0, velocity_pc=None, svel_pc="same", vel_rtol=1e-5, vel_max_it=10000, schur_rtol=1e-5, schur_max_it=10000,
+                 svel_preonly=False):
+        self._h = ctypes.c_void_p()
+        self.stokes = stokes
+        _ck(lib().sb200_saddle_create(stokes._h, ctypes.c_int(saddle_type), ctypes.byref(self._h)))
+        _ck(lib().sb200_saddle_set_inner(self._h, ctypes.c_double(vel_rtol), ctypes.c_int(vel_max_it), ctypes.c_double(schur_rtol), ctypes.c_int(schur_max_it),
+                                         ctypes.c_int(int(svel_preonly))))
+        self._keep = []
+        fv = self._as_fn(velocity_pc)
+        fs = fv if svel_pc == "same" else self._as_fn(svel_pc)
+        _ck(lib().sb200_saddle_set_velocity_pc(self._h, fv, None, fs, None, ctypes.c_int(0)))
+
+    def _as_fn(self, f):
+        if f is None:
+            return None
+        n = self.stokes.gv
+
+        def cb(_ctx, d_x, d_y, _stream):
+            try:
+                _wrap(d_y, n).copy_(f(_wrap(d_x, n)))
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        c = _APPLY(cb)
+        self._keep.append(c)
+        return c
+
+    def apply(self, x, y=None, remove_constant_pressure=False):
+        """y = StokesPCApply{type}(x); remove_constant_pressure adds the projection KSPSetNullSpace applies on the outer KSP."""
+        import torch
+
+        if y is None:
+            y = torch.empty_like(x)
+        assert x.numel() == self.stokes.g and y.numel() == self.stokes.g
+        fn = lib().sb200_apply_saddle if remove_constant_pressure else lib().sb200_saddle_apply
+        _ck(fn(self._h, _ptr(x), _ptr(y), _stream()))
+        return y
+
+    def as_ksp_pc(self):
+        """(function pointer, context) of sb200_apply_saddle for sb200_ksp_set_operators: no Python in the outer iteration."""
+        return ctypes.cast(lib().sb200_apply_saddle, ctypes.c_void_p), self._h
+
+    @property
+    def inner_its(self):
+        a, b = ctypes.c_longlong(), ctypes.c_longlong()
+        _ck(lib().sb200_saddle_get_inner_its(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return {"velocity": a.value, "schur": b.value}
+
+    def destroy(self):
+        if self._h:
+            _ck(lib().sb200_saddle_destroy(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def vec_split(x, d):
+    """scatterGV / scatterGP (stokes.C:867-877) on device tensors."""
+    import torch
+
+    nodes = x.numel() // (d + 1)
+    v = torch.empty(nodes * d, dtype=torch.float64, device=x.device)
+    p = torch.empty(nodes, dtype=torch.float64, device=x.device)
+    _ck(lib().sb200_vec_split(ctypes.c_longlong(nodes), ctypes.c_int(d), _ptr(x), _ptr(v), _ptr(p), _stream()))
+    return v, p
+
+
+def vec_merge(v, p, d):
+    import torch
+
+    nodes = p.numel()
+    x = torch.empty(nodes * (d + 1), dtype=torch.float64, device=p.device)
+    _ck(lib().sb200_vec_merge(ctypes.c_longlong(nodes), ctypes.c_int(d), _ptr(v), _ptr(p), _ptr(x), _stream()))
+    return x
+
+
+def vec_axpby(a, x, b, y):
+    """y <- a x + b y in place (VecAXPBY)."""
+    _ck(lib().sb200_vec_axpby(ctypes.c_longlong(y.numel()), ctypes.c_double(a), None if x is None else _ptr(x), ctypes.c_double(b), _ptr(y), _stream()))
+    return y
+
+
+def vec_pointwise_divide(x, diag):
+    import torch
+
+    y = torch.empty_like(x)
+    _ck(lib().sb200_vec_pointwise_divide(ctypes.c_longlong(x.numel()), _ptr(x), _ptr(diag), _ptr(y), _stream()))
+    return y
+
+
+def vec_remove_mean(x, stride=1, offset=0):
+    """MatNullSpaceRemove with the constant vector on x[offset::stride], in place."""
+    import torch
+
+    scratch = torch.empty(1024, dtype=torch.float64, device=x.device)  # SB200_REDUCE_SCRATCH_DOUBLES
+    n = (x.numel() - offset + stride - 1) // stride
+    _ck(lib().sb200_vec_remove_mean(ctypes.c_longlong(n), ctypes.c_int(stride), ctypes.c_int(offset), _ptr(x), _ptr(scratch), _stream()))
+    return x
 
 
 def _wrap(ptr, n):

@@ -195,6 +195,13 @@ struct StokesCtxB200 {
   Mat MatVV, MatPV, MatVP, MatSchur, MatVVPC;
   StokesVelocitySolve svel = nullptr;  // KSPSolve(KSPSchurVelocity, ., .) (stokes.C:531)
   void* svel_ksp = nullptr;
+  // StokesPCApply0..3: one device-resident composition per saddle type, created at its first application
+  sb200_saddle* saddle[4] = {nullptr, nullptr, nullptr, nullptr};
+  StokesVelocitySolve vel_pc = nullptr, svel_pc = nullptr;  // PCApply on MatVVPC for KSPVelocity / KSPSchurVelocity
+  void* vel_pc_ctx = nullptr;
+  void* svel_pc_ctx = nullptr;
+  double vel_rtol = 1e-5, schur_rtol = 1e-5;  // KSP defaults
+  int vel_max_it = 10000, schur_max_it = 10000, svel_preonly = 0;
 };
 
 static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std::vector<double>* U2, std::vector<double>* D) {
@@ -250,6 +257,7 @@ PetscErrorCode StokesDestroy(StokesCtxB200* c) {  // stokes.C:348-388
   MatDestroy(c->MatPV);
   MatDestroy(c->MatVP);
   MatDestroy(c->MatVV);
+  for (sb200_saddle* p : c->saddle) sb200_saddle_destroy(p);
   PetscErrorCode rc = sb200_stokes_destroy(c->s);
   delete c;
   return rc;
@@ -422,5 +430,94 @@ PetscErrorCode StokesSetContinuation(StokesCtxB200* c, PetscReal exponent, Petsc
   c->opt.regularization = regularization;
   return sb200_stokes_set_rheology(c->s, c->opt.rheology, c->opt.hardness, exponent, regularization, c->opt.gamma0);
 }
+
+// ---- the saddle-point PCShells (stokes.C:171-185 selects one by -pc_saddle_type) -----------------------------------------------
+PetscErrorCode StokesSetVelocityPC(StokesCtxB200* c, StokesVelocitySolve vel_pc, void* vel_ctx, StokesVelocitySolve svel_pc, void* svel_ctx) {
+  c->vel_pc = vel_pc;
+  c->vel_pc_ctx = vel_ctx;
+  c->svel_pc = svel_pc;
+  c->svel_pc_ctx = svel_ctx;
+  return 0;
+}
+
+PetscErrorCode StokesSetInnerSolves(StokesCtxB200* c, PetscReal vel_rtol, PetscInt vel_max_it, PetscReal schur_rtol, PetscInt schur_max_it, PetscTruth svel_preonly) {
+  if (vel_rtol < 0 || schur_rtol < 0 || vel_max_it < 0 || schur_max_it < 0) return SB200_ERR_USER;
+  c->vel_rtol = vel_rtol;
+  c->vel_max_it = vel_max_it;
+  c->schur_rtol = schur_rtol;
+  c->schur_max_it = schur_max_it;
+  c->svel_preonly = svel_preonly ? 1 : 0;
+  return 0;
+}
+
+// the C ABI hands a preconditioner raw device pointers; wrap them as Vecs for the PETSc-side PCApply
+static int vec_trampoline(StokesCtxB200* c, StokesVelocitySolve f, void* fctx, const double* d_r, double* d_z) {
+  Vec r = nullptr, z = nullptr;
+  PetscErrorCode rc = VecCreateSeqCUDAWithArray(PETSC_COMM_SELF, (PetscInt)c->gv, (double*)d_r, &r);
+  if (!rc) rc = VecCreateSeqCUDAWithArray(PETSC_COMM_SELF, (PetscInt)c->gv, d_z, &z);
+  if (!rc) rc = f(fctx, r, z);
+  if (r) VecDestroy(r);
+  if (z) VecDestroy(z);
+  return rc;
+}
+static int vel_pc_trampoline(void* vctx, const double* d_r, double* d_z, void*) {
+  StokesCtxB200* c = (StokesCtxB200*)vctx;
+  return vec_trampoline(c, c->vel_pc, c->vel_pc_ctx, d_r, d_z);
+}
+static int svel_pc_trampoline(void* vctx, const double* d_r, double* d_z, void*) {
+  StokesCtxB200* c = (StokesCtxB200*)vctx;
+  return vec_trampoline(c, c->svel_pc, c->svel_pc_ctx, d_r, d_z);
+}
+
+static PetscErrorCode stokes_saddle(StokesCtxB200* c, int type, sb200_saddle** out) {
+  if (!c->saddle[type]) CHK(sb200_saddle_create(c->s, type, &c->saddle[type]));
+  sb200_saddle* p = c->saddle[type];
+  CHK(sb200_saddle_set_velocity_pc(p, c->vel_pc ? vel_pc_trampoline : nullptr, c, c->svel_pc ? svel_pc_trampoline : nullptr, c, 0));
+  CHK(sb200_saddle_set_inner(p, c->vel_rtol, c->vel_max_it, c->schur_rtol, c->schur_max_it, c->svel_preonly));
+  *out = p;
+  return 0;
+}
+
+static PetscErrorCode stokes_pc_apply(PC pc, int type, Vec x, Vec y) {
+  StokesCtxB200* c = nullptr;
+  CHK(PCShellGetContext(pc, (void**)&c));
+  if (!c || x->n != (PetscInt)c->g || y->n != (PetscInt)c->g) return SB200_ERR_USER;
+  sb200_saddle* p = nullptr;
+  CHK(stokes_saddle(c, type, &p));
+  const PetscScalar* a;
+  PetscScalar* b;
+  CHK(VecCUDAGetArrayRead(x, &a));
+  CHK(VecCUDAGetArrayWrite(y, &b));
+  return sb200_saddle_apply(p, a, b, nullptr);
+}
+PetscErrorCode StokesPCApply0(PC pc, Vec x, Vec y) { return stokes_pc_apply(pc, 0, x, y); }  // stokes.C:1714-1742  block LU
+PetscErrorCode StokesPCApply1(PC pc, Vec x, Vec y) { return stokes_pc_apply(pc, 1, x, y); }  // stokes.C:1747-1768  upper triangular
+PetscErrorCode StokesPCApply2(PC pc, Vec x, Vec y) { return stokes_pc_apply(pc, 2, x, y); }  // stokes.C:1773-1792  diagonal
+PetscErrorCode StokesPCApply3(PC pc, Vec x, Vec y) { return stokes_pc_apply(pc, 3, x, y); }  // stokes.C:1797-1817  lower triangular
+
+PetscErrorCode StokesNullSpaceRemove(StokesCtxB200* c, Vec x) {  // MatNullSpaceRemove with the vector of stokes.C:1013-1020
+  if (x->n != (PetscInt)c->g) return SB200_ERR_USER;
+  sb200_saddle* p = nullptr;
+  CHK(stokes_saddle(c, 0, &p));
+  PetscScalar* a;
+  CHK(VecCUDAGetArrayWrite(x, &a));
+  return sb200_saddle_remove_constant_pressure(p, a, nullptr);
+}
+
+PetscErrorCode StokesGetInnerIterations(StokesCtxB200* c, PetscInt* velocity, PetscInt* schur) {
+  long long v = 0, s = 0;
+  for (sb200_saddle* p : c->saddle)
+    if (p) {
+      long long a = 0, b = 0;
+      CHK(sb200_saddle_get_inner_its(p, &a, &b));
+      v += a;
+      s += b;
+    }
+  if (velocity) *velocity = (PetscInt)v;
+  if (schur) *schur = (PetscInt)s;
+  return 0;
+}
+
+sb200_stokes* StokesGetHandle(StokesCtxB200* c) { return c ? c->s : nullptr; }
 
 }  // extern "C"

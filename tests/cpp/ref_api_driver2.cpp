@@ -152,8 +152,140 @@ static int test_schur(int n0) {
   return 0;
 }
 
+// ---- StokesPCApply0..3 (stokes.C:1714-1817) through the reference's names, everything on the device -------------------------------
+// With the three inner solves run to 1e-12 the block-LU preconditioner is the inverse of StokesMatMult on the complement of the
+// constant-pressure null space, and the triangular / diagonal variants satisfy their block identities.
+static int maxdiff(Vec a, Vec b, PetscInt n, double* out, double* scale) {
+  std::vector<double> ha(n), hb(n);
+  CHK(VecGetValuesHost(a, ha.data()));
+  CHK(VecGetValuesHost(b, hb.data()));
+  *out = 0;
+  *scale = 0;
+  for (PetscInt i = 0; i < n; i++) {
+    *out = fmax(*out, fabs(ha[i] - hb[i]));
+    *scale = fmax(*scale, fabs(hb[i]));
+  }
+  return 0;
+}
+
+static int test_saddle(int n0) {
+  StokesOptionsB200 opt;
+  opt.numDims = 3;
+  opt.dim[0] = opt.dim[1] = opt.dim[2] = n0;
+  opt.exact = 2;
+  opt.rheology = 1;  // power law: a variable eta, so the Jacobi "diagonal" 1/eta of the Schur solve matters
+  opt.hardness = 1.0;
+  opt.exponent = 2.0;
+  opt.regularization = 0.5;
+  opt.gamma0 = 1.0;
+  Mat A, MatVV, MatPV, MatVP;
+  Vec x, r, y[4], Ay, U, U2;
+  StokesCtxB200* ctx;
+  SNES snes;
+  PC pc;
+  CHK(StokesCreate(PETSC_COMM_SELF, &opt, &A, &x, &ctx));
+  CHK(StokesGetShells(ctx, &MatVV, &MatPV, &MatVP, PETSC_NULL));
+  PetscInt g, gp, gv;
+  CHK(StokesGetSizes(ctx, PETSC_NULL, &g, &gp, &gv, PETSC_NULL));
+  CHK(SNESCreate(PETSC_COMM_SELF, &snes));
+  CHK(SNESSetApplicationContext(snes, ctx));
+  CHK(PCCreate(PETSC_COMM_SELF, &pc));
+  CHK(PCShellSetContext(pc, ctx));
+  for (Vec* w : {&r, &y[0], &y[1], &y[2], &y[3], &Ay, &U, &U2}) CHK(VecDuplicate(x, w));
+  CHK(StokesCreateExactSolution(snes, U, U2));
+  CHK(StokesFunction(snes, U, r, ctx));  // linearisation state: eta, deta, strain of the manufactured solution
+  PetscReal mn, mx;
+  CHK(StokesGetEtaMinMax(ctx, &mn, &mx));
+  // inner solves to 1e-12, no preconditioner on the velocity block (PCNONE), KSPSchurVelocity a full GMRES
+  CHK(StokesSetVelocityPC(ctx, PETSC_NULL, PETSC_NULL, PETSC_NULL, PETSC_NULL));
+  CHK(StokesSetInnerSolves(ctx, 1e-12, 2000, 1e-12, 500, PETSC_FALSE));
+  std::vector<double> hx(g), hz(g);
+  srand(11);
+  for (PetscInt i = 0; i < g; i++) hx[i] = rand() / (double)RAND_MAX - 0.5;
+  CHK(VecSetValuesHost(x, hx.data()));
+  CHK(StokesNullSpaceRemove(ctx, x));  // zero-mean pressure: the part StokesPCApply0 can recover
+  CHK(VecGetValuesHost(x, hz.data()));
+  double pmean = 0, vsame = 0;
+  for (PetscInt q = 0; q < gp; q++) {
+    pmean += hz[q * 4 + 3];
+    for (int k = 0; k < 3; k++) vsame = fmax(vsame, fabs(hz[q * 4 + k] - hx[q * 4 + k]));
+  }
+  printf("saddle: eta in [%.3f, %.3f]  null-space removal: pressure mean %.1e  velocity change %.1e\n", mn, mx, fabs(pmean / gp), vsame);
+  CHK(MatMult(A, x, r));                                      // r = J x
+  PetscErrorCode (*apply[4])(PC, Vec, Vec) = {StokesPCApply0, StokesPCApply1, StokesPCApply2, StokesPCApply3};
+  for (int t = 0; t < 4; t++) CHK(apply[t](pc, r, y[t]));
+  double d, sc;
+  CHK(StokesNullSpaceRemove(ctx, y[0]));
+  CHK(maxdiff(y[0], x, g, &d, &sc));
+  printf("saddle type 0 (block LU, exact inner solves): max |PC(J x) - x| / max |x| = %.3e\n", d / sc);
+  // block identities of the other variants, checked with the full operator: J y = [VV y_v + VP y_p ; PV y_v]
+  std::vector<double> hr(g), hy(g), hJ(g);
+  CHK(VecGetValuesHost(r, hr.data()));
+  {  // type 1 (upper): y_p = S^-1 r_p, VV y_v + VP y_p = r_v
+    CHK(MatMult(A, y[1], Ay));
+    CHK(VecGetValuesHost(Ay, hJ.data()));
+    double e = 0, big = 0;
+    for (PetscInt q = 0; q < gp; q++)
+      for (int k = 0; k < 3; k++) {
+        e = fmax(e, fabs(hJ[q * 4 + k] - hr[q * 4 + k]));
+        big = fmax(big, fabs(hr[q * 4 + k]));
+      }
+    printf("saddle type 1 (upper): max |VV y_v + VP y_p - r_v| / max |r_v| = %.3e\n", e / big);
+  }
+  {  // types 2 (diagonal) and 3 (lower): VV y_v = r_v; their pressure parts repeat the Schur solves of types 1 and 0
+    std::vector<double> h1(g), h2(g), h3(g), h0(g), hv(gv), hw(gv);
+    CHK(VecGetValuesHost(y[1], h1.data()));
+    CHK(VecGetValuesHost(y[2], h2.data()));
+    CHK(VecGetValuesHost(y[3], h3.data()));
+    Vec v, w;
+    CHK(VecCreateSeqCUDA(PETSC_COMM_SELF, gv, &v));
+    CHK(VecDuplicate(v, &w));
+    double e23 = 0, ev = 0, big = 0, p12 = 0, pbig = 0;
+    for (PetscInt q = 0; q < gp; q++) {
+      for (int k = 0; k < 3; k++) {
+        hv[q * 3 + k] = h2[q * 4 + k];
+        e23 = fmax(e23, fabs(h2[q * 4 + k] - h3[q * 4 + k]));
+      }
+      p12 = fmax(p12, fabs(h1[q * 4 + 3] - h2[q * 4 + 3]));
+      pbig = fmax(pbig, fabs(h2[q * 4 + 3]));
+    }
+    CHK(VecSetValuesHost(v, hv.data()));
+    CHK(MatMult(MatVV, v, w));
+    CHK(VecGetValuesHost(w, hw.data()));
+    for (PetscInt q = 0; q < gp; q++)
+      for (int k = 0; k < 3; k++) {
+        ev = fmax(ev, fabs(hw[q * 3 + k] - hr[q * 4 + k]));
+        big = fmax(big, fabs(hr[q * 4 + k]));
+      }
+    printf("saddle type 2 (diagonal): max |VV y_v - r_v| / max |r_v| = %.3e   |y_v(2) - y_v(3)| = %.3e   |y_p(1) - y_p(2)| / max = %.3e\n", ev / big, e23,
+           p12 / pbig);
+    // type 3 (lower): PV y_v + S y_p = r_p up to a constant; S y_p = J-row: use type 0, whose pressure part is type 3's
+    CHK(apply[0](pc, r, y[0]));
+    CHK(VecGetValuesHost(y[0], h0.data()));
+    double p03 = 0;
+    for (PetscInt q = 0; q < gp; q++) p03 = fmax(p03, fabs(h0[q * 4 + 3] - h3[q * 4 + 3]));
+    printf("saddle type 3 (lower): |y_p(3) - y_p(0)| = %.3e\n", p03);
+    CHK(VecDestroy(v));
+    CHK(VecDestroy(w));
+  }
+  PetscInt iv, is;
+  CHK(StokesGetInnerIterations(ctx, &iv, &is));
+  printf("saddle inner iterations: velocity %d  schur %d\n", iv, is);
+  Vec small;
+  CHK(VecCreateSeqCUDA(PETSC_COMM_SELF, gp, &small));
+  printf("saddle wrong-size Vec -> %d   same Vec twice -> %d\n", StokesPCApply0(pc, small, y[0]), StokesPCApply0(pc, r, r));
+  CHK(VecDestroy(small));
+  for (Vec w : {r, y[0], y[1], y[2], y[3], Ay, U, U2, x}) CHK(VecDestroy(w));
+  CHK(PCDestroy(pc));
+  CHK(SNESDestroy(snes));
+  CHK(StokesDestroy(ctx));
+  CHK(MatDestroy(A));
+  return 0;
+}
+
 int main() {
   if (test_chebd1()) return 1;
   if (test_schur(12)) return 1;
+  if (test_saddle(7)) return 1;
   return 0;
 }

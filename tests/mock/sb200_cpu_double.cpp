@@ -230,6 +230,44 @@ int sb200_memcpy_h2d(void* d, const void* s, size_t n, void*) { std::memcpy(d, s
 int sb200_memcpy_d2h(void* d, const void* s, size_t n, void*) { std::memcpy(d, s, n); return 0; }
 int sb200_memcpy_d2d(void* d, const void* s, size_t n, void*) { std::memcpy(d, s, n); return 0; }
 int sb200_memset0(void* d, size_t n, void*) { std::memset(d, 0, n); return 0; }
+
+// ---- vector helpers (csrc/vecops.cu) ------------------------------------------------------------------------------------------
+int sb200_vec_split(long long nodes, int d, const double* x, double* v, double* p, void*) {
+  if (nodes < 0 || d < 1 || !x || (!v && !p)) FAIL(SB200_ERR_ARG, "sb200_vec_split: bad arguments");
+  for (long long q = 0; q < nodes; q++) {
+    if (v)
+      for (int k = 0; k < d; k++) v[q * d + k] = x[q * (d + 1) + k];
+    if (p) p[q] = x[q * (d + 1) + d];
+  }
+  return 0;
+}
+int sb200_vec_merge(long long nodes, int d, const double* v, const double* p, double* x, void*) {
+  if (nodes < 0 || d < 1 || !x || (!v && !p)) FAIL(SB200_ERR_ARG, "sb200_vec_merge: bad arguments");
+  for (long long q = 0; q < nodes; q++) {
+    if (v)
+      for (int k = 0; k < d; k++) x[q * (d + 1) + k] = v[q * d + k];
+    if (p) x[q * (d + 1) + d] = p[q];
+  }
+  return 0;
+}
+int sb200_vec_axpby(long long n, double a, const double* x, double b, double* y, void*) {
+  if (n < 0 || !y || (!x && a != 0.0)) FAIL(SB200_ERR_ARG, "sb200_vec_axpby: bad arguments");
+  for (long long i = 0; i < n; i++) y[i] = a == 0.0 ? b * y[i] : (b == 0.0 ? a * x[i] : a * x[i] + b * y[i]);
+  return 0;
+}
+int sb200_vec_pointwise_divide(long long n, const double* x, const double* dg, double* y, void*) {
+  if (n < 0 || !x || !dg || !y) FAIL(SB200_ERR_ARG, "sb200_vec_pointwise_divide: bad arguments");
+  for (long long i = 0; i < n; i++) y[i] = x[i] / dg[i];
+  return 0;
+}
+int sb200_vec_remove_mean(long long n, int stride, int offset, double* x, double* scratch, void*) {
+  if (n < 0 || stride < 1 || offset < 0 || offset >= stride || !x || !scratch) FAIL(SB200_ERR_ARG, "sb200_vec_remove_mean: bad arguments");
+  double s = 0;
+  for (long long i = 0; i < n; i++) s += x[offset + i * stride];
+  s /= (double)n;
+  for (long long i = 0; i < n; i++) x[offset + i * stride] -= s;
+  return 0;
+}
 int sb200_stream_sync(void*) { return 0; }
 
 // ---- ChebMult -------------------------------------------------------------------------------------------------------------
@@ -720,5 +758,45 @@ int sb200_stokes_pc_velocity_csr(sb200_stokes* s, int* rowptr, int* colidx, doub
   if (rowptr) rowptr[G.g * nc] = (int)(fd_total_entries(G) * nc);
   return 0;
 }
+
+// ---- what the Python harness (spectral_petsc_b200/capi.py) calls besides the above, so that the GPU tests' own logic can be
+// dry-run on CPU over this double (tests/test_gpu_dry_run_cpu.py); single rank only ------------------------------------------------
+int sb200_version(void) { return 100; }
+int sb200_ksp_create_slab(long long n_local, int restart, int rank, int nranks, sb200_ksp** out) {
+  if (rank != 0 || nranks != 1) FAIL(SB200_ERR_SUP, "test double: single rank only");
+  return sb200_ksp_create(n_local, restart, out);
+}
+int sb200_ksp_get_history(const sb200_ksp* k, double* h_hist, int cap, int* n) {
+  *n = (int)k->history.size();
+  if (h_hist)
+    for (int i = 0; i < cap && i < *n; i++) h_hist[i] = k->history[i];
+  return 0;
+}
+int sb200_ksp_get_times(const sb200_ksp*, double* a, double* b, double* c) {
+  if (a) *a = 0;
+  if (b) *b = 0;
+  if (c) *c = 0;
+  return 0;
+}
+int sb200_stokes_slab_info(const sb200_stokes* s, int* rank, int* nranks, int* i0, int* nloc, long long* goff_nodes) {
+  if (rank) *rank = 0;
+  if (nranks) *nranks = 1;
+  if (i0) *i0 = 0;
+  if (nloc) *nloc = s->dim[0];
+  if (goff_nodes) *goff_nodes = 0;
+  return 0;
+}
+int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, int* i0, int* nloc, long long* goff, long long* gtotal) {
+  if (rank) *rank = 0;
+  if (nranks) *nranks = 1;
+  if (i0) *i0 = 0;
+  if (nloc) *nloc = e->dim[0];
+  if (goff) *goff = 0;
+  if (gtotal) *gtotal = e->g;
+  return 0;
+}
+int sb200_apply_elliptic_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_elliptic_matmult((sb200_elliptic*)ctx, x, y, stream); }
+int sb200_apply_stokes_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult((sb200_stokes*)ctx, x, y, stream); }
+int sb200_apply_stokes_matmult_vv(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult_vv((sb200_stokes*)ctx, x, y, stream); }
 
 }  // extern "C"

@@ -38,3 +38,17 @@ def check_driver2(txt):
     assert float(m.group(1)) == 0.0         # withDirichlet = PETSC_FALSE is StokesMatMultPV (stokes.C:557-566)
     assert float(m.group(2)) < 1e-5         # the manufactured velocity is divergence free once its boundary values are in
     assert float(m.group(3)) > 1e-2         # ... and is not when the boundary is zeroed
+    # StokesPCApply0..3 over the device-resident composition (host/saddle.cpp), inner solves to 1e-12
+    m = re.search(r"null-space removal: pressure mean (\S+)  velocity change (\S+)", txt)
+    assert float(m.group(1)) < 1e-15 and float(m.group(2)) == 0.0
+    m = re.search(r"saddle type 0 \(block LU, exact inner solves\): max \|PC\(J x\) - x\| / max \|x\| = (\S+)", txt)
+    assert float(m.group(1)) < 1e-8         # the block LU factorisation applied exactly inverts StokesMatMult (stokes.C:1712-1713)
+    m = re.search(r"saddle type 1 \(upper\): .* = (\S+)", txt)
+    assert float(m.group(1)) < 1e-9
+    m = re.search(r"saddle type 2 \(diagonal\): max \|VV y_v - r_v\| / max \|r_v\| = (\S+)   \|y_v\(2\) - y_v\(3\)\| = (\S+)   \|y_p\(1\) - y_p\(2\)\| / max = (\S+)", txt)
+    assert float(m.group(1)) < 1e-9 and float(m.group(2)) < 1e-12 and float(m.group(3)) < 1e-10
+    m = re.search(r"saddle type 3 \(lower\): \|y_p\(3\) - y_p\(0\)\| = (\S+)", txt)
+    assert float(m.group(1)) < 1e-10
+    m = re.search(r"saddle inner iterations: velocity (\d+)  schur (\d+)", txt)
+    assert int(m.group(1)) > 0 and int(m.group(2)) > 0
+    assert "saddle wrong-size Vec -> 83   same Vec twice -> 62" in txt

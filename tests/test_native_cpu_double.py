@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 HOST = ["tests/mock/sb200_cpu_double.cpp", "spectral_petsc_b200/host/reference_api.cpp", "spectral_petsc_b200/host/petsc_shim.cpp",
-        "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
+        "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/host/saddle.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,7 @@ def stokes_exe(tmp_path_factory):
 def exe(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("native") / "elliptic_cpu_double")
     src = ["apps/elliptic.cpp", "tests/mock/sb200_cpu_double.cpp", "spectral_petsc_b200/host/reference_api.cpp", "spectral_petsc_b200/host/petsc_shim.cpp",
-           "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
+           "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/host/saddle.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out] + [os.path.join(ROOT, s) for s in src])
     return out
 
@@ -106,6 +106,18 @@ def test_native_stokes_flow_equals_python_flow(stokes_exe, cmd):
         assert (a["snes_its"], a["reason"]) == (b["snes_its"], b["reason"])
         assert len(a["ksp_its"]) == len(b["ksp_its"]) and all(abs(x - y) <= 1 for x, y in zip(a["ksp_its"], b["ksp_its"]))
         assert abs(a["error"] - b["error"]) <= 1e-3 * b["error"] + 1e-8  # the solves stop at their tolerances on both sides
+
+
+@pytest.mark.parametrize("cmd", STOKES_CASES)
+def test_device_resident_saddle_pc_equals_host_orchestrated_one(stokes_exe, cmd):
+    """StokesPCApply0..3 composed on device vectors (host/saddle.cpp: sb200_saddle_* over the shells, sb200_ksp and the vector
+    helpers - the default) against the same composition written out on host copies in apps/stokes.cpp (-saddle_on_host 1)."""
+    _, dev = native_stokes(stokes_exe, cmd)
+    _, host = native_stokes(stokes_exe, cmd + " -saddle_on_host 1")
+    assert len(dev) == len(host) >= 1
+    for a, b in zip(dev, host):
+        assert (a["snes_its"], a["reason"], a["ksp_its"]) == (b["snes_its"], b["reason"], b["ksp_its"])
+        assert abs(a["error"] - b["error"]) <= 1e-6 * b["error"]
 
 
 def test_native_stokes_vtk_equals_python_vtk(stokes_exe, tmp_path):

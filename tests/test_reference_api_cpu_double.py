@@ -11,7 +11,7 @@ from support.ref_api_checks import check_driver1, check_driver2
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = ["tests/mock/sb200_cpu_double.cpp", "spectral_petsc_b200/host/reference_api.cpp", "spectral_petsc_b200/host/petsc_shim.cpp",
-        "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
+        "spectral_petsc_b200/host/host_ilu.cpp", "spectral_petsc_b200/host/saddle.cpp", "spectral_petsc_b200/csrc/exact.cpp", "spectral_petsc_b200/csrc/cheb_matrix.cpp"]
 
 
 @pytest.mark.parametrize("driver,check", [("ref_api_driver", check_driver1), ("ref_api_driver2", check_driver2)])
