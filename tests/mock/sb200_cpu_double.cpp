@@ -795,6 +795,7 @@ int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, in
   if (gtotal) *gtotal = e->g;
   return 0;
 }
+int sb200_elliptic_set_path(sb200_elliptic*, int path) { return path >= 0 && path <= 3 ? 0 : SB200_ERR_USER; }  // one CPU path here
 int sb200_apply_elliptic_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_elliptic_matmult((sb200_elliptic*)ctx, x, y, stream); }
 int sb200_apply_stokes_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult((sb200_stokes*)ctx, x, y, stream); }
 int sb200_apply_stokes_matmult_vv(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult_vv((sb200_stokes*)ctx, x, y, stream); }

@@ -29,3 +29,20 @@ def test_dry_run(libmock, module, filters, expect):
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     assert "dry run: %d test invocations passed" % expect in r.stdout
+
+
+def test_bench_extras_dry_run(libmock):
+    """The per-P sweep and the KSP metric that bench.py runs in child processes: every row and key they are meant to produce."""
+    import json
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "support", "dry_run_bench_extras.py"), libmock], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    ops = [row["op"] for row in d["p_sweep"]]
+    assert ops[:6] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)"]
+    ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic"]
+    assert ell == [(16, "generic"), (17, "generic"), (32, "generic"), (32, "chain per axis"), (32, "persistent chain")]
+    assert sum(row["op"] == "ChebMult" for row in d["p_sweep"]) == 6 and sum(row["op"].startswith("FormJacobian") for row in d["p_sweep"]) == 3
+    k = d["ksp"]
+    assert k["config1_elliptic16_exact2_pc_ilu2"]["iterations"] == 16 and k["config1_elliptic16_exact2_pc_lu"]["iterations"] == 13
+    assert k["config1_elliptic16_exact2_pc_lu"]["norm_of_error"] < 1e-9 and k["fgmres30_cycle_128"]["iterations"] == 30
