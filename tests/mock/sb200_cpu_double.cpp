@@ -796,6 +796,23 @@ int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, in
   return 0;
 }
 int sb200_elliptic_set_path(sb200_elliptic*, int path) { return path >= 0 && path <= 3 ? 0 : SB200_ERR_USER; }  // one CPU path here
+// host-buffer forms: "device" memory is host memory here, so they are the operator itself; the queue completes at submit
+static int g_pending = 0;
+int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V) { return sb200_elliptic_matmult(e, h_U, h_V, nullptr); }
+int sb200_elliptic_matmult_host_submit(sb200_elliptic* e, const double* h_U, double* h_V) {
+  if (g_pending >= 4) FAIL(SB200_ERR_USER, "host queue full: call sb200_elliptic_matmult_host_wait first");
+  g_pending++;
+  return sb200_elliptic_matmult(e, h_U, h_V, nullptr);
+}
+int sb200_elliptic_matmult_host_wait(sb200_elliptic*) {
+  if (g_pending <= 0) FAIL(SB200_ERR_USER, "host queue empty: nothing was submitted");
+  g_pending--;
+  return 0;
+}
+int sb200_elliptic_matmult_host_pending(const sb200_elliptic*, int* pending) {
+  *pending = g_pending;
+  return 0;
+}
 int sb200_apply_elliptic_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_elliptic_matmult((sb200_elliptic*)ctx, x, y, stream); }
 int sb200_apply_stokes_matmult(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult((sb200_stokes*)ctx, x, y, stream); }
 int sb200_apply_stokes_matmult_vv(void* ctx, const double* x, double* y, void* stream) { return sb200_stokes_matmult_vv((sb200_stokes*)ctx, x, y, stream); }

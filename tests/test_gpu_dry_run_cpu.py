@@ -46,3 +46,12 @@ def test_bench_extras_dry_run(libmock):
     k = d["ksp"]
     assert k["config1_elliptic16_exact2_pc_ilu2"]["iterations"] == 16 and k["config1_elliptic16_exact2_pc_lu"]["iterations"] == 13
     assert k["config1_elliptic16_exact2_pc_lu"]["norm_of_error"] < 1e-9 and k["fgmres30_cycle_128"]["iterations"] == 30
+    # the headline flow (bench.run_cuda at 16^3 over the double): every key of the JSON contract, both end-to-end legs
+    line = d["line"]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "roofline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["metric"] == "spectral MatMult GDOF/s (fp64)" and line["dtype"] == "f64" and line["value"] > 0 and line["warmup"] >= 3
+    assert line["e2e"]["queued_equals_sync_call_bitwise"] is True and "submit" in line["e2e"]["api"]
+    assert line["e2e"]["h2d_bytes_per_step"] == line["e2e"]["d2h_bytes_per_step"] == 8 * line["config"]["global_vec_len"]
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["traffic"] == 231122176
