@@ -150,6 +150,14 @@ def test_native_stokes_executable(cuda, tmp_path):
             assert a == b
         else:
             assert np.allclose([float(t) for t in a.split()], [float(t) for t in b.split()], rtol=1e-5, atol=1e-6)
+    # the saddle-point PC composed on the device (the default, sb200_saddle_*) against the same composition on host copies
+    rh = subprocess.run([exe] + (cmd + vn + " -saddle_on_host 1").split(), capture_output=True, text=True, timeout=900)
+    assert rh.returncode == 0, rh.stderr + rh.stdout
+    kd = [l for l in out if l.startswith("KSP iterations per Newton step:") or l.startswith("Number of nonlinear iterations")]
+    kh = [l for l in rh.stdout.split("\n") if l.startswith("KSP iterations per Newton step:") or l.startswith("Number of nonlinear iterations")]
+    assert len(kd) == len(kh) == 6
+    for a, b in zip(kd, kh):
+        assert all(abs(int(x) - int(y)) <= 1 for x, y in zip(a.replace("=", ":").split(":")[1].split(), b.replace("=", ":").split(":")[1].split()))
     # BASELINE config 4 (README:44) with ILU(2) where the README asks for hypre: 26 outer iterations over the oracle (245 with ILU(0), 11 with LU)
     r = subprocess.run([exe] + ("-exact 2 -cont0 1 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_type fgmres -dim 20,20,20 -ksp_rtol 1e-10 "
                                 "-ksp_max_it 400 -vel_pc_factor_levels 2 -svel_pc_factor_levels 2").split(),
