@@ -132,6 +132,12 @@ int sb200_saddle_create(sb200_stokes* s, int type, sb200_saddle** out) {
   P->s = s;
   P->type = type;
   int rc = sb200_stokes_sizes(s, &P->m, &P->g, &P->gp, &P->gv, &P->dv);
+  int nranks = 1;
+  if (!rc) rc = sb200_stokes_slab_info(s, nullptr, &nranks, nullptr, nullptr, nullptr);
+  if (!rc && nranks != 1) {  // the inner KSPs and the null-space projection here reduce over one rank's vectors only
+    sb200::set_last_error("sb200_saddle_create: the saddle-point preconditioners are single-GPU (the context is slab-partitioned)");
+    rc = SB200_ERR_SUP;
+  }
   if (!rc && P->gp <= 0) rc = SB200_ERR_USER;
   if (!rc) P->d = (int)(P->gv / P->gp);
   for (int i = 0; i < 8 && !rc; i++) rc = sb200_malloc((void**)&P->v[i], (size_t)P->gv * sizeof(double) + 16);
