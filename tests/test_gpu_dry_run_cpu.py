@@ -55,3 +55,12 @@ def test_bench_extras_dry_run(libmock):
     assert line["e2e"]["queued_equals_sync_call_bitwise"] is True and "submit" in line["e2e"]["api"]
     assert line["e2e"]["h2d_bytes_per_step"] == line["e2e"]["d2h_bytes_per_step"] == 8 * line["config"]["global_vec_len"]
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["traffic"] == 231122176
+
+
+def test_smoke_dry_run(libmock):
+    """__graft_entry__.smoke() with the harness pointed at the test double: the calls it makes and its oracle comparisons."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from support.dry_run_gpu_tests import patch\npatch(%r)\nimport __graft_entry__ as g\ng.smoke()\n") % (ROOT, os.path.join(ROOT, "tests"), libmock)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    assert "smoke ok" in r.stdout and "StokesMatMult" in r.stdout
