@@ -292,15 +292,6 @@ struct Flow {
   }
 };
 
-// StokesVecView (stokes.C:1898-1915)
-void vec_view(FILE* f, const double* a, long long nodes, int pernode, int perline) {
-  for (long long i = 0; i < nodes; i++) {
-    for (int j = 0; j < pernode && j < perline; j++) fprintf(f, "%20e ", a[i * pernode + j]);
-    for (int j = pernode; j < perline; j++) fprintf(f, "0 ");
-    fprintf(f, "\n");
-  }
-}
-
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -505,92 +496,11 @@ int main(int argc, char** argv) {
   }
 
   if (want_vtk) {  // StokesStateView(ctx, x, "final state") (stokes.C:238-242, 1821-1894)
-    const long long nodes = F.m;
-    Vecd dirichlet(F.dv), coord(nodes * d);
-    CHK(sb200_stokes_exact_solution(d, dim, (int)opt.exact, nullptr, nullptr, dirichlet.data()));
-    std::vector<char> bdy(nodes);
-    {
-      int ind[3] = {0, 0, 0};
-      for (long long node = 0; node < nodes; node++) {
-        bool b = false;
-        for (int j = 0; j < d; j++) {
-          coord[node * d + j] = cos(ind[j] * M_PI / (dim[j] - 1));
-          b = b || ind[j] == 0 || ind[j] == dim[j] - 1;
-        }
-        bdy[node] = b;
-        for (int j = d - 1; j >= 0; j--) {
-          if (++ind[j] < dim[j]) break;
-          ind[j] = 0;
-        }
-      }
-    }
-    Vecd fields[4];  // velocity, pressure, vel_force, div_force on the full grid
-    const Vecd* globals[2] = {&hx, &hU2};
-    for (int w = 0; w < 2; w++) {
-      Vecd v, p, pL(nodes, 0.0);
-      F.split(*globals[w], v, p);
-      Vecd& vL = fields[2 * w];
-      vL.assign(nodes * d, 0.0);
-      long long qi = 0, qb = 0;
-      for (long long node = 0; node < nodes; node++) {
-        if (bdy[node]) {
-          for (int k = 0; k < d; k++) vL[node * d + k] = dirichlet[qb * d + k];  // scatterDL
-          qb++;
-        } else {
-          for (int k = 0; k < d; k++) vL[node * d + k] = v[qi * d + k];  // scatterVL
-          pL[node] = p[qi];                                                // scatterPL
-          qi++;
-        }
-      }
-      Tmp dp(F.m);
-      if (!dp.v) return SB200_ERR_CUDA;
-      CHK(upload(pL, dp.v));
-      CHK(StokesPressureReduceOrder(dp.v, F.ctx));
-      CHK(download(dp.v, fields[2 * w + 1]));
-    }
-    Vecd eta, deta, strain[3];
-    {
-      Tmp s0(F.m), s1(F.m * d);
-      if (!s0.v || !s1.v) return SB200_ERR_CUDA;
-      CHK(StokesGetState(F.ctx, 0, s0.v));
-      CHK(download(s0.v, eta));
-      CHK(StokesGetState(F.ctx, 1, s0.v));
-      CHK(download(s0.v, deta));
-      for (int j = 0; j < d; j++) {
-        CHK(StokesGetState(F.ctx, 2 + j, s1.v));
-        CHK(download(s1.v, strain[j]));
-      }
-    }
-    FILE* f = fopen(vtk_path.c_str(), "w");
-    if (!f) {
+    CHK(upload(hx, x));
+    if (StokesStateViewFile(F.ctx, x, vtk_path.c_str())) {
       fprintf(stderr, "error: cannot write %s\n", vtk_path.c_str());
       return 1;
     }
-    const int mm = dim[0], nn = dim[1], pp = d > 2 ? dim[2] : 1;
-    fprintf(f, "# vtk DataFile Version 2.0\nStokes Output\nASCII\nDATASET STRUCTURED_GRID\n");
-    fprintf(f, "DIMENSIONS %d %d %d\nPOINTS %d double\n", mm, nn, pp, mm * nn * pp);
-    vec_view(f, coord.data(), nodes, d, 3);
-    fprintf(f, "\nPOINT_DATA %d\nVECTORS velocity double\n", mm * nn * pp);
-    vec_view(f, fields[0].data(), nodes, d, 3);
-    fprintf(f, "\nSCALARS pressure double 1\nLOOKUP_TABLE default\n");
-    vec_view(f, fields[1].data(), nodes, 1, 1);
-    fprintf(f, "\nVECTORS vel_force double\n");
-    vec_view(f, fields[2].data(), nodes, d, 3);
-    fprintf(f, "\nSCALARS div_force double 1\nLOOKUP_TABLE default\n");
-    vec_view(f, fields[3].data(), nodes, 1, 1);
-    fprintf(f, "\nSCALARS eta double 1\nLOOKUP_TABLE default\n");
-    vec_view(f, eta.data(), nodes, 1, 1);
-    fprintf(f, "\nSCALARS deta double 1\nLOOKUP_TABLE default\n");
-    vec_view(f, deta.data(), nodes, 1, 1);
-    fprintf(f, "\nTENSORS strain double\n");
-    for (long long i = 0; i < nodes; i++) {
-      for (int j = 0; j < 3; j++) {
-        for (int k = 0; k < 3; k++) fprintf(f, "%20e ", (j < d && k < d) ? strain[j][i * d + k] : 0.0);
-        fprintf(f, "\n");
-      }
-      fprintf(f, "\n");
-    }
-    fclose(f);
   }
   o.warn_unused();
 

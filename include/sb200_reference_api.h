@@ -100,6 +100,12 @@ PetscErrorCode StokesPCApply3(PC pc, Vec x, Vec y);
 /* the null space StokesRemoveConstantPressure attaches to the outer KSP (stokes.C:1006-1025), applied to a global Vec in place */
 PetscErrorCode StokesNullSpaceRemove(StokesCtxB200* ctx, Vec x);
 PetscErrorCode StokesGetInnerIterations(StokesCtxB200* ctx, PetscInt* velocity, PetscInt* schur);
+/* StokesStateView(ctx, state, label) (stokes.C:1821-1894, called for -output_vtk at :238-242): the VTK dump of velocity, pressure,
+ * forcing, eta, deta and the strain tensor on the full grid.  Like the reference it ignores the label and writes ./stokes.vtk
+ * (stokes.C:1856); StokesStateViewFile takes the path.  Set-up / output work: runs on host copies, with the boundary pressure
+ * extrapolated on the device by StokesPressureReduceOrder. */
+PetscErrorCode StokesStateView(StokesCtxB200* ctx, Vec state, const char* label);
+PetscErrorCode StokesStateViewFile(StokesCtxB200* ctx, Vec state, const char* path);
 /* the C-ABI handle behind the context (for sb200_saddle_create / sb200_ksp_set_operators without going through Vecs) */
 struct sb200_stokes* StokesGetHandle(StokesCtxB200* ctx);
 PetscErrorCode StokesSetContinuation(StokesCtxB200* ctx, PetscReal exponent, PetscReal regularization); /* stokes.C:218-219 */

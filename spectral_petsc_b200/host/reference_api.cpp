@@ -1,6 +1,7 @@
 // The reference's operator interface on the B200 path (include/sb200_reference_api.h): same
 // names, same argument meaning, same error behaviour; each function cites what it replaces.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -200,6 +201,7 @@ struct StokesCtxB200 {
   StokesVelocitySolve vel_pc = nullptr, svel_pc = nullptr;  // PCApply on MatVVPC for KSPVelocity / KSPSchurVelocity
   void* vel_pc_ctx = nullptr;
   void* svel_pc_ctx = nullptr;
+  std::vector<double> h_force;  // host copy of c->force (stokes.C:1001), what StokesStateView writes as vel_force / div_force
   double vel_rtol = 1e-5, schur_rtol = 1e-5;  // KSP defaults
   int vel_max_it = 10000, schur_max_it = 10000, svel_preonly = 0;
 };
@@ -373,6 +375,7 @@ PetscErrorCode StokesCreateExactSolution(SNES snes, Vec U, Vec U2) {  // stokes.
   stokes_fill(c, &hu, &hu2, nullptr);
   CHK(VecSetValuesHost(U, hu.data()));
   CHK(VecSetValuesHost(U2, hu2.data()));
+  c->h_force = hu2;
   const PetscScalar* f;
   CHK(VecCUDAGetArrayRead(U2, &f));
   return sb200_stokes_set_force(c->s, f, nullptr);  // VecCopy(U2, c->force) stokes.C:1001
@@ -517,6 +520,123 @@ PetscErrorCode StokesGetInnerIterations(StokesCtxB200* c, PetscInt* velocity, Pe
   if (schur) *schur = (PetscInt)s;
   return 0;
 }
+
+// ---- StokesStateView / StokesVecView (stokes.C:1821-1915): the VTK dump of -output_vtk ---------------------------------------------
+// StokesVecView writes `nodes` lines of `perline` numbers, the first `pernode` of them from the array (stokes.C:1898-1915).
+static void stokes_vec_view(FILE* f, const double* a, long long nodes, int pernode, int perline) {
+  for (long long i = 0; i < nodes; i++) {
+    for (int j = 0; j < pernode && j < perline; j++) fprintf(f, "%20e ", a[i * pernode + j]);
+    for (int j = pernode; j < perline; j++) fprintf(f, "0 ");
+    fprintf(f, "\n");
+  }
+}
+
+PetscErrorCode StokesStateViewFile(StokesCtxB200* c, Vec state, const char* path) {
+  const int d = (int)c->opt.numDims;
+  const long long nodes = c->m;
+  if (!state || state->n != (PetscInt)c->g || !path) return SB200_ERR_USER;
+  if (c->h_force.size() != (size_t)c->g) return SB200_ERR_USER;  // c->force is set by StokesCreateExactSolution (stokes.C:1001)
+  std::vector<double> hx((size_t)c->g), dirichlet((size_t)c->dv), coord((size_t)nodes * d);
+  CHK(VecGetValuesHost(state, hx.data()));
+  CHK(stokes_fill(c, nullptr, nullptr, &dirichlet));
+  std::vector<char> bdy((size_t)nodes);
+  {  // node coordinates and the boundary flag, in walk order (stokes.C:791-879)
+    int ind[3] = {0, 0, 0};
+    for (long long node = 0; node < nodes; node++) {
+      bool b = false;
+      for (int j = 0; j < d; j++) {
+        coord[node * d + j] = cos(ind[j] * M_PI / (c->opt.dim[j] - 1));
+        b = b || ind[j] == 0 || ind[j] == c->opt.dim[j] - 1;
+      }
+      bdy[node] = b;
+      for (int j = d - 1; j >= 0; j--) {
+        if (++ind[j] < c->opt.dim[j]) break;
+        ind[j] = 0;
+      }
+    }
+  }
+  // velocity, pressure of the state and of the forcing on the full grid (stokes.C:1828-1850): interior from the global vector,
+  // Dirichlet values on the boundary, pressure extrapolated to the boundary by StokesPressureReduceOrder
+  std::vector<double> fields[4];
+  const std::vector<double>* globals[2] = {&hx, &c->h_force};
+  Vec dp = nullptr;
+  CHK(VecCreateSeqCUDA(PETSC_COMM_SELF, (PetscInt)c->m, &dp));
+  for (int w = 0; w < 2; w++) {
+    std::vector<double>& vL = fields[2 * w];
+    std::vector<double> pL((size_t)nodes, 0.0);
+    vL.assign((size_t)nodes * d, 0.0);
+    const std::vector<double>& G = *globals[w];
+    long long qi = 0, qb = 0;
+    for (long long node = 0; node < nodes; node++) {
+      if (bdy[node]) {
+        for (int k = 0; k < d; k++) vL[node * d + k] = dirichlet[qb * d + k];  // scatterDL
+        qb++;
+      } else {
+        for (int k = 0; k < d; k++) vL[node * d + k] = G[qi * (d + 1) + k];  // scatterGV + scatterVL
+        pL[node] = G[qi * (d + 1) + d];                                        // scatterGP + scatterPL
+        qi++;
+      }
+    }
+    PetscErrorCode rc = VecSetValuesHost(dp, pL.data());
+    if (!rc) rc = StokesPressureReduceOrder(dp, c);
+    fields[2 * w + 1].resize((size_t)nodes);
+    if (!rc) rc = VecGetValuesHost(dp, fields[2 * w + 1].data());
+    if (rc) {
+      VecDestroy(dp);
+      return rc;
+    }
+  }
+  CHK(VecDestroy(dp));
+  std::vector<double> eta((size_t)nodes), deta((size_t)nodes), strain[3];
+  {
+    Vec s0 = nullptr, s1 = nullptr;
+    PetscErrorCode rc = VecCreateSeqCUDA(PETSC_COMM_SELF, (PetscInt)c->m, &s0);
+    if (!rc) rc = VecCreateSeqCUDA(PETSC_COMM_SELF, (PetscInt)(c->m * d), &s1);
+    if (!rc) rc = StokesGetState(c, 0, s0);
+    if (!rc) rc = VecGetValuesHost(s0, eta.data());
+    if (!rc) rc = StokesGetState(c, 1, s0);
+    if (!rc) rc = VecGetValuesHost(s0, deta.data());
+    for (int j = 0; j < d && !rc; j++) {
+      strain[j].resize((size_t)nodes * d);
+      rc = StokesGetState(c, 2 + j, s1);
+      if (!rc) rc = VecGetValuesHost(s1, strain[j].data());
+    }
+    if (s0) VecDestroy(s0);
+    if (s1) VecDestroy(s1);
+    if (rc) return rc;
+  }
+  FILE* f = fopen(path, "w");
+  if (!f) return SB200_ERR_USER;  // PETSC_ERR_FILE_OPEN is 65; the shim has no file error class of its own
+  const int mm = c->opt.dim[0], nn = c->opt.dim[1], pp = d > 2 ? c->opt.dim[2] : 1;
+  fprintf(f, "# vtk DataFile Version 2.0\nStokes Output\nASCII\nDATASET STRUCTURED_GRID\n");
+  fprintf(f, "DIMENSIONS %d %d %d\nPOINTS %d double\n", mm, nn, pp, mm * nn * pp);
+  stokes_vec_view(f, coord.data(), nodes, d, 3);
+  fprintf(f, "\nPOINT_DATA %d\nVECTORS velocity double\n", mm * nn * pp);
+  stokes_vec_view(f, fields[0].data(), nodes, d, 3);
+  fprintf(f, "\nSCALARS pressure double 1\nLOOKUP_TABLE default\n");
+  stokes_vec_view(f, fields[1].data(), nodes, 1, 1);
+  fprintf(f, "\nVECTORS vel_force double\n");
+  stokes_vec_view(f, fields[2].data(), nodes, d, 3);
+  fprintf(f, "\nSCALARS div_force double 1\nLOOKUP_TABLE default\n");
+  stokes_vec_view(f, fields[3].data(), nodes, 1, 1);
+  fprintf(f, "\nSCALARS eta double 1\nLOOKUP_TABLE default\n");
+  stokes_vec_view(f, eta.data(), nodes, 1, 1);
+  fprintf(f, "\nSCALARS deta double 1\nLOOKUP_TABLE default\n");
+  stokes_vec_view(f, deta.data(), nodes, 1, 1);
+  fprintf(f, "\nTENSORS strain double\n");
+  for (long long i = 0; i < nodes; i++) {
+    for (int j = 0; j < 3; j++) {
+      for (int k = 0; k < 3; k++) fprintf(f, "%20e ", (j < d && k < d) ? strain[j][i * d + k] : 0.0);
+      fprintf(f, "\n");
+    }
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return 0;
+}
+
+// The reference ignores its third argument (a label, "final state" at stokes.C:240) and always writes stokes.vtk (stokes.C:1856).
+PetscErrorCode StokesStateView(StokesCtxB200* c, Vec state, const char*) { return StokesStateViewFile(c, state, "stokes.vtk"); }
 
 sb200_stokes* StokesGetHandle(StokesCtxB200* c) { return c ? c->s : nullptr; }
 
