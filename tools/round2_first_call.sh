@@ -1,0 +1,30 @@
+#!/bin/bash
+# Everything that round 1 left unmeasured, in ONE GPU call (about 8-10 box minutes):
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Outputs land in gpurun_out/ (r02_*): copy the summaries worth keeping into profiles/.
+# Order: the things whose numbers matter most first, so a call cut short still leaves them behind; every step is time-boxed and
+# a failing step does not stop the rest.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+step() { echo "=== $1" | tee -a $O/r02_steps.log; shift; ( "$@" ) >> $O/r02_steps.log 2>&1; echo "    exit $?" | tee -a $O/r02_steps.log; }
+
+# 1. late GPU tests first (never run on a GPU in round 1), then the whole suite
+step "late GPU tests" timeout 600 python -m pytest tests/test_gpu_zz_saddle.py tests/test_gpu_zz_reference_api2.py tests/test_gpu_zz_drivers.py -x -q
+step "full GPU suite" timeout 1200 python -m pytest tests -m gpu -x -q
+
+# 2. the bench line (with the per-P sweep and the KSP metric in child processes) and the reference arm
+timeout 600 python bench.py > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err; echo "bench exit $?" >> $O/r02_steps.log
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/r02_bench_ref.json 2>> $O/r02_steps.log
+
+# 3. per-launch time lists (never a bench value): the Stokes step and the native saddle-point PC
+timeout 300 python tools/stokes_once.py > $O/r02_plain_stokes.log 2>&1 && \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_stokes.csv python tools/stokes_once.py > $O/r02_ncu_stokes.log 2>&1
+timeout 300 python tools/saddle_once.py > $O/r02_plain_saddle.log 2>&1 && \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $O/r02_launches_saddle.csv python tools/saddle_once.py > $O/r02_ncu_saddle.log 2>&1
+
+# 4. one full capture of the Stokes kernels (the 52 % item of round 1): 14 launches of one StokesMatMult
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'eo_deriv|vv_flux|pad_nodes|crop|reduce_order' -c 16 -o $O/r02_prof_stokes python tools/stokes_once.py > $O/r02_ncu_full_stokes.log 2>&1
+# 5. the device assembly of the preconditioning matrices at 128^3 (not timed in round 1)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fd_assemble' -c 4 -o $O/r02_prof_fd python tools/p_sweep.py 1 > $O/r02_ncu_full_fd.log 2>&1
+tail -3 $O/r02_steps.log
