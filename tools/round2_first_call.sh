@@ -10,7 +10,7 @@ O=gpurun_out
 step() { echo "=== $1" | tee -a $O/r02_steps.log; shift; ( "$@" ) >> $O/r02_steps.log 2>&1; echo "    exit $?" | tee -a $O/r02_steps.log; }
 
 # 1. late GPU tests first (never run on a GPU in round 1), then the whole suite
-step "late GPU tests" timeout 600 python -m pytest tests/test_gpu_zz_saddle.py tests/test_gpu_zz_reference_api2.py tests/test_gpu_zz_drivers.py -x -q
+step "late GPU tests" timeout 600 python -m pytest tests/test_zz1_gpu_saddle.py tests/test_zz2_gpu_reference_api2.py tests/test_zz3_gpu_drivers.py -x -q
 step "full GPU suite" timeout 1200 python -m pytest tests -m gpu -x -q
 
 # 2. the bench line (with the per-P sweep and the KSP metric in child processes) and the reference arm
