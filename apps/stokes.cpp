@@ -332,8 +332,12 @@ int main(int argc, char** argv) {
     fprintf(stderr, "error: Rheology type %d not implemented\n", (int)opt.rheology);  // stokes.C:492
     return 83;
   }
-  if (opt.exact < 0 || opt.exact > 2) {
+  if (opt.exact < 0 || opt.exact > 3) {
     fprintf(stderr, "error: Exact solution %d not implemented\n", (int)opt.exact);  // stokes.C:452
+    return 83;
+  }
+  if (opt.exact == 3 && nd != 2) {
+    fprintf(stderr, "error: StokesExact3 only implemented for dimension 2 but %d given\n", nd);  // stokes.C:2021
     return 83;
   }
   Flow F;

@@ -214,7 +214,7 @@ static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std:
 
 PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A, Vec* x, StokesCtxB200** ctx) {
   // stokes.C:257-345 with StokesProcessOptions' switches (stokes.C:434-493)
-  if (opt->exact < 0 || opt->exact > 2) return SB200_ERR_SUP;      // stokes.C:452 (exact 3 is 2-D only, not wired)
+  if (opt->exact < 0 || opt->exact > 3) return SB200_ERR_SUP;      // stokes.C:452; StokesExact3 itself refuses d != 2 (stokes.C:2021)
   if (opt->rheology < 0 || opt->rheology > 1) return SB200_ERR_SUP;  // stokes.C:492
   StokesCtxB200* c = new StokesCtxB200();
   c->opt = *opt;
@@ -228,7 +228,12 @@ PetscErrorCode StokesCreate(MPI_Comm comm, const StokesOptionsB200* opt, Mat* A,
   CHK(sb200_stokes_set_rheology(c->s, opt->rheology, opt->hardness, opt->exponent, opt->regularization, opt->gamma0));
   // Dirichlet values = exact solution on the boundary (StokesDirichlet, stokes.C:2039-2050)
   std::vector<double> D((size_t)c->dv);
-  stokes_fill(c, nullptr, nullptr, &D);
+  rc = stokes_fill(c, nullptr, nullptr, &D);
+  if (rc) {  // e.g. -exact 3 in three dimensions
+    sb200_stokes_destroy(c->s);
+    delete c;
+    return rc;
+  }
   void* dd = nullptr;
   CHK(sb200_malloc(&dd, D.size() * sizeof(double) + 8));
   CHK(sb200_memcpy_h2d(dd, D.data(), D.size() * sizeof(double), nullptr));

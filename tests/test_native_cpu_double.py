@@ -137,6 +137,14 @@ def test_native_stokes_vtk_equals_python_vtk(stokes_exe, tmp_path):
 
 
 def test_native_stokes_option_errors(stokes_exe):
-    for bad in ("-boundary 1", "-rheology 2", "-pcvel 1", "-pc_saddle_type 4", "-ksp_type gmres", "-dim 8,8,8,8", "-exact 3", "-vel_pc_type hypre"):
+    for bad in ("-boundary 1", "-rheology 2", "-pcvel 1", "-pc_saddle_type 4", "-ksp_type gmres", "-dim 8,8,8,8", "-exact 4", "-exact 3 -dim 6,6,6", "-vel_pc_type hypre"):
         r = subprocess.run([stokes_exe, "-exact", "2"] + bad.split(), capture_output=True, text=True, timeout=60)
         assert r.returncode == 83 and r.stderr.startswith("error:"), (bad, r.stderr)
+
+
+def test_native_stokes_exact3_two_dimensional_shear(stokes_exe):
+    """-exact 3 (StokesExact3, stokes.C:2016-2034: u = y + 1, v = p = 0, no forcing; 2-D only): the linear field is resolved
+    exactly, so one Newton step from zero lands on it to solver tolerance."""
+    out, steps = native_stokes(stokes_exe, "-exact 3 -dim 10,8 -cont0 1 " + BASE + " -ksp_rtol 1e-10 -ksp_max_it 200")
+    assert "DOF distribution: 144 global   48/80 pressure    96/160 velocity    64 dirichlet    0 mixed" in out
+    assert len(steps) == 1 and steps[0]["snes_its"] == 1 and steps[0]["reason"] == "CONVERGED_FNORM_RELATIVE" and steps[0]["error"] < 1e-7
