@@ -40,7 +40,9 @@ def test_bench_extras_dry_run(libmock):
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     ops = [row["op"] for row in d["p_sweep"]]
     assert ops[:6] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)"]
-    ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic"]
+    cfg = [(row["op"], row["dim"], row["launches"]) for row in d["p_sweep"] if "dim" in row]
+    assert [c[:2] for c in cfg] == [("MatMult_Elliptic", "12x12x12x12x12"), ("FormFunction", "12x12x12x12x12"), ("MatMult_Elliptic", "16x16x16"), ("FormFunction", "16x16x16")]
+    ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic" and "P" in row]
     assert ell == [(16, "generic"), (17, "generic"), (32, "generic"), (32, "chain per axis"), (32, "persistent chain")]
     assert sum(row["op"] == "ChebMult" for row in d["p_sweep"]) == 6 and sum(row["op"].startswith("FormJacobian") for row in d["p_sweep"]) == 3
     k = d["ksp"]

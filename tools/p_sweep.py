@@ -71,6 +71,30 @@ def rows(steps=10, Ps=(16, 32, 48, 64, 96, 128, 129), dev=None, flush=None):
         E.destroy()
 
 
+def config_rows(steps=10, dev=None, flush=None):
+    """BASELINE configs that are not cubes of the sweep: elliptic 5-D 12^5 (config 3, the README's arbitrary-dimension example) and
+    the 16^3 grid of config 1 - both far below the size where a roofline binds, so the launch count is the number to read."""
+    dev = dev or torch.device("cuda:0")
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    bw = hbm_gbs()
+    for dim in ([12] * 5, [16] * 3):
+        d, m = len(dim), int(np.prod(dim))
+        E = sp.Elliptic(dim, gamma=4.0, exponent=2.0)
+        E.form_function(torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(E.g)).to(dev))
+        U = torch.from_numpy(np.random.default_rng(0).standard_normal(E.g)).to(dev)
+        V, F = torch.empty_like(U), torch.empty_like(U)
+        fl, by = sum(2 * 2.0 * p for p in dim) * m, 8.0 * (2 * E.g + (2 + d) * m)
+        for name, fn in (("MatMult_Elliptic", lambda: E.mat_mult(U, V)), ("FormFunction", lambda: E.form_function(U, F))):
+            l0 = sp.launch_count()
+            fn()
+            nl = sp.launch_count() - l0
+            ms = timeit(fn, steps, flush)
+            yield {"op": name, "dim": "x".join(str(p) for p in dim), "launches": nl, "ms": ms, "gdof_s": m / ms / 1e6, "t_hbm_ms": by / bw / 1e6,
+                   "t_fp64_ms": fl / FP64_TFLOPS / 1e9, "frac_of_binding_roofline": max(by / bw / 1e6, fl / FP64_TFLOPS / 1e9) / ms}
+        E.destroy()
+
+
 def stokes_rows(steps=10, P=128, dev=None, flush=None):
     """The Stokes shells at P^3 (BASELINE config 5 state: -rheology 1 -exponent 3 -eps 1e-4) and the device assembly of MatVVPC."""
     dev = dev or torch.device("cuda:0")
@@ -113,6 +137,8 @@ def main():
     for row in rows(steps):
         print(json.dumps(row), flush=True)
     for row in stokes_rows(steps):
+        print(json.dumps(row), flush=True)
+    for row in config_rows(steps):
         print(json.dumps(row), flush=True)
 
 
