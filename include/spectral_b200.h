@@ -169,6 +169,10 @@ int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, voi
 /* StokesDivergence(ctx, withDirichlet, xG, yG) (stokes.C:570-595): the same with the Dirichlet velocities inserted on the boundary
  * when with_dirichlet != 0 (what the residual uses, :746); with_dirichlet = 0 is StokesMatMultPV. */
 int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d_x, double* d_y, void* stream);
+/* Opt-in (default 0): StokesMatMult and StokesFunction take their pressure rows  sum_i D_i v_i  from the trace of the velocity
+ * gradient their viscous part computes anyway, instead of running StokesDivergence on the same input a second time
+ * (stokes.C:509,746); same values bit for bit, one pad pass and d derivative passes fewer per application. */
+int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on);
 /* StokesMatMultVP (stokes.C:599-619): pressure gradient with P_N - P_{N-2} extrapolation, gp -> gv. */
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 /* StokesMatGetDiagonalSchur (stokes.C:542-553): y = 1/eta at pressure nodes (gp doubles). */

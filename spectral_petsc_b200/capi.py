@@ -392,6 +392,10 @@ class Stokes:
         _ck(lib().sb200_stokes_set_rheology(self._h, ctypes.c_int(rheology), ctypes.c_double(hardness), ctypes.c_double(exponent),
                                             ctypes.c_double(regularization), ctypes.c_double(gamma0)))
 
+    def set_trace_divergence(self, on):
+        """Opt-in: pressure rows of mat_mult / function from the trace of the gradient the viscous part computes (same bits)."""
+        _ck(lib().sb200_stokes_set_trace_divergence(self._h, ctypes.c_int(int(on))))
+
     def set_dirichlet(self, values):
         assert values.numel() == self.dv
         _ck(lib().sb200_stokes_set_dirichlet(self._h, _ptr(values), _stream()))

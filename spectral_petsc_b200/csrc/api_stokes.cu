@@ -140,6 +140,12 @@ int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d
   return s->c->divergence_into(d_x, s->c->gd.d, 0, with_dirichlet != 0, d_y, 1, 0, (cudaStream_t)stream);
 }
 
+int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  s->c->trace_divergence = on != 0;
+  return 0;
+}
+
 int sb200_stokes_matmult_schur(sb200_stokes* s, const double* d_x, double* d_y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream) {
   SB_CHECK(s && d_x && d_y, SB200_ERR_ARG, "null pointer");
   return s->c->matmult_schur(d_x, d_y, solve, solve_ctx, (cudaStream_t)stream);

@@ -104,6 +104,20 @@ __global__ void crop_sum_kernel(GridDesc gd, int nc, int nterms, TermPtrs tp, do
   }
 }
 
+// dst[gid*dstride + doff] = ((0 + G_0[node*d + 0]) + G_1[node*d + 1]) + G_2[node*d + 2] at interior nodes, G_i = D_i v (m*d each):
+// the divergence as the trace of the velocity gradient, accumulated in the order of stokes.C:584-590 with the arithmetic of
+// crop_sum_kernel(sign = 1), so the result has the bits of the separate StokesDivergence pass.
+__global__ void crop_trace_kernel(GridDesc gd, int d, TermPtrs tp, double* __restrict__ dst, int dstride, int doff) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
+    const NodeInfo n = decode_node(gd, idx);
+    if (!n.interior) continue;
+    double v = 0.0;
+    for (int t = 0; t < d; t++) v = __dadd_rn(v, __dmul_rn(1.0, tp.t[t][idx * d + t]));
+    dst[n.gid * dstride + doff] = v;
+  }
+}
+
 template <int D>
 struct VPtrs {
   double* v[D];
@@ -581,6 +595,15 @@ int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, d
   return 0;
 }
 
+int StokesCtx::crop_trace(double* const* grads, double* dst, int dstride, int doff, cudaStream_t s) {
+  TermPtrs tp;
+  for (int t = 0; t < 3; t++) tp.t[t] = t < gd.d ? grads[t] : nullptr;
+  crop_trace_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, gd.d, tp, dst, dstride, doff);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int StokesCtx::pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s) {
   pad_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, gd.d, src, sstride, soff, with_dirichlet ? dirichlet : nullptr, local);
   count_launch();
@@ -618,7 +641,8 @@ int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) 
   return crop(d, yL, dst, dstride, doff, false, nullptr, s);
 }
 
-int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s) {
+int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s,
+                               double* div_dst, int div_stride, int div_off) {
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));                                             // :635-637
@@ -629,6 +653,7 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
   }
+  if (div_dst) SB_TRY(crop_trace(&workV[2], div_dst, div_stride, div_off, s));  // before the flux overwrites the gradient
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
@@ -748,8 +773,12 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
 int StokesCtx::matmult(const double* xG, double* yG, cudaStream_t s) {
   SB_CHECK(xG && yG && xG != yG, SB200_ERR_ARG, "StokesMatMult: x and y must be distinct non-null vectors");
   const int d = gd.d;
-  SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s));                 // :508  vG1 = VV v
-  SB_TRY(divergence_into(xG, d + 1, 0, false, yG, d + 1, d, s));          // :509  pG1 = PV v
+  if (trace_divergence) {
+    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s, yG, d + 1, d));  // :508-509  vG1 = VV v and pG1 = PV v from one gradient
+  } else {
+    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s));               // :508  vG1 = VV v
+    SB_TRY(divergence_into(xG, d + 1, 0, false, yG, d + 1, d, s));        // :509  pG1 = PV v
+  }
   SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :512-513  vG1 += VP p
   return 0;
 }
@@ -766,6 +795,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
   }
+  if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));  // :746 from the gradient above (same Dirichlet-padded input)
   init_minmax_kernel<<<1, 1, 0, s>>>(minmax);
   count_launch();
   Rheo r{rheology, hardness, exponent, regularization, gamma0};
@@ -781,7 +811,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   count_launch();
   SB_CUDA(cudaGetLastError());
   SB_TRY(viscous_tail(yG, d + 1, 0, s));                                // :737-744 -> velocity slots
-  SB_TRY(divergence_into(xG, d + 1, 0, true, yG, d + 1, d, s));         // :746 -> pressure slots
+  if (!trace_divergence) SB_TRY(divergence_into(xG, d + 1, 0, true, yG, d + 1, d, s));  // :746 -> pressure slots
   SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :747-750
   // :756 yG -= force
   {

@@ -57,7 +57,15 @@ struct StokesCtx {
   int pad_pres(const double* src, int sstride, int soff, double* local, cudaStream_t s);
   int crop(int nc, const double* local, double* dst, int dstride, int doff, bool add, const double* sub, cudaStream_t s);
   int viscous_tail(double* dst, int dstride, int doff, cudaStream_t s);
-  int matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s);
+  // div_dst != nullptr: also write  sum_i D_i v_i  (the trace of the velocity gradient this shell computes anyway) into
+  // div_dst[gid*div_stride + div_off] - what a following StokesMatMultPV on the same input would compute a second time
+  int matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s,
+                      double* div_dst = nullptr, int div_stride = 0, int div_off = 0);
+  int crop_trace(double* const* grads, double* dst, int dstride, int doff, cudaStream_t s);
+  // Opt-in (sb200_stokes_set_trace_divergence; off by default until measured on a GPU): StokesMatMult and StokesFunction take
+  // their pressure rows from the trace of the velocity gradient of the viscous block instead of padding the same velocity and
+  // differentiating its components again (stokes.C:509,746 call StokesDivergence on the input the gradient was just taken of).
+  bool trace_divergence = false;
   int divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride, int doff,
                       cudaStream_t s);
   int pressure_reduce_order(double* pL, cudaStream_t s);

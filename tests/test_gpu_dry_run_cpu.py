@@ -21,7 +21,7 @@ def libmock(tmp_path_factory):
 
 
 @pytest.mark.parametrize("module,filters,expect", [
-    ("test_zz1_gpu_saddle", [], 23),
+    ("test_zz1_gpu_saddle", [], 28),
     ("test_zz3_gpu_drivers", ["test_elliptic_config1_and_nonlinear", "test_stokes_continuation_and_vtk"], 2),
 ])
 def test_dry_run(libmock, module, filters, expect):
@@ -39,7 +39,8 @@ def test_bench_extras_dry_run(libmock):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     ops = [row["op"] for row in d["p_sweep"]]
-    assert ops[:6] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)"]
+    assert ops[:8] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesMatMult (trace divergence)",
+                       "StokesFunction (trace divergence)", "StokesPCSetUp0 (device CSR)"]
     cfg = [(row["op"], row["dim"], row["launches"]) for row in d["p_sweep"] if "dim" in row]
     assert [c[:2] for c in cfg] == [("MatMult_Elliptic", "12x12x12x12x12"), ("FormFunction", "12x12x12x12x12"), ("MatMult_Elliptic", "16x16x16"), ("FormFunction", "16x16x16")]
     ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic" and "P" in row]

@@ -119,3 +119,31 @@ def test_outer_fgmres_with_native_saddle_pc_matches_python_pc(cuda):
     K.destroy()
     dev.destroy()
     S.destroy()
+
+
+@pytest.mark.parametrize("dim,rheology", [([16, 16, 16], 1), ([32, 32, 32], 1), ([9, 7, 6], 1), ([8, 6], 0), ([20, 20, 20], 0)], ids=str)
+def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
+    """Opt-in sb200_stokes_set_trace_divergence: the pressure rows of StokesMatMult / StokesFunction taken from the trace of the
+    velocity gradient the viscous part computes, instead of a second StokesDivergence pass on the same input (stokes.C:509,746)."""
+    S = _state(cuda, dim, rheology)
+    d = len(dim)
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal(S.g)).to(cuda)
+    xs = torch.from_numpy(0.3 * rng.standard_normal(S.g)).to(cuda)
+    F0 = S.function(xs).clone()
+    l0 = sp.launch_count()
+    y0 = S.mat_mult(x).clone()
+    n_off = sp.launch_count() - l0
+    S.set_trace_divergence(True)
+    F1 = S.function(xs).clone()
+    l0 = sp.launch_count()
+    y1 = S.mat_mult(x).clone()
+    n_on = sp.launch_count() - l0
+    S.set_trace_divergence(False)
+    for a, b in ((y1, y0), (F1, F0)):
+        assert float((a - b).abs().max()) <= 1e-13 * float(b.abs().max())
+        assert torch.equal(a.reshape(-1, d + 1)[:, :d], b.reshape(-1, d + 1)[:, :d])  # the velocity rows do not change path
+    if n_off:  # (0 over the CPU test double of the dry run)
+        assert n_on < n_off
+    print("trace-divergence %s: launches %d -> %d, pressure rows bitwise equal: %s" % (dim, n_off, n_on, torch.equal(y1, y0) and torch.equal(F1, F0)))
+    S.destroy()

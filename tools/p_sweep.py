@@ -123,6 +123,17 @@ def stokes_rows(steps=10, P=128, dev=None, flush=None):
         ms = timeit(fn, steps, flush)
         t_fp64 = nder * 2.0 * P * m / FP64_TFLOPS / 1e9
         yield {"op": name, "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64, "frac_of_fp64_roofline": t_fp64 / ms}
+    # the opt-in that takes the pressure rows from the trace of the viscous part's velocity gradient (one pad pass and d
+    # derivative passes fewer; sb200_stokes_set_trace_divergence) - measured beside the default so the switch can be decided
+    S.set_trace_divergence(True)
+    for name, fn, ndof, nder in (ops[0], ops[4]):
+        l0 = sp.launch_count()
+        fn()
+        nl = sp.launch_count() - l0
+        ms = timeit(fn, steps, flush)
+        t_fp64 = (nder - 3) * 2.0 * P * m / FP64_TFLOPS / 1e9  # 21 scalar derivatives instead of 24
+        yield {"op": name + " (trace divergence)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64, "frac_of_fp64_roofline": t_fp64 / ms}
+    S.set_trace_divergence(False)
     csr = S.pc_velocity_csr()
     ms_vals = timeit(lambda: S.pc_velocity_csr(pattern=csr[:2]), steps, flush)
     nnz = csr[2].numel()
