@@ -173,6 +173,11 @@ int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d
  * gradient their viscous part computes anyway, instead of running StokesDivergence on the same input a second time
  * (stokes.C:509,746); same values bit for bit, one pad pass and d derivative passes fewer per application. */
 int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on);
+/* Opt-in (default 0): StokesMatMult and StokesFunction subtract the boundary-extrapolated pressure from the diagonal of the viscous
+ * flux (the stress eta*eps - p I), so the divergence of the viscous part also produces the pressure gradient of StokesMatMultVP
+ * (stokes.C:512-513,747-750): d derivative passes and one read-modify-write crop fewer.  Same operator, ~1e-15 relative rounding
+ * difference (the two terms are summed before the derivative instead of after). */
+int sb200_stokes_set_fold_pressure(sb200_stokes* s, int on);
 /* StokesMatMultVP (stokes.C:599-619): pressure gradient with P_N - P_{N-2} extrapolation, gp -> gv. */
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 /* StokesMatGetDiagonalSchur (stokes.C:542-553): y = 1/eta at pressure nodes (gp doubles). */

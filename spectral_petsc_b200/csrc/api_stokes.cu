@@ -146,6 +146,12 @@ int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on) {
   return 0;
 }
 
+int sb200_stokes_set_fold_pressure(sb200_stokes* s, int on) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  s->c->fold_pressure = on != 0;
+  return 0;
+}
+
 int sb200_stokes_matmult_schur(sb200_stokes* s, const double* d_x, double* d_y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream) {
   SB_CHECK(s && d_x && d_y, SB200_ERR_ARG, "null pointer");
   return s->c->matmult_schur(d_x, d_y, solve, solve_ctx, (cudaStream_t)stream);

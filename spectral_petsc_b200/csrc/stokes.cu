@@ -125,8 +125,12 @@ struct VPtrs {
 };
 
 // stokes.C:647-662: symmetrise, z = eps:E0, v = eta*eps + deta*E0*z
-template <int D>
-__global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, const double* __restrict__ deta, VPtrs<D> p) {
+// FOLD (opt-in, StokesCtx::fold_pressure): v_jj -= pl, the boundary-extrapolated local pressure, so that the viscous tail
+// -sum_j D_j V_j also produces the pressure gradient D_i p of StokesMatMultVP (stokes.C:611-614).  FOLD = false compiles to the
+// kernel as it was.
+template <int D, bool FOLD = false>
+__global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, const double* __restrict__ deta, VPtrs<D> p,
+                               const double* __restrict__ pl = nullptr) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
     double g[D][D], st[D][D], S0[D][D];
@@ -146,12 +150,15 @@ __global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, cons
         z = __dadd_rn(z, __dmul_rn(st[j][k], S0[j][k]));
       }
     const double e = eta[i], de = deta[i];
+    const double pli = FOLD ? pl[i] : 0.0;
 #pragma unroll
     for (int j = 0; j < D; j++)
 #pragma unroll
       for (int k = 0; k < D; k++) {
         const double s = __dmul_rn(e, st[j][k]);
-        p.v[j][i * D + k] = __dadd_rn(s, __dmul_rn(__dmul_rn(de, S0[j][k]), z));
+        double val = __dadd_rn(s, __dmul_rn(__dmul_rn(de, S0[j][k]), z));
+        if (FOLD && j == k) val = __dadd_rn(val, -pli);
+        p.v[j][i * D + k] = val;
       }
   }
 }
@@ -183,9 +190,9 @@ __device__ __forceinline__ double atomicMaxD(double* addr, double v) {
 }
 
 // stokes.C:708-725 + rheology (stokes.C:1920-1944): s = sym(grad v), gamma = 1/2 s:s, eta/deta, V = eta*s, strain = s
-template <int D>
+template <int D, bool FOLD = false>
 __global__ void rheology_kernel(long long m, Rheo r, double* __restrict__ eta, double* __restrict__ deta, VPtrs<D> p,
-                                double* __restrict__ minmax) {
+                                double* __restrict__ minmax, const double* __restrict__ pl = nullptr) {
   // p.s[j] (const view) and the written strain are the same arrays: strain is read raw and overwritten
   const long long stride = (long long)gridDim.x * blockDim.x;
   double lmin = DBL_MAX, lmax = -DBL_MAX;
@@ -225,7 +232,9 @@ __global__ void rheology_kernel(long long m, Rheo r, double* __restrict__ eta, d
     for (int j = 0; j < D; j++)
 #pragma unroll
       for (int k = 0; k < D; k++) {
-        p.v[j][i * D + k] = __dmul_rn(e, s[j][k]);
+        double val = __dmul_rn(e, s[j][k]);
+        if (FOLD && j == k) val = __dadd_rn(val, -pl[i]);  // opt-in: V = eta*eps - p I, see vv_flux_kernel
+        p.v[j][i * D + k] = val;
         sw[j][i * D + k] = s[j][k];
       }
   }
@@ -642,7 +651,7 @@ int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) 
 }
 
 int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s,
-                               double* div_dst, int div_stride, int div_off) {
+                               double* div_dst, int div_stride, int div_off, const double* p_local) {
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));                                             // :635-637
@@ -657,11 +666,13 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    vv_flux_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+    if (p_local) vv_flux_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local);
+    else vv_flux_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
   } else {
     VPtrs<3> p;
     for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    vv_flux_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+    if (p_local) vv_flux_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local);
+    else vv_flux_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
   }
   count_launch();
   SB_CUDA(cudaGetLastError());
@@ -773,13 +784,19 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
 int StokesCtx::matmult(const double* xG, double* yG, cudaStream_t s) {
   SB_CHECK(xG && yG && xG != yG, SB200_ERR_ARG, "StokesMatMult: x and y must be distinct non-null vectors");
   const int d = gd.d;
-  if (trace_divergence) {
-    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s, yG, d + 1, d));  // :508-509  vG1 = VV v and pG1 = PV v from one gradient
-  } else {
-    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s));               // :508  vG1 = VV v
-    SB_TRY(divergence_into(xG, d + 1, 0, false, yG, d + 1, d, s));        // :509  pG1 = PV v
+  const double* pfold = nullptr;
+  if (fold_pressure) {  // opt-in: the padded, boundary-extrapolated pressure (:606-609) enters the viscous flux as -p I
+    SB_TRY(pad_pres(xG, d + 1, d, workP[0], s));
+    SB_TRY(pressure_reduce_order(workP[0], s));
+    pfold = workP[0];
   }
-  SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :512-513  vG1 += VP p
+  if (trace_divergence) {
+    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s, yG, d + 1, d, pfold));  // :508-509  vG1 = VV v and pG1 = PV v from one gradient
+  } else {
+    SB_TRY(matmult_vv_into(xG, d + 1, 0, yG, d + 1, 0, s, nullptr, 0, 0, pfold));  // :508  vG1 = VV v
+    SB_TRY(divergence_into(xG, d + 1, 0, false, yG, d + 1, d, s));                 // :509  pG1 = PV v (workP is free again by now)
+  }
+  if (!fold_pressure) SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :512-513  vG1 += VP p
   return 0;
 }
 
@@ -796,23 +813,31 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
   }
   if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));  // :746 from the gradient above (same Dirichlet-padded input)
+  const double* pfold = nullptr;
+  if (fold_pressure) {  // opt-in, as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750)
+    SB_TRY(pad_pres(xG, d + 1, d, workP[0], s));
+    SB_TRY(pressure_reduce_order(workP[0], s));
+    pfold = workP[0];
+  }
   init_minmax_kernel<<<1, 1, 0, s>>>(minmax);
   count_launch();
   Rheo r{rheology, hardness, exponent, regularization, gamma0};
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    rheology_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+    if (pfold) rheology_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold);
+    else rheology_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
   } else {
     VPtrs<3> p;
     for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    rheology_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+    if (pfold) rheology_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold);
+    else rheology_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
   }
   count_launch();
   SB_CUDA(cudaGetLastError());
   SB_TRY(viscous_tail(yG, d + 1, 0, s));                                // :737-744 -> velocity slots
   if (!trace_divergence) SB_TRY(divergence_into(xG, d + 1, 0, true, yG, d + 1, d, s));  // :746 -> pressure slots
-  SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :747-750
+  if (!fold_pressure) SB_TRY(matmult_vp_into(xG, d + 1, d, yG, d + 1, 0, true, nullptr, s));  // :747-750
   // :756 yG -= force
   {
     SB_TRY(axpy_launch(g, -1.0, force, yG, s));

@@ -60,12 +60,17 @@ struct StokesCtx {
   // div_dst != nullptr: also write  sum_i D_i v_i  (the trace of the velocity gradient this shell computes anyway) into
   // div_dst[gid*div_stride + div_off] - what a following StokesMatMultPV on the same input would compute a second time
   int matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s,
-                      double* div_dst = nullptr, int div_stride = 0, int div_off = 0);
+                      double* div_dst = nullptr, int div_stride = 0, int div_off = 0, const double* p_local = nullptr);
   int crop_trace(double* const* grads, double* dst, int dstride, int doff, cudaStream_t s);
   // Opt-in (sb200_stokes_set_trace_divergence; off by default until measured on a GPU): StokesMatMult and StokesFunction take
   // their pressure rows from the trace of the velocity gradient of the viscous block instead of padding the same velocity and
   // differentiating its components again (stokes.C:509,746 call StokesDivergence on the input the gradient was just taken of).
   bool trace_divergence = false;
+  // Opt-in (sb200_stokes_set_fold_pressure; off by default until measured): StokesMatMult and StokesFunction subtract the padded,
+  // boundary-extrapolated pressure from the diagonal of the viscous flux (V = eta*eps - p I, the stress), so the one divergence
+  // of the viscous tail also yields the pressure gradient and StokesMatMultVP's d derivative passes and its add-crop disappear.
+  // Same operator; the sum -D_j V_jj + D_j p is rounded once instead of twice (differences ~1e-15 relative).
+  bool fold_pressure = false;
   int divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride, int doff,
                       cudaStream_t s);
   int pressure_reduce_order(double* pL, cudaStream_t s);

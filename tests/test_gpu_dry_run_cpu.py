@@ -39,8 +39,9 @@ def test_bench_extras_dry_run(libmock):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     ops = [row["op"] for row in d["p_sweep"]]
-    assert ops[:8] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesMatMult (trace divergence)",
-                       "StokesFunction (trace divergence)", "StokesPCSetUp0 (device CSR)"]
+    assert ops[:10] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesMatMult (trace divergence)",
+                        "StokesFunction (trace divergence)", "StokesMatMult (trace divergence + folded pressure)",
+                        "StokesFunction (trace divergence + folded pressure)", "StokesPCSetUp0 (device CSR)"]
     cfg = [(row["op"], row["dim"], row["launches"]) for row in d["p_sweep"] if "dim" in row]
     assert [c[:2] for c in cfg] == [("MatMult_Elliptic", "12x12x12x12x12"), ("FormFunction", "12x12x12x12x12"), ("MatMult_Elliptic", "16x16x16"), ("FormFunction", "16x16x16")]
     ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic" and "P" in row]

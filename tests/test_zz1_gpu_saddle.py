@@ -146,4 +146,22 @@ def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
     if n_off:  # (0 over the CPU test double of the dry run)
         assert n_on < n_off
     print("trace-divergence %s: launches %d -> %d, pressure rows bitwise equal: %s" % (dim, n_off, n_on, torch.equal(y1, y0) and torch.equal(F1, F0)))
+    # opt-in 2, alone and with the first: the pressure gradient out of the viscous divergence (flux = eta*eps - p I); the sum of the
+    # two terms is rounded once instead of twice, so the bar is the parity bar of the operator (1e-12), not bit equality
+    for trace in (False, True):
+        S.set_trace_divergence(trace)
+        S.set_fold_pressure(True)
+        F2 = S.function(xs).clone()
+        l0 = sp.launch_count()
+        y2 = S.mat_mult(x).clone()
+        n_fold = sp.launch_count() - l0
+        S.set_fold_pressure(False)
+        S.set_trace_divergence(False)
+        for a, b in ((y2, y0), (F2, F0)):
+            assert float((a - b).abs().max()) <= 1e-12 * float(b.abs().max())
+        if n_off:
+            assert n_fold < n_off
+        print("fold-pressure (trace %s) %s: launches %d -> %d, max rel diff %.2e" % (trace, dim, n_off, n_fold, float((y2 - y0).abs().max() / y0.abs().max())))
+    # the switches leave no state behind
+    assert torch.equal(S.mat_mult(x), y0) and torch.equal(S.function(xs), F0)
     S.destroy()

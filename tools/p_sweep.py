@@ -133,7 +133,18 @@ def stokes_rows(steps=10, P=128, dev=None, flush=None):
         ms = timeit(fn, steps, flush)
         t_fp64 = (nder - 3) * 2.0 * P * m / FP64_TFLOPS / 1e9  # 21 scalar derivatives instead of 24
         yield {"op": name + " (trace divergence)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64, "frac_of_fp64_roofline": t_fp64 / ms}
+    S.set_fold_pressure(True)  # ... and the pressure gradient out of the same viscous divergence: 18 scalar derivatives
+    for name, fn, ndof, nder in (ops[0], ops[4]):
+        l0 = sp.launch_count()
+        fn()
+        nl = sp.launch_count() - l0
+        ms = timeit(fn, steps, flush)
+        t_fp64 = (nder - 6) * 2.0 * P * m / FP64_TFLOPS / 1e9
+        yield {"op": name + " (trace divergence + folded pressure)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64,
+               "frac_of_fp64_roofline": t_fp64 / ms}
+    S.set_fold_pressure(False)
     S.set_trace_divergence(False)
+    S.function(xs)  # back to the state the default path leaves
     csr = S.pc_velocity_csr()
     ms_vals = timeit(lambda: S.pc_velocity_csr(pattern=csr[:2]), steps, flush)
     nnz = csr[2].numel()
