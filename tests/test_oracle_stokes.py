@@ -91,3 +91,39 @@ def test_vv_is_jacobian_of_viscous_residual():
     S.function(x)
     J = S.mat_mult(dx)
     assert np.abs((Fp - Fm) / (2 * h) - J).max() / np.abs(J).max() < 1e-6
+
+
+@pytest.mark.parametrize("dim", [[9, 7, 6], [12, 10]], ids=str)
+def test_folded_form_of_the_block_operator(dim):
+    """The identity behind the CUDA path's two opt-ins (sb200_stokes_set_trace_divergence / _set_fold_pressure): with the gradient
+    G_j = D_j w of the padded velocity, PV v = trace(G) and VV v + VP p = -sum_j D_j (V_j - p_ext e_j), p_ext the padded and
+    boundary-extrapolated pressure - i.e. StokesMatMult from ONE gradient and ONE divergence (18 scalar derivatives, not 24)."""
+    O = StokesCtx(dim, rheology=1, exponent=2.0, regularization=0.5, exact=2)
+    U, _ = O.create_exact_solution()
+    O.function(U)
+    d = O.d
+    x = np.random.default_rng(0).standard_normal(O.g)
+    y0 = O.mat_mult(x)
+    v, p = O.split(x)
+    xL = O.vel_local(v, False)
+    G = [O.dvel(i, xL) for i in range(d)]
+    div = np.zeros(O.m)
+    for i in range(d):
+        div = div + G[i][:, i]
+    st = [[0.5 * (G[j][:, k] + G[k][:, j]) for k in range(d)] for j in range(d)]
+    z = np.zeros(O.m)
+    for j in range(d):
+        for k in range(d):
+            z = z + st[j][k] * O.strain[j][:, k]
+    pL = np.zeros(O.m)
+    pL[O.int_nodes] = p
+    O.pressure_reduce_order(pL)
+    yL = np.zeros((O.m, d))
+    for j in range(d):
+        Vj = np.empty((O.m, d))
+        for k in range(d):
+            Vj[:, k] = O.eta * st[j][k] + O.deta * O.strain[j][:, k] * z - (pL if j == k else 0.0)
+        yL = yL + (-1.0) * O.dvel(j, Vj)
+    y1 = O.merge(yL[O.int_nodes].reshape(-1), div[O.int_nodes])
+    assert np.array_equal(O.split(y1)[1], O.split(y0)[1])          # the divergence rows: the same numbers, bit for bit
+    assert np.abs(y1 - y0).max() <= 1e-14 * np.abs(y0).max()       # the velocity rows: one rounding of the sum instead of two
