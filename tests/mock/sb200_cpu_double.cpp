@@ -798,6 +798,37 @@ int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, in
   return 0;
 }
 int sb200_elliptic_set_path(sb200_elliptic*, int path) { return path >= 0 && path <= 3 ? 0 : SB200_ERR_USER; }  // one CPU path here
+// the remaining single-rank entry points of the Python harness (dry runs of the GPU test modules)
+int sb200_device_count(int* n) { *n = 1; return 0; }
+int sb200_set_device(int) { return 0; }
+int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y) { return sb200_cheb_apply(c, h_x, h_y, nullptr); }
+int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F) { return sb200_elliptic_function(e, h_U, h_F, nullptr); }
+int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y) { return sb200_stokes_matmult(s, h_x, h_y, nullptr); }
+int sb200_stokes_function_host(sb200_stokes* s, const double* h_x, double* h_y) { return sb200_stokes_function(s, h_x, h_y, nullptr); }
+int sb200_elliptic_create_slab(int d, const int* dim, int rank, int nranks, sb200_elliptic** out) {
+  if (rank != 0 || nranks != 1) FAIL(SB200_ERR_SUP, "test double: single rank only");
+  return sb200_elliptic_create(d, dim, out);
+}
+int sb200_stokes_create_slab(int d, const int* dim, int rank, int nranks, sb200_stokes** out) {
+  if (rank != 0 || nranks != 1) FAIL(SB200_ERR_SUP, "test double: single rank only");
+  return sb200_stokes_create(d, dim, out);
+}
+int sb200_elliptic_get_state(sb200_elliptic* e, int which, double* out, void*) {  // 0 eta, 1 deta, 2+j gradu[j]
+  if (which < 0 || which > 1 + e->d) FAIL(SB200_ERR_USER, "get_state: which out of range");
+  const std::vector<double>& a = which == 0 ? e->eta : (which == 1 ? e->deta : e->gradu[which - 2]);
+  std::copy(a.begin(), a.end(), out);
+  return 0;
+}
+int sb200_elliptic_pad(sb200_elliptic* e, const double* U, int with_dirichlet, double* local, void*) {
+  std::fill(local, local + e->m, 0.0);
+  for (long long q = 0; q < e->g; q++) local[e->ixG[q]] = U[q];
+  for (size_t q = 0; q < e->ixD.size(); q++) local[e->ixD[q]] = with_dirichlet ? e->dirichlet[q] : 0.0;
+  return 0;
+}
+int sb200_elliptic_crop(sb200_elliptic* e, const double* local, double* U, void*) {
+  for (long long q = 0; q < e->g; q++) U[q] = local[e->ixG[q]];
+  return 0;
+}
 // host-buffer forms: "device" memory is host memory here, so they are the operator itself; the queue completes at submit
 static int g_pending = 0;
 int sb200_elliptic_matmult_host(sb200_elliptic* e, const double* h_U, double* h_V) { return sb200_elliptic_matmult(e, h_U, h_V, nullptr); }
