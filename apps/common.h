@@ -94,10 +94,15 @@ struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
   int levels = 0;
   sb200_host_ilu* ilu = nullptr;
   std::vector<int> rowptr, colidx;
-  std::vector<double> vals, dinv, hx, hy;
+  std::vector<double> vals, diag, hx, hy;
+  double* d_diag = nullptr;  // jacobi: the diagonal of P on the device, so that applying it needs no host round trip
   int n = 0;
-  ~HostPc() {
+  ~HostPc() { release(); }
+  void release() {  // call before main returns (device memory)
     if (ilu) sb200_host_ilu_destroy(ilu);
+    if (d_diag) sb200_free(d_diag);
+    ilu = nullptr;
+    d_diag = nullptr;
   }
   static bool known(const std::string& t) { return t == "ilu" || t == "jacobi" || t == "none"; }
   // PCSetUp: bring the values of P down (pattern once) and (re)factor
@@ -122,10 +127,13 @@ struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
       if (first) CHK(sb200_host_ilu_create(rows, rowptr.data(), colidx.data(), vals.data(), levels, &ilu));
       else CHK(sb200_host_ilu_refactor(ilu, vals.data()));
     } else if (type == "jacobi") {
-      dinv.assign(rows, 1.0);
+      diag.assign(rows, 1.0);
       for (int i = 0; i < rows; i++)
         for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
-          if (colidx[p] == i) dinv[i] = 1.0 / vals[p];
+          if (colidx[p] == i) diag[i] = vals[p];
+      if (!d_diag) CHK(sb200_malloc((void**)&d_diag, (size_t)rows * sizeof(double)));
+      CHK(sb200_memcpy_h2d(d_diag, diag.data(), (size_t)rows * sizeof(double), nullptr));
+      CHK(sb200_stream_sync(nullptr));
     }
     return 0;
   }
@@ -136,14 +144,16 @@ struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
       return 0;
     }
     if (type == "jacobi") {
-      for (int i = 0; i < n; i++) z[i] = dinv[i] * r[i];
+      for (int i = 0; i < n; i++) z[i] = r[i] / diag[i];  // the same division the device form performs
       return 0;
     }
     return sb200_host_ilu_solve(ilu, r, z);
   }
-  // the same on device arrays: down, apply, up
+  // the same on device arrays: jacobi and none stay on the device (VecPointwiseDivide / copy); ilu goes down, applies, comes up
   int apply_device(const double* d_x, double* d_y, void* stream) {
     const size_t bytes = (size_t)n * sizeof(double);
+    if (type == "jacobi") return sb200_vec_pointwise_divide(n, d_x, d_diag, d_y, stream);
+    if (type == "none") return sb200_memcpy_d2d(d_y, d_x, bytes, stream);
     int rc = sb200_memcpy_d2h(hx.data(), d_x, bytes, stream);
     if (!rc) rc = sb200_stream_sync(stream);
     if (!rc) rc = apply_host(hx.data(), hy.data());

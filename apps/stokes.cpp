@@ -13,7 +13,9 @@
 //     orchestration in this file; their small vector updates run on host copies (the velocity PC below moves every vector
 //     through the host anyway);
 //   * the PC on MatVVPC is PETSc's own (ILU(0) by default, hypre in README:44) and out of scope: the HOST stand-in of
-//     apps/common.h applies it (-vel_pc_type / -svel_pc_type ilu | jacobi | none, -vel_pc_factor_levels k).
+//     apps/common.h applies it (-vel_pc_type / -svel_pc_type ilu | jacobi | none, -vel_pc_factor_levels k).  jacobi and none are
+//     applied on the device (the diagonal of MatVVPC uploaded once per set-up), so with them no vector of a linear solve ever
+//     crosses PCIe: outer FGMRES, StokesPCApply, the three inner Krylov solves and the PC all work on device vectors.
 // The Python command line (python -m spectral_petsc_b200.stokes) runs the identical flow; tests compare the two.
 #include <functional>
 #include <memory>

@@ -91,6 +91,7 @@ STOKES_CASES = [
     "-exact 2 -cont0 1 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 1 -vel_pc_factor_levels 2 -svel_pc_factor_levels 2",
     "-exact 2 -cont0 1 " + BASE + " -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 2 -svel_pc_type jacobi",
     "-exact 2 -cont0 1 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -dim 8,8,8 -ksp_rtol 1e-8 -ksp_max_it 200 -pc_saddle_type 3 -vel_pc_factor_levels 1",  # svel: GMRES, not preonly
+    "-exact 2 -cont0 1 " + BASE + " -dim 10,10,10 -ksp_rtol 1e-11 -ksp_max_it 400 -vel_pc_type jacobi -svel_pc_type jacobi",  # no host round trip anywhere in the linear solve
 ]
 
 
