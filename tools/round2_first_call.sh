@@ -27,4 +27,10 @@ timeout 300 python tools/saddle_once.py > $O/r02_plain_saddle.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'eo_deriv|vv_flux|pad_nodes|crop|reduce_order' -c 16 -o $O/r02_prof_stokes python tools/stokes_once.py > $O/r02_ncu_full_stokes.log 2>&1
 # 5. the device assembly of the preconditioning matrices at 128^3 (not timed in round 1)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fd_assemble' -c 4 -o $O/r02_prof_fd python tools/p_sweep.py 1 > $O/r02_ncu_full_fd.log 2>&1
+# 6. a Stokes linear solve at 128^3 with nothing leaving the device (Jacobi on MatVVPC applied on the device): wall time of the
+#    native executable, outer iteration count; 20^3 with the host ILU(2) stand-in beside it
+( time timeout 900 apps/stokes -exact 2 -cont0 1 -dim 128,128,128 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_rtol 1e-6 -ksp_max_it 60 \
+    -vel_pc_type jacobi -svel_pc_type jacobi -ksp_monitor ) > $O/r02_stokes128_device_jacobi.log 2>&1
+( time timeout 300 apps/stokes -exact 2 -cont0 1 -dim 20,20,20 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_rtol 1e-10 -ksp_max_it 400 \
+    -vel_pc_factor_levels 2 -svel_pc_factor_levels 2 -ksp_monitor ) > $O/r02_stokes20_ilu2.log 2>&1
 tail -3 $O/r02_steps.log
