@@ -149,3 +149,22 @@ def test_native_stokes_exact3_two_dimensional_shear(stokes_exe):
     out, steps = native_stokes(stokes_exe, "-exact 3 -dim 10,8 -cont0 1 " + BASE + " -ksp_rtol 1e-10 -ksp_max_it 200")
     assert "DOF distribution: 144 global   48/80 pressure    96/160 velocity    64 dirichlet    0 mixed" in out
     assert len(steps) == 1 and steps[0]["snes_its"] == 1 and steps[0]["reason"] == "CONVERGED_FNORM_RELATIVE" and steps[0]["error"] < 1e-7
+
+
+@pytest.mark.parametrize("cos_scale", ["3", "2.8"])
+def test_tests_sh_convergence_sweep(exe, cos_scale):
+    """The reference's own test script (tests.sh): ./elliptic -dim n,n -exact 0 -cos_scale c -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12 for
+    a range of n, reading 'Norm of error'.  The nonlinear problem converges spectrally: the error falls from O(1e-2) at n = 16 to
+    rounding level at n = 36..44; the native flow reproduces the Python flow over the oracle."""
+    def err(n):
+        r = subprocess.run([exe] + ("-dim %d,%d -exact 0 -cos_scale %s -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12" % (n, n, cos_scale)).split(),
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr + r.stdout
+        return float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+
+    e = {n: err(n) for n in (16, 20, 28, 36, 44)}
+    assert 1e-3 < e[16] < 1e-1 and e[20] < e[16] / 10 and e[28] < 1e-6 and e[36] < 1e-11 and e[44] < 1e-12
+    lines = []
+    ro = drivers.elliptic_main(("-dim 20,20 -exact 0 -cos_scale %s -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12" % cos_scale).split(), out=lines.append,
+                               make_problem=OracleElliptic)
+    assert abs(e[20] - ro["error_abs"]) <= 1e-6 * ro["error_abs"] + 1e-12

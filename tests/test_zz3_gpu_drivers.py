@@ -168,3 +168,15 @@ def test_native_stokes_executable(cuda, tmp_path):
     assert float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1]) < 1e-6
     kits = [int(t) for t in [l for l in r.stdout.split("\n") if l.startswith("KSP iterations per Newton step:")][0].split(":")[1].split()]
     assert len(kits) == 1 and abs(kits[0] - 26) <= 2
+
+
+def test_native_elliptic_tests_sh_sweep(cuda):
+    """The reference's tests.sh on the GPU executable: spectral convergence of the nonlinear 2-D problem (errors measured over the CPU
+    double: 5.0e-2 / 1.3e-3 / 6.1e-8 / 2.6e-13 at n = 16 / 20 / 28 / 36 for -cos_scale 3)."""
+    exe = os.path.join(ROOT, "apps", "elliptic")
+    errs = {}
+    for n in (16, 20, 28, 36):
+        r = subprocess.run([exe] + ("-dim %d,%d -exact 0 -cos_scale 3 -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12" % (n, n)).split(), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr + r.stdout
+        errs[n] = float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
+    assert abs(errs[16] - 4.9979e-2) < 1e-4 and abs(errs[20] - 1.29596e-3) < 1e-6 and abs(errs[28] - 6.084e-8) < 2e-9 and errs[36] < 1e-11
