@@ -16,8 +16,9 @@ DRIVER    := tests/cpp/ref_api_driver
 DRIVER2   := tests/cpp/ref_api_driver2
 APP_ELL   := apps/elliptic
 APP_STK   := apps/stokes
+APP_CHEB  := apps/cheb
 
-all: $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK)
+all: $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK) $(APP_CHEB)
 
 $(DRIVER): tests/cpp/ref_api_driver.cpp $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../../spectral_petsc_b200'
@@ -29,6 +30,9 @@ $(APP_ELL): apps/elliptic.cpp apps/common.h $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
 
 $(APP_STK): apps/stokes.cpp apps/common.h $(LIB) $(HDRS)
+	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
+
+$(APP_CHEB): apps/cheb.cpp apps/common.h $(LIB) $(HDRS)
 	g++ -O2 -std=c++17 -o $@ $< -Lspectral_petsc_b200 -lspectral_b200 -Wl,-rpath,'$$ORIGIN/../spectral_petsc_b200'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
@@ -47,6 +51,6 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK)
+	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK) $(APP_CHEB)
 
 .PHONY: all clean

@@ -278,6 +278,7 @@ int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb20
   long long s = 1;
   for (int r = 0; r < rank; r++) s *= dims[r];
   if (s != n_total) FAIL(SB200_ERR_USER, "dimensions do not agree");
+  if (dims[tr] < 2) FAIL(SB200_ERR_USER, "transformed extent must be >= 2");
   sb200_cheb* c = new sb200_cheb();
   c->P = dims[tr];
   c->N = n_total;

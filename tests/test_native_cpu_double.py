@@ -168,3 +168,31 @@ def test_tests_sh_convergence_sweep(exe, cos_scale):
     ro = drivers.elliptic_main(("-dim 20,20 -exact 0 -cos_scale %s -gamma 4 -ksp_rtol 1e-12 -snes_rtol 1e-12" % cos_scale).split(), out=lines.append,
                                make_problem=OracleElliptic)
     assert abs(e[20] - ro["error_abs"]) <= 1e-6 * ro["error_abs"] + 1e-12
+
+
+# ---- apps/cheb.cpp: the reference's cheb.c ---------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cheb_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("native") / "cheb_cpu_double")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out, os.path.join(ROOT, "apps", "cheb.cpp")] + [os.path.join(ROOT, s) for s in HOST])
+    return out
+
+
+def cheb_norms(exe, args):
+    r = subprocess.run([exe] + args.split(), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr + r.stdout
+    return [float(l.split()[-1]) for l in r.stdout.split("\n") if l.startswith("Norm of error")]
+
+
+def test_native_cheb_known_answers(cheb_exe):
+    """cheb.c's two printed norms: 1.029e-02 at the default m1 = 5 with spectral decay, and 6.245e-06 / 8.72e-05 /
+    1.04e-03 for the derivative of exp(x) + exp(y) + exp(z) along axes 0 / 1 / 2 of the (8, 7, 6) grid."""
+    assert cheb_norms(cheb_exe, "") == pytest.approx([1.029e-02, 6.245e-06], rel=1e-3)  # defaults: m1 5, (8, 7, 1), axis 0
+    assert cheb_norms(cheb_exe, "-m1 8")[0] == pytest.approx(6.2e-06, rel=2e-2) and cheb_norms(cheb_exe, "-m1 16")[0] < 1e-13
+    for axis, want in ((0, 6.245e-06), (1, 8.72e-05), (2, 1.04e-03)):
+        assert cheb_norms(cheb_exe, "-m 8 -n 7 -p 6 -d %d" % axis)[1] == pytest.approx(want, rel=2e-3)
+    assert cheb_norms(cheb_exe, "-m 24 -n 20 -p 18 -d 2")[1] < 1e-12
+    r = subprocess.run([cheb_exe, "-d", "2"], capture_output=True, text=True, timeout=60)  # p = 1 by default: nothing to differentiate along axis 2
+    assert r.returncode == 83 and "must be >= 2" in r.stderr
+    r = subprocess.run([cheb_exe, "-d", "3"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 83 and "tdim out of range" in r.stderr  # chebyshev.c:106

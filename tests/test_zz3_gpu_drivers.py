@@ -180,3 +180,21 @@ def test_native_elliptic_tests_sh_sweep(cuda):
         assert r.returncode == 0, r.stderr + r.stdout
         errs[n] = float([l for l in r.stdout.split("\n") if l.startswith("Norm of error")][0].split("abs =")[1].split()[0])
     assert abs(errs[16] - 4.9979e-2) < 1e-4 and abs(errs[20] - 1.29596e-3) < 1e-6 and abs(errs[28] - 6.084e-8) < 2e-9 and errs[36] < 1e-11
+
+
+def test_native_cheb_executable(cuda):
+    """apps/cheb: the reference's cheb.c (K1 / K2 of SURVEY 8c) on the GPU through MatCreateChebD1 / MatCreateCheb."""
+    exe = os.path.join(ROOT, "apps", "cheb")
+    assert os.path.exists(exe), "run `make` (or __graft_entry__.build()) first"
+
+    def norms(args):
+        r = subprocess.run([exe] + args.split(), capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr + r.stdout
+        return [float(l.split()[-1]) for l in r.stdout.split("\n") if l.startswith("Norm of error")]
+
+    a = norms("")
+    assert abs(a[0] - 1.029e-02) < 1e-5 and abs(a[1] - 6.245e-06) < 1e-8
+    for axis, want in ((0, 6.245e-06), (1, 8.72e-05), (2, 1.04e-03)):
+        assert abs(norms("-m 8 -n 7 -p 6 -d %d" % axis)[1] / want - 1.0) < 2e-3
+    assert norms("-m1 16")[0] < 1e-13 and norms("-m 128 -n 128 -p 128 -d 0")[1] < 1e-10
+    assert subprocess.run([exe, "-d", "3"], capture_output=True, text=True, timeout=60).returncode == 83
