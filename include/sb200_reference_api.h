@@ -60,6 +60,19 @@ PetscErrorCode StokesMatMultVV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultPV(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatMultVP(Mat A, Vec xG, Vec yG);
 PetscErrorCode StokesMatGetDiagonalSchur(Mat S, Vec y);
+/* StokesExact0..3 (stokes.C:1948-2034): value = [u_0..u_{d-1}, p], rhs = forcing at the point coord (either may be NULL);
+ * StokesDirichlet (stokes.C:2039-2050) evaluates ctx->exact and reports a Dirichlet condition.  Host functions. */
+typedef enum { DIRICHLET, NEUMANN, MIXED, OUTFLOW } StokesBdyType; /* stokes.C:14 `BdyType`; elliptic.C's enum of that name is above */
+typedef PetscErrorCode (*StokesExactFunc)(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void* ctx);
+typedef struct {
+  StokesExactFunc exact;
+  void* exactCtx;
+} StokesExactBoundaryCtx;
+PetscErrorCode StokesExact0(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void* ctx);
+PetscErrorCode StokesExact1(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void* ctx);
+PetscErrorCode StokesExact2(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void* ctx);
+PetscErrorCode StokesExact3(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void* ctx);
+PetscErrorCode StokesDirichlet(PetscInt d, PetscReal* coord, PetscReal* normal, StokesBdyType* type, PetscReal* value, void* ctx);
 /* StokesDivergence(ctx, withDirichlet, xG, yG) (stokes.C:570-595) */
 PetscErrorCode StokesDivergence(StokesCtxB200* ctx, PetscTruth withDirichlet, Vec xG, Vec yG);
 /* The rheologies as the host callbacks StokesOptions stores (stokes.C:1920-1944); ctx = the StokesOptionsB200 holding hardness,

@@ -159,6 +159,8 @@ int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream)
  * U2 (g doubles each, AoS [v, p]) and the Dirichlet velocities StokesDirichlet gives the boundary nodes (dv doubles, :2039-2050);
  * any output may be NULL.  -exact 3 is 2-D only (:2022).  Needs no device. */
 int sb200_stokes_exact_solution(int d, const int* dim, int exact, double* h_u, double* h_u2, double* h_dirichlet);
+/* one node of StokesExact{exact} (stokes.C:1948-2034): value = [u_0..u_{d-1}, p] and the forcing rhs at the point coord (host) */
+int sb200_stokes_exact_eval(int exact, int d, const double* coord, double* value, double* rhs);
 /* StokesMatMult(A, x, y) (stokes.C:499-519): x, y of g doubles, AoS [v_0..v_{d-1}, p] per interior node. */
 int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 int sb200_stokes_matmult_host(sb200_stokes* s, const double* h_x, double* h_y);

@@ -114,6 +114,45 @@ int sb200_elliptic_exact_solution(int d, const int* dim, int exact, double cos_s
   return 0;
 }
 
+// One node of StokesExact0..3 (stokes.C:1948-2034): value = [u_0..u_{d-1}, p], rhs = the forcing, d + 1 numbers each (either
+// may be NULL).  -exact 2 in three dimensions leaves value[3] unset in the reference (stokes.C:2004-2005); it is 0 here.
+int sb200_stokes_exact_eval(int exact, int d, const double* c, double* value, double* rhs_out) {
+  if (d < 2 || d > 3 || !c) {
+    sb200::set_last_error("the Stokes problem needs 2 or 3 dimensions");
+    return SB200_ERR_USER;
+  }
+  if (exact < 0 || exact > 3) {
+    sb200::set_last_error("Exact solution not implemented");  // stokes.C:452
+    return SB200_ERR_SUP;
+  }
+  if (exact == 3 && d != 2) {
+    sb200::set_last_error("StokesExact3 only implemented for dimension 2");  // stokes.C:2022
+    return SB200_ERR_USER;
+  }
+  double val[4] = {0, 0, 0, 0}, rhs[4] = {0, 0, 0, 0};
+  if (exact == 1 || exact == 2) {  // StokesExact1 / 2 (stokes.C:1963-2012)
+    const double eta = 1.0;
+    const double u = sin(0.5 * kPi * c[0]) * cos(0.5 * kPi * c[1]);
+    const double v = -cos(0.5 * kPi * c[0]) * sin(0.5 * kPi * c[1]);
+    val[0] = u;
+    val[1] = v;
+    rhs[0] = (0.5 * kPi) * (0.5 * kPi) * eta * u;
+    rhs[1] = (0.5 * kPi) * (0.5 * kPi) * eta * v;
+    if (exact == 1) {
+      val[d] = 0.25 * (cos(kPi * c[0]) + cos(kPi * c[1])) + 10 * (c[0] + c[1]);
+      rhs[0] += -0.25 * kPi * sin(kPi * c[0]) + 10;
+      rhs[1] += -0.25 * kPi * sin(kPi * c[1]) + 10;
+    }
+  } else if (exact == 3) {  // StokesExact3 (stokes.C:2016-2034): shear flow u = y + 1
+    val[0] = c[1] + 1.0;
+  }
+  for (int k = 0; k <= d; k++) {
+    if (value) value[k] = val[k];
+    if (rhs_out) rhs_out[k] = rhs[k];
+  }
+  return 0;
+}
+
 int sb200_stokes_exact_solution(int d, const int* dim, int exact, double* h_u, double* h_u2, double* h_dirichlet) {
   if (int rc = check_grid(d, dim, 3)) return rc;
   if (d < 2) {
@@ -130,23 +169,8 @@ int sb200_stokes_exact_solution(int d, const int* dim, int exact, double* h_u, d
   }
   long long gi = 0, di = 0;
   walk(d, dim, [&](const double* c, bool bdy) {
-    double val[4] = {0, 0, 0, 0}, rhs[4] = {0, 0, 0, 0};
-    if (exact == 1 || exact == 2) {  // StokesExact1 / 2 (stokes.C:1963-2012); -exact 2 in 3-D: pressure defined as 0
-      const double eta = 1.0;
-      const double u = sin(0.5 * kPi * c[0]) * cos(0.5 * kPi * c[1]);
-      const double v = -cos(0.5 * kPi * c[0]) * sin(0.5 * kPi * c[1]);
-      val[0] = u;
-      val[1] = v;
-      rhs[0] = (0.5 * kPi) * (0.5 * kPi) * eta * u;
-      rhs[1] = (0.5 * kPi) * (0.5 * kPi) * eta * v;
-      if (exact == 1) {
-        val[d] = 0.25 * (cos(kPi * c[0]) + cos(kPi * c[1])) + 10 * (c[0] + c[1]);
-        rhs[0] += -0.25 * kPi * sin(kPi * c[0]) + 10;
-        rhs[1] += -0.25 * kPi * sin(kPi * c[1]) + 10;
-      }
-    } else if (exact == 3) {  // StokesExact3 (stokes.C:2016-2034): shear flow u = y + 1
-      val[0] = c[1] + 1.0;
-    }
+    double val[4], rhs[4];
+    sb200_stokes_exact_eval(exact, d, c, val, rhs);  // arguments validated above
     if (bdy) {  // StokesDirichlet evaluates the exact solution (stokes.C:2039-2050); d velocity dofs per boundary node (:796-801)
       if (h_dirichlet)
         for (int k = 0; k < d; k++) h_dirichlet[di * d + k] = val[k];

@@ -302,6 +302,21 @@ PetscErrorCode StokesDivergence(StokesCtxB200* c, PetscTruth withDirichlet, Vec 
   return sb200_stokes_divergence(c->s, withDirichlet ? 1 : 0, x, y, nullptr);
 }
 
+// StokesExact0..3 (stokes.C:1948-2034) and StokesDirichlet (stokes.C:2039-2050): the manufactured solutions as the per-point host
+// callbacks StokesOptions stores; StokesCreateExactSolution evaluates the same expressions at every node.
+PetscErrorCode StokesExact0(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void*) { return sb200_stokes_exact_eval(0, d, coord, value, rhs); }
+PetscErrorCode StokesExact1(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void*) { return sb200_stokes_exact_eval(1, d, coord, value, rhs); }
+PetscErrorCode StokesExact2(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void*) { return sb200_stokes_exact_eval(2, d, coord, value, rhs); }
+PetscErrorCode StokesExact3(PetscInt d, PetscReal* coord, PetscReal* value, PetscReal* rhs, void*) { return sb200_stokes_exact_eval(3, d, coord, value, rhs); }
+PetscErrorCode StokesDirichlet(PetscInt d, PetscReal* coord, PetscReal*, StokesBdyType* type, PetscReal* value, void* void_ctx) {
+  StokesExactBoundaryCtx* ctx = (StokesExactBoundaryCtx*)void_ctx;
+  *type = DIRICHLET;
+  PetscReal full[4];  // the exact solution has d + 1 values; the boundary condition wants what the reference's callee writes
+  PetscErrorCode rc = ctx->exact(d, coord, full, PETSC_NULL, ctx->exactCtx);
+  for (PetscInt k = 0; !rc && k <= d; k++) value[k] = full[k];
+  return rc;
+}
+
 PetscErrorCode StokesRheologyLinear(PetscInt, PetscReal, PetscReal* eta, PetscReal* deta, void*) {  // stokes.C:1920-1926
   *eta = 1.0;
   *deta = 0.0;

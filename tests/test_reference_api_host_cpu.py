@@ -94,3 +94,41 @@ def test_stokes_jacobian_reports_different_nonzero_pattern():
     m = re.search(r"DIFFERENT_NONZERO_PATTERN\s*=\s*(\d+)", txt)
     assert m is None or flag.value == int(m.group(1))
     assert flag.value != -1
+
+
+class StokesExactBoundaryCtx(ctypes.Structure):
+    _fields_ = [("exact", ctypes.c_void_p), ("exactCtx", ctypes.c_void_p)]
+
+
+@pytest.mark.parametrize("exact,d", [(0, 2), (0, 3), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2)])
+def test_stokes_exact_point_functions(exact, d):
+    """StokesExact0..3 / StokesDirichlet (stokes.C:1948-2050) as per-point host callbacks: the numbers StokesCreateExactSolution puts
+    into the vectors (sb200_stokes_exact_solution, compared with the oracle in tests/test_exact_solutions_cpu.py)."""
+    L = sp.lib()
+    dim = [6, 5, 4][:d]
+    U, U2, dirichlet = sp.stokes_exact_solution(dim, exact)
+    fn = getattr(L, "StokesExact%d" % exact)
+    fn.argtypes = [ctypes.c_int, PD, PD, PD, ctypes.c_void_p]
+    nodes = np.stack(np.meshgrid(*[np.cos(np.arange(p) * np.pi / (p - 1)) for p in dim], indexing="ij"), axis=-1).reshape(-1, d)
+    bdy = np.zeros(len(nodes), dtype=bool)
+    for j, p in enumerate(dim):
+        idx = np.indices(dim)[j].reshape(-1)
+        bdy |= (idx == 0) | (idx == p - 1)
+    val, rhs, bval = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_double * 4)()
+    bctx = StokesExactBoundaryCtx(ctypes.cast(fn, ctypes.c_void_p), None)
+    L.StokesDirichlet.argtypes = [ctypes.c_int, PD, PD, ctypes.POINTER(ctypes.c_int), PD, ctypes.c_void_p]
+    gi = di = 0
+    for c, b in zip(nodes, bdy):
+        cc = (ctypes.c_double * 3)(*c)
+        assert fn(d, cc, val, rhs, None) == 0
+        if b:
+            kind = ctypes.c_int(-1)
+            assert L.StokesDirichlet(d, cc, None, ctypes.byref(kind), bval, ctypes.addressof(bctx)) == 0 and kind.value == 0  # DIRICHLET
+            assert list(bval[:d]) == list(dirichlet.reshape(-1, d)[di])
+            di += 1
+        else:
+            assert list(val[:d + 1]) == list(U.reshape(-1, d + 1)[gi]) and list(rhs[:d + 1]) == list(U2.reshape(-1, d + 1)[gi])
+            gi += 1
+    assert gi * (d + 1) == U.size and di * d == dirichlet.size
+    if exact == 3:
+        assert L.StokesExact3(3, (ctypes.c_double * 3)(0.1, 0.2, 0.3), val, rhs, None) != 0  # "only implemented for dimension 2" (stokes.C:2021)
