@@ -16,6 +16,15 @@ import spectral_petsc_b200 as sp  # noqa: E402
 from spectral_petsc_b200 import dist as spd  # noqa: E402
 
 
+def apply_switches(S):
+    """SB200_STOKES_OPTS=trace,fold turns on the two evaluation switches (sb200_stokes_set_trace_divergence / _set_fold_pressure):
+    in slab mode they also remove 2 of the 8 axis-0 derivative exchanges of a StokesMatMult."""
+    opts = os.environ.get("SB200_STOKES_OPTS", "").split(",")
+    S.set_trace_divergence("trace" in opts)
+    S.set_fold_pressure("fold" in opts)
+    return [o for o in opts if o in ("trace", "fold")]
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -33,6 +42,7 @@ def main():
         O.create_exact_solution()
         S = sp.Stokes(dim, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-2, gamma0=1.0, rank=rank, nranks=world)
         spd.attach_peers(S)
+        apply_switches(S)
         S.set_dirichlet(torch.from_numpy(spd.split_dirichlet(O.dirichlet.reshape(-1), dim, world, ncomp=3)[rank].copy()).to(dev))
         S.set_force(torch.from_numpy(spd.split_global(O.force, dim, world, ncomp=4)[rank].copy()).to(dev))
         xs = 0.3 * np.random.default_rng(1).standard_normal(O.g)
@@ -53,6 +63,7 @@ def main():
         S = sp.Stokes(dim, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0, rank=rank, nranks=world)
         if world > 1:
             spd.attach_peers(S)
+        switches = apply_switches(S)
         S.set_dirichlet(torch.zeros(S.dv, dtype=torch.float64, device=dev))
         S.set_force(torch.zeros(S.g, dtype=torch.float64, device=dev))
         gen = torch.Generator(device=dev).manual_seed(rank)
@@ -81,7 +92,7 @@ def main():
             res[name] = t.item()
         if rank == 0:
             m = Pt ** 3
-            print(json.dumps({"bench": "stokes_slab", "P": Pt, "ranks": world, "ms": res,
+            print(json.dumps({"bench": "stokes_slab", "P": Pt, "ranks": world, "switches": switches, "ms": res,
                               "gdof_s": {k: 4 * m / v / 1e6 for k, v in res.items()}}), flush=True)
         S.destroy()
     dist.barrier()
