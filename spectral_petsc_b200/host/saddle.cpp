@@ -34,6 +34,7 @@ struct sb200_saddle {
   sb200_ksp* kvel = nullptr;    // KSPVelocity      (stokes.C:334-337)
   sb200_ksp* kschur = nullptr;  // KSPSchur         (stokes.C:328-333)
   sb200_ksp* ksvel = nullptr;   // KSPSchurVelocity (stokes.C:338-341), unless preonly
+  int r_vel = 0, r_schur = 0, r_svel = 0;  // Krylov space each solver was created with
   long long its_vel = 0, its_schur = 0;
   // device work vectors by role (enums below), the Jacobi "diagonal", one reduction scratch
   double* v[8] = {};
@@ -63,6 +64,18 @@ int op_schur_velocity(void* ctx, const double* x, double* y, void* stream) {  //
   sb200_saddle* P = (sb200_saddle*)ctx;
   CHK(sb200_stokes_matmult_vv(P->s, x, P->v[SV1], stream));
   return pc_or_copy(P->svel_pc, P->svel_ctx, P->gv, P->v[SV1], y, stream);
+}
+
+// GMRES(30) that may take at most maxits < 30 iterations never restarts, so it only needs maxits + 1 basis vectors: the solver is
+// (re)created with restart = min(30, maxits) - identical iterates, a sixth of the memory for the usual -vel_ksp_max_it 4.
+int ensure_ksp(sb200_ksp** k, int* have, long long n, int maxits) {
+  const int want = maxits < 1 ? 1 : (maxits < 30 ? maxits : 30);
+  if (*k && *have == want) return 0;
+  if (*k) sb200_ksp_destroy(*k);
+  *k = nullptr;
+  CHK(sb200_ksp_create(n, want, k));
+  *have = want;
+  return 0;
 }
 
 // left-preconditioned GMRES: x = KSPSolve(b), Minv(b) staged in pb
@@ -144,8 +157,6 @@ int sb200_saddle_create(sb200_stokes* s, int type, sb200_saddle** out) {
   for (int i = 0; i < 5 && !rc; i++) rc = sb200_malloc((void**)&P->p[i], (size_t)P->gp * sizeof(double) + 16);
   if (!rc) rc = sb200_malloc((void**)&P->diag, (size_t)P->gp * sizeof(double) + 16);
   if (!rc) rc = sb200_malloc((void**)&P->scratch, SB200_REDUCE_SCRATCH_DOUBLES * sizeof(double));
-  if (!rc) rc = sb200_ksp_create(P->gv, 30, &P->kvel);
-  if (!rc) rc = sb200_ksp_create(P->gp, 30, &P->kschur);
   if (rc) {
     sb200_saddle_destroy(P);
     return rc;
@@ -182,7 +193,9 @@ int sb200_saddle_apply(sb200_saddle* P, const double* d_x, double* d_y, void* st
     sb200::set_last_error("StokesPCApply: x and y must be distinct non-null vectors");
     return SB200_ERR_ARG;
   }
-  if (!P->svel_preonly && !P->ksvel) CHK(sb200_ksp_create(P->gv, 30, &P->ksvel));
+  CHK(ensure_ksp(&P->kvel, &P->r_vel, P->gv, P->vel_maxits));
+  CHK(ensure_ksp(&P->kschur, &P->r_schur, P->gp, P->schur_maxits));
+  if (!P->svel_preonly) CHK(ensure_ksp(&P->ksvel, &P->r_svel, P->gv, P->vel_maxits));
   double *xv = P->v[XV], *xp = P->p[XP], *v1 = P->v[V1], *p1 = P->p[P1], *tp = P->p[TP];
   CHK(sb200_vec_split(P->gp, P->d, d_x, xv, xp, stream));              // scatterGV / scatterGP
   CHK(sb200_stokes_get_diagonal_schur(P->s, P->diag, stream));         // PCJacobi's MatGetDiagonal (1 / eta of the current state)
