@@ -292,7 +292,8 @@ int KspCtx::init(long long n_, int restart_, int rank, int nranks) {
   if (ldv < 2) ldv = 2;
   const size_t nb = (size_t)ldv * sizeof(double);
   SB_CUDA(cudaMalloc((void**)&V, nb * (restart + 1)));
-  SB_CUDA(cudaMalloc((void**)&Z, nb * restart));
+  // Z (the preconditioned vectors of the flexible variant) is allocated by the first solve that has a preconditioner: without one
+  // the basis itself plays that role, and the inner solves of the saddle-point PCs never set one
   SB_CUDA(cudaMalloc((void**)&w, nb));
   SB_CUDA(cudaMalloc((void**)&small, SmallPtrs::count(restart) * sizeof(double)));
   SB_CUDA(cudaMemset(small, 0, SmallPtrs::count(restart) * sizeof(double)));
@@ -365,6 +366,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
   reason = 0;
   history.clear();
   t_op = t_pc = t_orth = 0.0;
+  if (pc && !Z) SB_CUDA(cudaMalloc((void**)&Z, (size_t)ldv * sizeof(double) * restart));
   double* Zb = pc ? Z : V;  // without a PC the preconditioned vectors are the basis itself
 
   // ||b|| for KSPConvergedDefault
