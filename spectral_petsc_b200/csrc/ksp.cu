@@ -293,7 +293,9 @@ int KspCtx::init(long long n_, int restart_, int rank, int nranks) {
   const size_t nb = (size_t)ldv * sizeof(double);
   SB_CUDA(cudaMalloc((void**)&V, nb * (restart + 1)));
   // Z (the preconditioned vectors of the flexible variant) is allocated by the first solve that has a preconditioner: without one
-  // the basis itself plays that role, and the inner solves of the saddle-point PCs never set one
+  // the basis itself plays that role, and the inner solves of the saddle-point PCs never set one.  On a slab partition it is
+  // allocated here: a solve is a collective there, and no rank may enter an allocating call while its peers' kernels wait for it.
+  if (nranks > 1) SB_CUDA(cudaMalloc((void**)&Z, nb * restart));
   SB_CUDA(cudaMalloc((void**)&w, nb));
   SB_CUDA(cudaMalloc((void**)&small, SmallPtrs::count(restart) * sizeof(double)));
   SB_CUDA(cudaMemset(small, 0, SmallPtrs::count(restart) * sizeof(double)));
