@@ -23,8 +23,9 @@ timeout 300 python tools/stokes_once.py > $O/r02_plain_stokes.log 2>&1 && \
 timeout 300 python tools/saddle_once.py > $O/r02_plain_saddle.log 2>&1 && \
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $O/r02_launches_saddle.csv python tools/saddle_once.py > $O/r02_ncu_saddle.log 2>&1
 
-# 4. one full capture of the Stokes kernels (the 52 % item of round 1): 14 launches of one StokesMatMult
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'eo_deriv|vv_flux|pad_nodes|crop|reduce_order' -c 16 -o $O/r02_prof_stokes python tools/stokes_once.py > $O/r02_ncu_full_stokes.log 2>&1
+# 4. one full capture of the Stokes kernels (the 52 % item of round 1): the 14 launches of the SECOND StokesMatMult of
+#    tools/stokes_once.py (of the kernels matching the filter, StokesFunction launches 13 and the first StokesMatMult 14: skipped)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'eo_deriv|vv_flux|pad_nodes|crop|reduce_order' -s 27 -c 14 -o $O/r02_prof_stokes python tools/stokes_once.py > $O/r02_ncu_full_stokes.log 2>&1
 # 5. the device assembly of the preconditioning matrices at 128^3 (not timed in round 1)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fd_assemble' -c 4 -o $O/r02_prof_fd python tools/p_sweep.py 1 > $O/r02_ncu_full_fd.log 2>&1
 # 6. a Stokes linear solve at 128^3 with nothing leaving the device (Jacobi on MatVVPC applied on the device): wall time of the
