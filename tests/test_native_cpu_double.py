@@ -196,3 +196,21 @@ def test_native_cheb_known_answers(cheb_exe):
     assert r.returncode == 83 and "must be >= 2" in r.stderr
     r = subprocess.run([cheb_exe, "-d", "3"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 83 and "tdim out of range" in r.stderr  # chebyshev.c:106
+
+
+def test_host_layer_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """apps/stokes + the unchanged host layer (reference_api, saddle, petsc shim, ILU) over the test double, built with
+    -fsanitize=address,undefined: a nonlinear continuation with the device-composed block-LU PC, a full GMRES as KSPSchurVelocity
+    and the VTK dump must run without a report (heap errors, leaks, undefined behaviour)."""
+    exe = str(tmp_path / "stokes_asan")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                         os.path.join(ROOT, "apps", "stokes.cpp")] + [os.path.join(ROOT, s) for s in HOST], capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + cc.stderr[-200:])
+    cmd = ("-exact 2 -cont 1 -rheology 1 -eps 1e-2 -exponent 2 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -dim 7,7,7 -ksp_rtol 1e-8 -ksp_max_it 200 "
+           "-snes_max_it 10 -output_vtk " + str(tmp_path / "a.vtk"))
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([exe] + cmd.split(), capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr and "LeakSanitizer" not in r.stderr
+    assert r.stdout.count("Reason for solver termination: CONVERGED_FNORM_RELATIVE") == 2
