@@ -42,4 +42,7 @@ if [ "$NG" -ge 2 ]; then
       tests/dist/dist_stokes.py 24 128 >> $O/r02_stokes_slab_n$NG.jsonl 2>> $O/r02_steps.log
   done
 fi
+# 8. memcheck of the kernels written after round 1's last GPU run (vecops, crop_trace, the FOLD variants) at small sizes
+step "memcheck saddle" timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python tools/saddle_once.py 16
+step "memcheck stokes switches" timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz1_gpu_saddle.py -x -q -k "trace_divergence and 16"
 tail -3 $O/r02_steps.log
