@@ -66,7 +66,33 @@ def ksp_case():
     np.savez_compressed(os.path.join(OUT, "ksp_elliptic_8x8x8_exact2.npz"), dim=np.array(dim), its=its, hist=np.array(hist), dx=dx, u=u)
 
 
+def saddle_case():
+    """StokesPCApply0..3 (stokes.C:1714-1817) over the oracle shells and the oracle FGMRES, by spectral_petsc_b200.solvers (the
+    composition tests/test_gpu_solvers.py pins to the reference's flow): power-law state of the manufactured solution, Jacobi on
+    MatVVPC as the velocity PC, -vel_ksp_max_it 4 -schur_ksp_max_it 3 -svel_ksp_type preonly."""
+    from spectral_petsc_b200 import solvers
+
+    dim = [7, 6, 5]
+    O = StokesCtx(dim, rheology=1, exponent=2.0, regularization=0.5, exact=2)
+    U, _ = O.create_exact_solution()
+    O.function(U)
+    dinv = 1.0 / O.pc_velocity_matrix().diagonal()
+
+    def krylov(op, b, pc, rtol, maxits, restart):
+        x, its, hist, reason = fgmres(op, b, M=pc, restart=restart, rtol=rtol, maxits=maxits)
+        return x, its, reason
+
+    x = np.random.default_rng(11).standard_normal(O.g)
+    out = {"dim": np.array(dim), "x": x}
+    for t in range(4):
+        pc = solvers.StokesSaddlePC(O, 3, krylov, lambda r: dinv * r, saddle_type=t, vel_max_it=4, schur_max_it=3, svel_preonly=True)
+        out["y%d" % t] = pc.apply(x)
+        out["its%d" % t] = np.array([pc.inner_its["velocity"], pc.inner_its["schur"]])
+    np.savez_compressed(os.path.join(OUT, "saddle_7x6x5.npz"), **out)
+
+
 if __name__ == "__main__":
+    saddle_case()
     cheb_case()
     elliptic_case([8, 6], "elliptic_8x6.npz")
     elliptic_case([7, 6, 5], "elliptic_7x6x5.npz")

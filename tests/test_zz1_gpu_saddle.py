@@ -165,3 +165,25 @@ def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
     # the switches leave no state behind
     assert torch.equal(S.mat_mult(x), y0) and torch.equal(S.function(xs), F0)
     S.destroy()
+
+
+def test_device_saddle_hits_the_oracle_golden_vectors(cuda):
+    """tests/golden/saddle_7x6x5.npz (tests/golden/make_golden.py: StokesPCApply0..3 composed over the ORACLE shells and the oracle's
+    FGMRES): the device composition over the CUDA shells reproduces those vectors and the inner iteration counts."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "saddle_7x6x5.npz"))
+    dim = [int(v) for v in z["dim"]]
+    S = _state(cuda, dim, 1)
+    import scipy.sparse as sps
+
+    rowptr, colidx, vals = [t.cpu().numpy() for t in S.pc_velocity_csr()]
+    dinv = torch.from_numpy(1.0 / sps.csr_matrix((vals, colidx, rowptr), shape=(S.gv, S.gv)).diagonal()).to(cuda)
+    x = torch.from_numpy(z["x"]).to(cuda)
+    for t in range(4):
+        dev = sp.StokesSaddle(S, t, velocity_pc=lambda r: dinv * r, vel_max_it=4, schur_max_it=3, svel_preonly=True)
+        y = dev.apply(x).cpu().numpy()
+        assert np.abs(y - z["y%d" % t]).max() <= 1e-9 * np.abs(z["y%d" % t]).max()
+        assert [dev.inner_its["velocity"], dev.inner_its["schur"]] == [int(v) for v in z["its%d" % t]]
+        dev.destroy()
+    S.destroy()
