@@ -57,6 +57,24 @@ def test_no_cpu_fallback_without_gpu():
     assert ei.value.code == 97
 
 
+def test_vector_helpers_have_no_cpu_path_either():
+    import numpy as np
+    import torch
+
+    import spectral_petsc_b200 as sp
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = sp.lib()
+    a, b = np.ones(8), np.ones(8)
+    pa, pb = a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)
+    assert L.sb200_vec_axpby(ctypes.c_longlong(8), ctypes.c_double(2.0), pa, ctypes.c_double(1.0), pb, None) == 97  # SB200_ERR_CUDA
+    assert L.sb200_vec_split(ctypes.c_longlong(2), 3, pa, pb, None, None) == 97
+    assert list(b) == [1.0] * 8  # nothing was computed on the host
+    assert L.sb200_vec_axpby(ctypes.c_longlong(8), ctypes.c_double(2.0), None, ctypes.c_double(1.0), pb, None) == 62  # argument check first
+    assert L.sb200_saddle_create(None, 0, None) == 62 and L.sb200_saddle_apply(None, pa, pb, None) == 62
+
+
 def test_product_never_imports_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "spectral_petsc_b200")):
         for f in files:
