@@ -226,6 +226,10 @@ def ksp_secondary(sp, torch, dev, G128, U128):
         out["config4_stokes20_exact2_block_lu"] = ksp_config4(sp, torch, dev)
     except Exception as e:  # written after the last GPU run of round 1: must not cost the figures above
         out["config4_stokes20_exact2_block_lu"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        out["elliptic128_exact2_device_jacobi"] = ksp_device_jacobi(sp, torch, dev, list(G128.dim))
+    except Exception as e:  # written after the last GPU run of round 1: must not cost the figures above
+        out["elliptic128_exact2_device_jacobi"] = {"error": "%s: %s" % (type(e).__name__, e)}
     K = sp.KSP(G128.g)
     K.set_operators(G128)
     K.set_tolerances(rtol=1e-30, maxits=30)
@@ -240,6 +244,43 @@ def ksp_secondary(sp, torch, dev, G128, U128):
                                  "ms_per_iteration": wall / max(r["its"], 1), "residual_reduction": r["rnorm"] / r["bnorm"]}
     K.destroy()
     return out
+
+
+def ksp_device_jacobi(sp, torch, dev, dim, maxits=3000):
+    """'KSP time to rtol 1e-10' on the headline grid with NOTHING on the host: ./elliptic -dim 128,128,128 -exact 2 -ksp_rtol 1e-10
+    -pc_type jacobi.  FGMRES(30) on the MatShell, the preconditioner the diagonal of the device-assembled finite-difference matrix
+    (FormJacobian), applied on the device.  Jacobi is a weak PC (the reference's ILU(2) / hypre are PETSc's and out of scope), so the
+    iteration count is large; what the figure shows is the cost per iteration of operator + Krylov vector work at this size."""
+    u, u2, dirichlet = sp.elliptic_exact_solution(dim, 2)
+    G = sp.Elliptic(dim, gamma=0.0)
+    G.set_dirichlet(torch.from_numpy(dirichlet).to(dev))
+    G.set_rhs(torch.from_numpy(u2).to(dev))
+    F = G.form_function(torch.zeros(G.g, dtype=torch.float64, device=dev))
+    rowptr, colidx, vals = G.jacobian_csr()
+    counts = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(G.g, device=rowptr.device), counts)
+    diag = vals[colidx.long() == rows]
+    assert diag.numel() == G.g
+    del rows, counts, rowptr, colidx, vals
+    K = sp.KSP(G.g)
+    K.set_operators(G, pc=lambda r: r / diag)
+    rhs = -1.0 * F
+    K.set_tolerances(rtol=1e-10, maxits=5)
+    K.solve(rhs)  # warm-up: 5 iterations
+    K.set_tolerances(rtol=1e-10, maxits=maxits)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dx = K.solve(rhs)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    r, t = K.result, K.times_ms
+    res = {"dim": "x".join(str(p) for p in dim), "ksp_rtol": 1e-10, "pc": "Jacobi of the device-assembled FD matrix, applied on the device", "iterations": r["its"],
+           "reason": r["reason"], "time_ms_total": wall, "ms_per_iteration": wall / max(r["its"], 1), "time_ms_operator": t["operator"], "time_ms_pc": t["pc"],
+           "time_ms_ksp_vector_work": t["ksp_vector_work"], "residual_reduction": r["rnorm"] / r["bnorm"],
+           "norm_of_error": float((dx.cpu() - torch.from_numpy(u)).abs().max())}
+    K.destroy()
+    G.destroy()
+    return res
 
 
 def ksp_config4(sp, torch, dev):

@@ -51,6 +51,8 @@ def test_bench_extras_dry_run(libmock):
     k = d["ksp"]
     assert k["config1_elliptic16_exact2_pc_ilu2"]["iterations"] == 16 and k["config1_elliptic16_exact2_pc_lu"]["iterations"] == 13
     assert k["config1_elliptic16_exact2_pc_lu"]["norm_of_error"] < 1e-9 and k["fgmres30_cycle_128"]["iterations"] == 30
+    dj = k["elliptic128_exact2_device_jacobi"]  # 16^3 in this dry run
+    assert "error" not in dj and dj["reason"] == 2 and 20 < dj["iterations"] < 200 and dj["norm_of_error"] < 1e-8
     c4 = k["config4_stokes20_exact2_block_lu"]
     assert "error" not in c4 and c4["reason"] == 2 and abs(c4["iterations"] - 26) <= 1 and c4["norm_of_error_velocity"] < 1e-6  # 26: apps/stokes with ILU(2)
     assert c4["pc_host_standin_calls"] > 0 and c4["inner_iterations"]["velocity"] > 0 and c4["inner_iterations"]["schur"] > 0
