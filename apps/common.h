@@ -110,6 +110,14 @@ struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
     if (type == "none") return 0;
     PetscInt rows, nz;
     CHK(MatGetSize(P, &rows, PETSC_NULL));
+    if (type == "jacobi") {  // the diagonal is taken on the device: the matrix never comes down
+      n = rows;
+      if (!d_diag) CHK(sb200_malloc((void**)&d_diag, (size_t)rows * sizeof(double)));
+      CHK(sb200_csr_diagonal(rows, P->d_rowptr, P->d_colidx, P->d_vals, d_diag, nullptr));
+      diag.resize(rows);  // host copy for apply_host (the -saddle_on_host cross-check)
+      CHK(sb200_memcpy_d2h(diag.data(), d_diag, (size_t)rows * sizeof(double), nullptr));
+      return sb200_stream_sync(nullptr);
+    }
     CHK(MatSeqAIJGetCSRHost(P, &nz, PETSC_NULL, PETSC_NULL, PETSC_NULL));
     const bool first = rowptr.empty();
     if (first) {
@@ -126,14 +134,6 @@ struct HostPc {  // stand-in for PETSc's PC on P: ilu (levels), jacobi, none
     if (type == "ilu") {
       if (first) CHK(sb200_host_ilu_create(rows, rowptr.data(), colidx.data(), vals.data(), levels, &ilu));
       else CHK(sb200_host_ilu_refactor(ilu, vals.data()));
-    } else if (type == "jacobi") {
-      diag.assign(rows, 1.0);
-      for (int i = 0; i < rows; i++)
-        for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
-          if (colidx[p] == i) diag[i] = vals[p];
-      if (!d_diag) CHK(sb200_malloc((void**)&d_diag, (size_t)rows * sizeof(double)));
-      CHK(sb200_memcpy_h2d(d_diag, diag.data(), (size_t)rows * sizeof(double), nullptr));
-      CHK(sb200_stream_sync(nullptr));
     }
     return 0;
   }

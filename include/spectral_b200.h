@@ -253,6 +253,9 @@ int sb200_vec_merge(long long nodes, int d, const double* d_v, const double* d_p
 int sb200_vec_axpby(long long n, double a, const double* d_x, double b, double* d_y, void* stream);
 /* VecPointwiseDivide: y = x / diag (PCJacobi on the "diagonal" of StokesMatGetDiagonalSchur, stokes.C:328-333) */
 int sb200_vec_pointwise_divide(long long n, const double* d_x, const double* d_diag, double* d_y, void* stream);
+/* MatGetDiagonal of a device CSR matrix (the SeqAIJ preconditioning matrices of FormJacobian / StokesPCSetUp0): what PCJacobi needs,
+ * without bringing the matrix to the host; rows without a stored diagonal entry give 0 */
+int sb200_csr_diagonal(long long nrows, const int* d_rowptr, const int* d_colidx, const double* d_vals, double* d_diag, void* stream);
 /* MatNullSpaceRemove with the constant vector on the n entries x[offset + i*stride] (stokes.C:1013-1023: the pressure slots of
  * the global vector are stride d+1, offset d).  d_scratch: SB200_REDUCE_SCRATCH_DOUBLES doubles of device memory. */
 #define SB200_REDUCE_SCRATCH_DOUBLES 1024

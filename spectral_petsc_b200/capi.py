@@ -715,6 +715,17 @@ def vec_pointwise_divide(x, diag):
     return y
 
 
+def csr_diagonal(rowptr, colidx, vals):
+    """MatGetDiagonal of a device CSR matrix (int32 rowptr / colidx, fp64 vals as returned by jacobian_csr / pc_velocity_csr)."""
+    import torch
+
+    n = rowptr.numel() - 1
+    assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32 and rowptr.is_contiguous() and colidx.is_contiguous()
+    diag = torch.empty(n, dtype=torch.float64, device=vals.device)
+    _ck(lib().sb200_csr_diagonal(ctypes.c_longlong(n), ctypes.c_void_p(rowptr.data_ptr()), ctypes.c_void_p(colidx.data_ptr()), _ptr(vals), _ptr(diag), _stream()))
+    return diag
+
+
 def vec_remove_mean(x, stride=1, offset=0):
     """MatNullSpaceRemove with the constant vector on x[offset::stride], in place."""
     import torch

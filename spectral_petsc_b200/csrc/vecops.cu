@@ -66,6 +66,19 @@ __global__ void __launch_bounds__(TPB) divide_kernel(long long n, const double* 
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) y[i] = x[i] / dg[i];
 }
 
+// diag[r] = the stored entry (r, r) of a CSR matrix, 0 if the row has none (MatGetDiagonal on the SeqAIJ preconditioning matrices:
+// what PCJacobi needs of them); rows are short (2d + 1 entries), one thread per row
+__global__ void __launch_bounds__(TPB) csr_diagonal_kernel(long long nrows, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                           const double* __restrict__ vals, double* __restrict__ diag) {
+  const long long stride = (long long)gridDim.x * TPB;
+  for (long long r = (long long)blockIdx.x * TPB + threadIdx.x; r < nrows; r += stride) {
+    double v = 0.0;
+    for (int q = rowptr[r]; q < rowptr[r + 1]; q++)
+      if (colidx[q] == r) v = vals[q];
+    diag[r] = v;
+  }
+}
+
 __device__ __forceinline__ double block_sum_all(double v, double* sm) {  // result on every thread, fixed order
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,6 +153,15 @@ int sb200_vec_pointwise_divide(long long n, const double* d_x, const double* d_d
   SB_CHECK(n >= 0 && d_x && d_diag && d_y, SB200_ERR_ARG, "sb200_vec_pointwise_divide: bad arguments");
   if (n == 0) return 0;
   divide_kernel<<<blocks_for(n, 148 * 16), TPB, 0, (cudaStream_t)stream>>>(n, d_x, d_diag, d_y);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sb200_csr_diagonal(long long nrows, const int* d_rowptr, const int* d_colidx, const double* d_vals, double* d_diag, void* stream) {
+  SB_CHECK(nrows >= 0 && d_rowptr && d_colidx && d_vals && d_diag, SB200_ERR_ARG, "sb200_csr_diagonal: bad arguments");
+  if (nrows == 0) return 0;
+  csr_diagonal_kernel<<<blocks_for(nrows, 148 * 16), TPB, 0, (cudaStream_t)stream>>>(nrows, d_rowptr, d_colidx, d_vals, d_diag);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;

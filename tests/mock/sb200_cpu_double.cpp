@@ -260,6 +260,16 @@ int sb200_vec_pointwise_divide(long long n, const double* x, const double* dg, d
   for (long long i = 0; i < n; i++) y[i] = x[i] / dg[i];
   return 0;
 }
+int sb200_csr_diagonal(long long nrows, const int* rowptr, const int* colidx, const double* vals, double* diag, void*) {
+  if (nrows < 0 || !rowptr || !colidx || !vals || !diag) FAIL(SB200_ERR_ARG, "sb200_csr_diagonal: bad arguments");
+  for (long long r = 0; r < nrows; r++) {
+    double v = 0.0;
+    for (int q = rowptr[r]; q < rowptr[r + 1]; q++)
+      if (colidx[q] == r) v = vals[q];
+    diag[r] = v;
+  }
+  return 0;
+}
 int sb200_vec_remove_mean(long long n, int stride, int offset, double* x, double* scratch, void*) {
   if (n < 0 || stride < 1 || offset < 0 || offset >= stride || !x || !scratch) FAIL(SB200_ERR_ARG, "sb200_vec_remove_mean: bad arguments");
   double s = 0;

@@ -187,3 +187,25 @@ def test_device_saddle_hits_the_oracle_golden_vectors(cuda):
         assert [dev.inner_its["velocity"], dev.inner_its["schur"]] == [int(v) for v in z["its%d" % t]]
         dev.destroy()
     S.destroy()
+
+
+@pytest.mark.parametrize("dim", [[8, 6], [9, 7, 6], [32, 32, 32], [6, 5, 4, 3]], ids=str)
+def test_csr_diagonal_of_the_device_assembled_matrices(cuda, dim):
+    """sb200_csr_diagonal (MatGetDiagonal for PCJacobi, no download of the matrix) on FormJacobian's P and, in 2-D / 3-D, on MatVVPC."""
+    def by_torch(rowptr, colidx, vals):
+        counts = (rowptr[1:] - rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(rowptr.numel() - 1, device=rowptr.device), counts)
+        return vals[colidx.long() == rows]
+
+    E = sp.Elliptic(dim, gamma=4.0, exponent=2.0)
+    E.form_function(torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(E.g)).to(cuda))
+    csr = E.jacobian_csr()
+    d = sp.csr_diagonal(*csr)
+    assert d.numel() == E.g and torch.equal(d, by_torch(*csr)) and float(d.abs().min()) > 0.0
+    E.destroy()
+    if len(dim) in (2, 3):
+        S = _state(cuda, dim, 1)
+        csr = S.pc_velocity_csr()
+        d = sp.csr_diagonal(*csr)
+        assert d.numel() == S.gv and torch.equal(d, by_torch(*csr)) and float(d.abs().min()) > 0.0
+        S.destroy()
