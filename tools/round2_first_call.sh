@@ -1,6 +1,8 @@
 #!/bin/bash
-# Everything that round 1 left unmeasured, in ONE GPU call (about 8-10 box minutes):
-#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Everything that round 1 left unmeasured, in ONE GPU call (expect 25-40 box minutes; the per-step timeouts add up to more, so give
+# the call room and read gpurun_out/r02_steps.log to see how far it got):
+#   gpurun --timeout 3000 -- 'bash tools/round2_first_call.sh'
+# Steps 1-2 alone (tests + bench, ~12 minutes) are the part that must not be skipped: STEPS=2 bash tools/round2_first_call.sh
 # Outputs land in gpurun_out/ (r02_*): copy the summaries worth keeping into profiles/.
 # Order: the things whose numbers matter most first, so a call cut short still leaves them behind; every step is time-boxed and
 # a failing step does not stop the rest.
@@ -17,6 +19,7 @@ step "full GPU suite" timeout 1200 python -m pytest tests -m gpu -x -q
 timeout 600 python bench.py > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err; echo "bench exit $?" >> $O/r02_steps.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/r02_bench_ref.json 2>> $O/r02_steps.log
 
+[ "${STEPS:-9}" -le 2 ] && { tail -3 $O/r02_steps.log; exit 0; }
 # 3. per-launch time lists (never a bench value): the Stokes step and the native saddle-point PC
 timeout 300 python tools/stokes_once.py > $O/r02_plain_stokes.log 2>&1 && \
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_stokes.csv python tools/stokes_once.py > $O/r02_ncu_stokes.log 2>&1
