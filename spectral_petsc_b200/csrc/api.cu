@@ -452,7 +452,7 @@ int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, v
 
 int sb200_elliptic_set_path(sb200_elliptic* e, int path) {
   SB_CHECK(e, SB200_ERR_ARG, "null context");
-  SB_CHECK(path >= 0 && path <= 3, SB200_ERR_USER, "path must be 0..3");
+  SB_CHECK(path >= 0 && path <= 4, SB200_ERR_USER, "path must be 0..4");
   e->c->path = path;
   return 0;
 }

@@ -266,6 +266,10 @@ EllipticCtx::~EllipticCtx() {
   if (dirichlet) cudaFree(dirichlet);
   if (b) cudaFree(b);
   if (sync) cudaFree(sync);
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (gstream) cudaStreamDestroy(gstream);
+  if (gU) cudaFree(gU);
+  if (gV) cudaFree(gV);
   for (DiffMatrix* dm : owned) {
     dm->destroy();
     delete dm;
@@ -329,7 +333,6 @@ int EllipticCtx::crop(const double* local, const double* rhs, double* V, cudaStr
 
 int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
   SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
-  const int d = gd.d;
   if (arena.nranks > 1) {
     SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
     if ((path == 0 || path == 3) && elliptic_slab_fused_supported(*this)) return elliptic_matmult_slab_fused(*this, U, V, s);
@@ -342,6 +345,48 @@ int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
     SB_CHECK(elliptic_fused_supported(*this), SB200_ERR_SUP, "fused path needs equal extents P in {32,64,128}");
     return elliptic_matmult_fused(*this, U, V, s);
   }
+  if (path == 4 && arena.nranks == 1) return matmult_graph(U, V, s);
+  return matmult_generic(U, V, s);
+}
+
+int EllipticCtx::matmult_graph(const double* U, double* V, cudaStream_t s) {
+  const size_t bytes = (size_t)gd.g * sizeof(double);
+  if (!gexec) {
+    if (!gU) SB_CUDA(cudaMalloc((void**)&gU, bytes));
+    if (!gV) SB_CUDA(cudaMalloc((void**)&gV, bytes));
+    if (!gstream) SB_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamSynchronize(s));  // the warm-up below uses the context's scratch fields on another stream
+    SB_CUDA(cudaMemsetAsync(gU, 0, bytes, gstream));
+    SB_TRY(matmult_generic(gU, gV, gstream));  // once outside the capture: function attributes, lazy module loading
+    SB_CUDA(cudaStreamSynchronize(gstream));
+    SB_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
+    const int rc = matmult_generic(gU, gV, gstream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      SB_CHECK(rc == 0, rc, "MatMult_Elliptic: the generic path failed while being captured");
+      set_last_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+      return SB200_ERR_CUDA;
+    }
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    gnodes = (int)nn;
+    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    SB_CUDA(ie);
+  }
+  // the captured kernels read eta / deta / gradu through the context's own (fixed) arrays, so a new state needs no re-capture
+  SB_CUDA(cudaMemcpyAsync(gU, U, bytes, cudaMemcpyDeviceToDevice, s));
+  SB_CUDA(cudaGraphLaunch(gexec, s));
+  SB_CUDA(cudaMemcpyAsync(V, gV, bytes, cudaMemcpyDeviceToDevice, s));
+  count_launch(gnodes);
+  return 0;
+}
+
+int EllipticCtx::matmult_generic(const double* U, double* V, cudaStream_t s) {
+  const int d = gd.d;
   SB_TRY(pad(U, false, w[0], s));                                              // :305-308
   for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], w[1 + k], nullptr, DERIV_STORE, s));  // :309-311
   FluxPtrs fp;

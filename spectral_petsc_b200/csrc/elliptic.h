@@ -75,6 +75,15 @@ struct EllipticCtx {
   int pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s);
   int crop(const double* local, const double* rhs, double* V, cudaStream_t s);
   int matmult(const double* U, double* V, cudaStream_t s);
+  int matmult_generic(const double* U, double* V, cudaStream_t s);
+  // path 4 (opt-in, single GPU): the generic path's launches captured once into a CUDA graph on fixed staging vectors and
+  // replayed per application - for the small grids (BASELINE configs 1 and 3) where 2d + 3 launches of a few us each are the cost
+  int matmult_graph(const double* U, double* V, cudaStream_t s);
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t gstream = nullptr;
+  double* gU = nullptr;
+  double* gV = nullptr;
+  int gnodes = 0;
   int function(const double* U, double* F, cudaStream_t s);
 };
 

@@ -808,7 +808,7 @@ int sb200_elliptic_slab_info(const sb200_elliptic* e, int* rank, int* nranks, in
   if (gtotal) *gtotal = e->g;
   return 0;
 }
-int sb200_elliptic_set_path(sb200_elliptic*, int path) { return path >= 0 && path <= 3 ? 0 : SB200_ERR_USER; }  // one CPU path here
+int sb200_elliptic_set_path(sb200_elliptic*, int path) { return path >= 0 && path <= 4 ? 0 : SB200_ERR_USER; }  // one CPU path here
 // the remaining single-rank entry points of the Python harness (dry runs of the GPU test modules)
 int sb200_device_count(int* n) { *n = 1; return 0; }
 int sb200_set_device(int) { return 0; }

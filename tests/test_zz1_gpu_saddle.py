@@ -209,3 +209,28 @@ def test_csr_diagonal_of_the_device_assembled_matrices(cuda, dim):
         d = sp.csr_diagonal(*csr)
         assert d.numel() == S.gv and torch.equal(d, by_torch(*csr)) and float(d.abs().min()) > 0.0
         S.destroy()
+
+
+@pytest.mark.parametrize("dim", [[16, 16, 16], [12, 12, 12, 12, 12], [20, 17, 9], [24, 24]], ids=str)
+def test_graph_captured_generic_path_equals_generic_path(cuda, dim):
+    """Opt-in path 4 of MatMult_Elliptic: the generic path's launches captured once into a CUDA graph and replayed - the same
+    kernels on the same data, so the same bits; a new FormFunction state is seen without re-capture."""
+    E = sp.Elliptic(dim, gamma=4.0, exponent=2.0)
+    rng = np.random.default_rng(2)
+    U = torch.from_numpy(rng.standard_normal(E.g)).to(cuda)
+    for trial in range(3):
+        E.form_function(torch.from_numpy(0.1 * rng.standard_normal(E.g)).to(cuda))  # new eta / deta / gradu each time
+        E.set_path(1)
+        l0 = sp.launch_count()
+        ref = E.mat_mult(U).clone()
+        n_generic = sp.launch_count() - l0
+        E.set_path(4)
+        out = E.mat_mult(U)
+        assert torch.equal(out, ref)
+        l0 = sp.launch_count()
+        out2 = E.mat_mult(U)
+        assert torch.equal(out2, ref)
+        if n_generic:
+            assert sp.launch_count() - l0 == n_generic  # the graph replays as many kernels as the generic path launches
+    E.set_path(0)
+    E.destroy()
