@@ -21,7 +21,8 @@ def libmock(tmp_path_factory):
 
 
 @pytest.mark.parametrize("module,filters,expect", [
-    ("test_zz1_gpu_saddle", [], 37),
+    ("test_zz1_gpu_saddle", [], 28),
+    ("test_zz4_gpu_optins", [], 9),
     ("test_zz3_gpu_drivers", ["test_elliptic_config1_and_nonlinear", "test_stokes_continuation_and_vtk"], 2),
     ("test_gpu_solvers", [], 5),  # green on the B200 in round 1; kept here as the regression net of the Python solver orchestration
 ])

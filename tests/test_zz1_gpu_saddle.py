@@ -121,52 +121,6 @@ def test_outer_fgmres_with_native_saddle_pc_matches_python_pc(cuda):
     S.destroy()
 
 
-@pytest.mark.parametrize("dim,rheology", [([16, 16, 16], 1), ([32, 32, 32], 1), ([9, 7, 6], 1), ([8, 6], 0), ([20, 20, 20], 0)], ids=str)
-def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
-    """Opt-in sb200_stokes_set_trace_divergence: the pressure rows of StokesMatMult / StokesFunction taken from the trace of the
-    velocity gradient the viscous part computes, instead of a second StokesDivergence pass on the same input (stokes.C:509,746)."""
-    S = _state(cuda, dim, rheology)
-    d = len(dim)
-    rng = np.random.default_rng(3)
-    x = torch.from_numpy(rng.standard_normal(S.g)).to(cuda)
-    xs = torch.from_numpy(0.3 * rng.standard_normal(S.g)).to(cuda)
-    F0 = S.function(xs).clone()
-    l0 = sp.launch_count()
-    y0 = S.mat_mult(x).clone()
-    n_off = sp.launch_count() - l0
-    S.set_trace_divergence(True)
-    F1 = S.function(xs).clone()
-    l0 = sp.launch_count()
-    y1 = S.mat_mult(x).clone()
-    n_on = sp.launch_count() - l0
-    S.set_trace_divergence(False)
-    for a, b in ((y1, y0), (F1, F0)):
-        assert float((a - b).abs().max()) <= 1e-13 * float(b.abs().max())
-        assert torch.equal(a.reshape(-1, d + 1)[:, :d], b.reshape(-1, d + 1)[:, :d])  # the velocity rows do not change path
-    if n_off:  # (0 over the CPU test double of the dry run)
-        assert n_on < n_off
-    print("trace-divergence %s: launches %d -> %d, pressure rows bitwise equal: %s" % (dim, n_off, n_on, torch.equal(y1, y0) and torch.equal(F1, F0)))
-    # opt-in 2, alone and with the first: the pressure gradient out of the viscous divergence (flux = eta*eps - p I); the sum of the
-    # two terms is rounded once instead of twice, so the bar is the parity bar of the operator (1e-12), not bit equality
-    for trace in (False, True):
-        S.set_trace_divergence(trace)
-        S.set_fold_pressure(True)
-        F2 = S.function(xs).clone()
-        l0 = sp.launch_count()
-        y2 = S.mat_mult(x).clone()
-        n_fold = sp.launch_count() - l0
-        S.set_fold_pressure(False)
-        S.set_trace_divergence(False)
-        for a, b in ((y2, y0), (F2, F0)):
-            assert float((a - b).abs().max()) <= 1e-12 * float(b.abs().max())
-        if n_off:
-            assert n_fold < n_off
-        print("fold-pressure (trace %s) %s: launches %d -> %d, max rel diff %.2e" % (trace, dim, n_off, n_fold, float((y2 - y0).abs().max() / y0.abs().max())))
-    # the switches leave no state behind
-    assert torch.equal(S.mat_mult(x), y0) and torch.equal(S.function(xs), F0)
-    S.destroy()
-
-
 def test_device_saddle_hits_the_oracle_golden_vectors(cuda):
     """tests/golden/saddle_7x6x5.npz (tests/golden/make_golden.py: StokesPCApply0..3 composed over the ORACLE shells and the oracle's
     FGMRES): the device composition over the CUDA shells reproduces those vectors and the inner iteration counts."""
@@ -209,28 +163,3 @@ def test_csr_diagonal_of_the_device_assembled_matrices(cuda, dim):
         d = sp.csr_diagonal(*csr)
         assert d.numel() == S.gv and torch.equal(d, by_torch(*csr)) and float(d.abs().min()) > 0.0
         S.destroy()
-
-
-@pytest.mark.parametrize("dim", [[16, 16, 16], [12, 12, 12, 12, 12], [20, 17, 9], [24, 24]], ids=str)
-def test_graph_captured_generic_path_equals_generic_path(cuda, dim):
-    """Opt-in path 4 of MatMult_Elliptic: the generic path's launches captured once into a CUDA graph and replayed - the same
-    kernels on the same data, so the same bits; a new FormFunction state is seen without re-capture."""
-    E = sp.Elliptic(dim, gamma=4.0, exponent=2.0)
-    rng = np.random.default_rng(2)
-    U = torch.from_numpy(rng.standard_normal(E.g)).to(cuda)
-    for trial in range(3):
-        E.form_function(torch.from_numpy(0.1 * rng.standard_normal(E.g)).to(cuda))  # new eta / deta / gradu each time
-        E.set_path(1)
-        l0 = sp.launch_count()
-        ref = E.mat_mult(U).clone()
-        n_generic = sp.launch_count() - l0
-        E.set_path(4)
-        out = E.mat_mult(U)
-        assert torch.equal(out, ref)
-        l0 = sp.launch_count()
-        out2 = E.mat_mult(U)
-        assert torch.equal(out2, ref)
-        if n_generic:
-            assert sp.launch_count() - l0 == n_generic  # the graph replays as many kernels as the generic path launches
-    E.set_path(0)
-    E.destroy()

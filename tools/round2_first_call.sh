@@ -12,7 +12,7 @@ O=gpurun_out
 step() { echo "=== $1" | tee -a $O/r02_steps.log; shift; ( "$@" ) >> $O/r02_steps.log 2>&1; echo "    exit $?" | tee -a $O/r02_steps.log; }
 
 # 1. late GPU tests first (never run on a GPU in round 1), then the whole suite
-step "late GPU tests" timeout 600 python -m pytest tests/test_zz1_gpu_saddle.py tests/test_zz2_gpu_reference_api2.py tests/test_zz3_gpu_drivers.py -x -q
+step "late GPU tests" timeout 900 python -m pytest tests/test_zz1_gpu_saddle.py tests/test_zz2_gpu_reference_api2.py tests/test_zz3_gpu_drivers.py tests/test_zz4_gpu_optins.py -q
 step "full GPU suite" timeout 1200 python -m pytest tests -m gpu -x -q
 
 # 2. the bench line (with the per-P sweep and the KSP metric in child processes) and the reference arm
@@ -50,5 +50,5 @@ if [ "$NG" -ge 2 ]; then
 fi
 # 8. memcheck of the kernels written after round 1's last GPU run (vecops, crop_trace, the FOLD variants) at small sizes
 step "memcheck saddle" timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python tools/saddle_once.py 16
-step "memcheck stokes switches" timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz1_gpu_saddle.py -x -q -k "trace_divergence and 16"
+step "memcheck stokes switches" timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz4_gpu_optins.py -x -q -k "16"
 tail -3 $O/r02_steps.log
