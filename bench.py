@@ -364,12 +364,13 @@ def child_main(name):
     if name == "p_sweep":
         import itertools
 
-        from tools.p_sweep import config_rows, rows, stokes_rows
+        from tools.p_sweep import config4_rows, config_rows, rows, stokes_rows
 
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         t_ex, extra = time.perf_counter(), []
         try:
-            for row in itertools.chain(stokes_rows(steps=5, dev=dev, flush=flush), config_rows(steps=5, dev=dev, flush=flush), rows(steps=5, dev=dev, flush=flush)):
+            for row in itertools.chain(stokes_rows(steps=5, dev=dev, flush=flush), config_rows(steps=5, dev=dev, flush=flush), config4_rows(steps=5, dev=dev, flush=flush),
+                                       rows(steps=5, dev=dev, flush=flush)):
                 extra.append({k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()})
                 if time.perf_counter() - t_ex > 60.0:
                     extra.append({"truncated": "60 s budget reached"})

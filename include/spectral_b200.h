@@ -181,6 +181,10 @@ int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on);
  * (stokes.C:512-513,747-750): d derivative passes and one read-modify-write crop fewer.  Same operator, ~1e-15 relative rounding
  * difference (the two terms are summed before the derivative instead of after). */
 int sb200_stokes_set_fold_pressure(sb200_stokes* s, int on);
+/* Opt-in (default 0, single GPU): the linear shells StokesMatMult / VV / PV / VP replay their launch sequence from a CUDA graph
+ * captured once on fixed staging vectors (same kernels, same results) - for small grids such as BASELINE config 4 (20^3), where a
+ * shell is 5-22 launches of a few microseconds each and the inner solves of the saddle-point PCs call them hundreds of times. */
+int sb200_stokes_set_graph(sb200_stokes* s, int on);
 /* StokesMatMultVP (stokes.C:599-619): pressure gradient with P_N - P_{N-2} extrapolation, gp -> gv. */
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream);
 /* StokesMatGetDiagonalSchur (stokes.C:542-553): y = 1/eta at pressure nodes (gp doubles). */

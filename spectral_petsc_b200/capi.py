@@ -396,6 +396,10 @@ class Stokes:
         """Opt-in: pressure rows of mat_mult / function from the trace of the gradient the viscous part computes (same bits)."""
         _ck(lib().sb200_stokes_set_trace_divergence(self._h, ctypes.c_int(int(on))))
 
+    def set_graph(self, on):
+        """Opt-in: the linear shells replay their launches from CUDA graphs (small, launch-bound grids)."""
+        _ck(lib().sb200_stokes_set_graph(self._h, ctypes.c_int(int(on))))
+
     def set_fold_pressure(self, on):
         """Opt-in: the pressure gradient of mat_mult / function comes out of the viscous divergence (flux = eta*eps - p I)."""
         _ck(lib().sb200_stokes_set_fold_pressure(self._h, ctypes.c_int(int(on))))

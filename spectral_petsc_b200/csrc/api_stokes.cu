@@ -13,7 +13,68 @@ struct sb200_stokes {
   double* d_in = nullptr;  // staging for *_host
   double* d_out = nullptr;
   FdAssembler* fd = nullptr;  // StokesPCSetUp0's MatVVPC (built on first use)
+  // opt-in (sb200_stokes_set_graph): one CUDA graph per linear shell, captured on fixed staging vectors and replayed - for the
+  // small grids (BASELINE config 4, 20^3) where a shell is 5-22 launches of a few us each
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    double* in = nullptr;
+    double* out = nullptr;
+    int nodes = 0;
+  };
+  GraphSlot graph[4];  // 0 StokesMatMult, 1 VV, 2 PV, 3 VP
+  cudaStream_t gstream = nullptr;
+  bool use_graph = false;
 };
+
+namespace {
+
+void drop_graphs(sb200_stokes* s) {  // the captured launch sequence depends on the evaluation switches
+  for (auto& g : s->graph) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+}
+
+// y = shell(x) through the slot's graph; `run` enqueues the shell's launches on a stream
+template <class Run>
+int run_graphed(sb200_stokes* s, int slot, long long n_in, long long n_out, const double* d_x, double* d_y, cudaStream_t stream, Run run) {
+  sb200_stokes::GraphSlot& g = s->graph[slot];
+  if (!g.exec) {
+    if (!g.in) SB_CUDA(cudaMalloc((void**)&g.in, (size_t)n_in * sizeof(double)));
+    if (!g.out) SB_CUDA(cudaMalloc((void**)&g.out, (size_t)n_out * sizeof(double)));
+    if (!s->gstream) SB_CUDA(cudaStreamCreateWithFlags(&s->gstream, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamSynchronize(stream));  // the warm-up below uses the context's scratch fields on another stream
+    SB_CUDA(cudaMemsetAsync(g.in, 0, (size_t)n_in * sizeof(double), s->gstream));
+    SB_TRY(run(g.in, g.out, s->gstream));  // once outside the capture: function attributes, lazy module loading
+    SB_CUDA(cudaStreamSynchronize(s->gstream));
+    SB_CUDA(cudaStreamBeginCapture(s->gstream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run(g.in, g.out, s->gstream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s->gstream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      SB_CHECK(rc == 0, rc, "Stokes shell: the launch sequence failed while being captured");
+      set_last_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+      return SB200_ERR_CUDA;
+    }
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    g.nodes = (int)nn;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SB_CUDA(ie);
+  }
+  SB_CUDA(cudaMemcpyAsync(g.in, d_x, (size_t)n_in * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  SB_CUDA(cudaGraphLaunch(g.exec, stream));
+  SB_CUDA(cudaMemcpyAsync(d_y, g.out, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  count_launch(g.nodes);
+  return 0;
+}
+
+bool graphed(const sb200_stokes* s) { return s->use_graph && s->c->arena.nranks == 1; }
+
+}  // namespace
 
 extern "C" {
 
@@ -112,21 +173,41 @@ int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream)
 
 int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s, SB200_ERR_ARG, "null context");
+  if (graphed(s)) {
+    SB_CHECK(d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMult: x and y must be distinct non-null vectors");
+    StokesCtx* c = s->c;
+    return run_graphed(s, 0, c->g, c->g, d_x, d_y, (cudaStream_t)stream, [c](const double* x, double* y, cudaStream_t st) { return c->matmult(x, y, st); });
+  }
   return s->c->matmult(d_x, d_y, (cudaStream_t)stream);
 }
 
 int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVV: bad vectors");
+  if (graphed(s)) {
+    StokesCtx* c = s->c;
+    return run_graphed(s, 1, c->gv, c->gv, d_x, d_y, (cudaStream_t)stream,
+                       [c](const double* x, double* y, cudaStream_t st) { return c->matmult_vv_into(x, c->gd.d, 0, y, c->gd.d, 0, st); });
+  }
   return s->c->matmult_vv_into(d_x, s->c->gd.d, 0, d_y, s->c->gd.d, 0, (cudaStream_t)stream);
 }
 
 int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultPV: bad vectors");
+  if (graphed(s)) {
+    StokesCtx* c = s->c;
+    return run_graphed(s, 2, c->gv, c->gp, d_x, d_y, (cudaStream_t)stream,
+                       [c](const double* x, double* y, cudaStream_t st) { return c->divergence_into(x, c->gd.d, 0, false, y, 1, 0, st); });
+  }
   return s->c->divergence_into(d_x, s->c->gd.d, 0, false, d_y, 1, 0, (cudaStream_t)stream);
 }
 
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVP: bad vectors");
+  if (graphed(s)) {
+    StokesCtx* c = s->c;
+    return run_graphed(s, 3, c->gp, c->gv, d_x, d_y, (cudaStream_t)stream,
+                       [c](const double* x, double* y, cudaStream_t st) { return c->matmult_vp_into(x, 1, 0, y, c->gd.d, 0, false, nullptr, st); });
+  }
   return s->c->matmult_vp_into(d_x, 1, 0, d_y, s->c->gd.d, 0, false, nullptr, (cudaStream_t)stream);
 }
 
@@ -143,12 +224,20 @@ int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d
 int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on) {
   SB_CHECK(s, SB200_ERR_ARG, "null context");
   s->c->trace_divergence = on != 0;
+  drop_graphs(s);
   return 0;
 }
 
 int sb200_stokes_set_fold_pressure(sb200_stokes* s, int on) {
   SB_CHECK(s, SB200_ERR_ARG, "null context");
   s->c->fold_pressure = on != 0;
+  drop_graphs(s);
+  return 0;
+}
+
+int sb200_stokes_set_graph(sb200_stokes* s, int on) {
+  SB_CHECK(s, SB200_ERR_ARG, "null context");
+  s->use_graph = on != 0;
   return 0;
 }
 
@@ -243,6 +332,12 @@ int sb200_stokes_pc_velocity_csr(sb200_stokes* s, int* d_rowptr, int* d_colidx, 
 
 int sb200_stokes_destroy(sb200_stokes* s) {
   if (!s) return 0;
+  drop_graphs(s);
+  for (auto& g : s->graph) {
+    if (g.in) cudaFree(g.in);
+    if (g.out) cudaFree(g.out);
+  }
+  if (s->gstream) cudaStreamDestroy(s->gstream);
   delete s->fd;
   delete s->c;
   if (s->d_in) cudaFree(s->d_in);

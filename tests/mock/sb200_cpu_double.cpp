@@ -635,6 +635,7 @@ int sb200_stokes_matmult_pv(sb200_stokes* s, const double* x, double* y, void*) 
   return 0;
 }
 int sb200_stokes_set_fold_pressure(sb200_stokes*, int) { return 0; }      // likewise
+int sb200_stokes_set_graph(sb200_stokes*, int) { return 0; }              // likewise
 int sb200_stokes_set_trace_divergence(sb200_stokes*, int) { return 0; }  // an implementation choice of the CUDA path; nothing to switch here
 int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* x, double* y, void*) {
   std::vector<double> p = st_div(s, x, with_dirichlet != 0);

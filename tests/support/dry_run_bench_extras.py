@@ -35,7 +35,7 @@ def main():
     import tools.p_sweep as ps
 
     dev, flush = torch.device("cpu"), torch.empty(1024, dtype=torch.uint8)
-    rows = (list(ps.stokes_rows(steps=1, P=16, dev=dev, flush=flush)) + list(ps.config_rows(steps=1, dev=dev, flush=flush))
+    rows = (list(ps.stokes_rows(steps=1, P=16, dev=dev, flush=flush)) + list(ps.config_rows(steps=1, dev=dev, flush=flush)) + list(ps.config4_rows(steps=1, dev=dev, flush=flush))
             + list(ps.rows(steps=1, Ps=(16, 17, 32), dev=dev, flush=flush)))
     G = sp.Elliptic([16, 16, 16], gamma=4.0, exponent=2.0)
     G.form_function(torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(G.g)))

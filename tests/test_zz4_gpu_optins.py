@@ -81,3 +81,38 @@ def test_graph_captured_generic_path_equals_generic_path(cuda, dim):
             assert sp.launch_count() - l0 == n_generic  # the graph replays as many kernels as the generic path launches
     E.set_path(0)
     E.destroy()
+
+
+@pytest.mark.parametrize("dim,rheology", [([20, 20, 20], 1), ([16, 16, 16], 1), ([8, 6], 0)], ids=str)
+def test_graph_replayed_stokes_shells_equal_the_launched_ones(cuda, dim, rheology):
+    """Opt-in sb200_stokes_set_graph: StokesMatMult / VV / PV / VP replayed from CUDA graphs (BASELINE config 4's 20^3 grid is
+    launch-bound) - the same kernels on the same data, so the same bits, also after a new StokesFunction state and with the
+    evaluation switches on; the saddle-point PC composed over graph-replayed shells gives the same vector."""
+    S = _state(cuda, dim, rheology)
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.standard_normal(S.g)).to(cuda)
+    v = torch.from_numpy(rng.standard_normal(S.gv)).to(cuda)
+    p = torch.from_numpy(rng.standard_normal(S.gp)).to(cuda)
+    shells = lambda: [S.mat_mult(x).clone(), S.mat_mult_vv(v).clone(), S.mat_mult_pv(v).clone(), S.mat_mult_vp(p).clone()]
+    for trial in range(2):
+        S.function(torch.from_numpy(0.3 * rng.standard_normal(S.g)).to(cuda))  # a new eta / deta / strain: no re-capture needed
+        for switches in (False, True):
+            S.set_trace_divergence(switches)
+            S.set_fold_pressure(switches)
+            S.set_graph(False)
+            ref = shells()
+            S.set_graph(True)
+            for a, b in zip(shells(), ref):
+                assert torch.equal(a, b)
+            for a, b in zip(shells(), ref):  # replay
+                assert torch.equal(a, b)
+    S.set_trace_divergence(False)
+    S.set_fold_pressure(False)
+    S.set_graph(False)
+    pc = sp.StokesSaddle(S, 0, velocity_pc=None, vel_max_it=4, schur_max_it=3, svel_preonly=True)
+    y_ref = pc.apply(x).clone()
+    S.set_graph(True)
+    assert torch.equal(pc.apply(x), y_ref)
+    S.set_graph(False)
+    pc.destroy()
+    S.destroy()

@@ -100,6 +100,36 @@ def config_rows(steps=10, dev=None, flush=None):
         E.destroy()
 
 
+def config4_rows(steps=10, dev=None, flush=None):
+    """BASELINE config 4's grid (stokes 20^3, linear viscosity): the linear shells as launched and as replayed from CUDA graphs
+    (sb200_stokes_set_graph, opt-in) - a launch-bound size, the launch count is the number to read."""
+    dev = dev or torch.device("cuda:0")
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dim = [20, 20, 20]
+    S = sp.Stokes(dim, rheology=0)
+    S.set_dirichlet(torch.zeros(S.dv, dtype=torch.float64, device=dev))
+    S.set_force(torch.zeros(S.g, dtype=torch.float64, device=dev))
+    rng = np.random.default_rng(0)
+    S.function(torch.from_numpy(0.1 * rng.standard_normal(S.g)).to(dev))
+    x = torch.from_numpy(rng.standard_normal(S.g)).to(dev)
+    xv = torch.from_numpy(rng.standard_normal(S.gv)).to(dev)
+    xp = torch.from_numpy(rng.standard_normal(S.gp)).to(dev)
+    y, yv, yp = torch.empty_like(x), torch.empty_like(xv), torch.empty_like(xp)
+    for name, fn, ndof in (("StokesMatMult", lambda: S.mat_mult(x, y), 4 * S.m), ("StokesMatMultVV", lambda: S.mat_mult_vv(xv, yv), 3 * S.m),
+                           ("StokesMatMultPV", lambda: S.mat_mult_pv(xv, yp), 3 * S.m), ("StokesMatMultVP", lambda: S.mat_mult_vp(xp, yv), S.m)):
+        for graph in (False, True):
+            S.set_graph(graph)
+            fn()
+            l0 = sp.launch_count()
+            fn()
+            nl = sp.launch_count() - l0
+            ms = timeit(fn, steps, flush)
+            yield {"op": name + (" (CUDA graph)" if graph else ""), "dim": "20x20x20", "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6}
+    S.set_graph(False)
+    S.destroy()
+
+
 def stokes_rows(steps=10, P=128, dev=None, flush=None):
     """The Stokes shells at P^3 (BASELINE config 5 state: -rheology 1 -exponent 3 -eps 1e-4) and the device assembly of MatVVPC."""
     dev = dev or torch.device("cuda:0")
@@ -166,6 +196,8 @@ def main():
     for row in stokes_rows(steps):
         print(json.dumps(row), flush=True)
     for row in config_rows(steps):
+        print(json.dumps(row), flush=True)
+    for row in config4_rows(steps):
         print(json.dumps(row), flush=True)
 
 

@@ -39,6 +39,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fd_
     -vel_pc_type jacobi -svel_pc_type jacobi -ksp_monitor -sb200_trace_divergence 1 -sb200_fold_pressure 1 ) > $O/r02_stokes128_device_jacobi_switches.log 2>&1
 ( time timeout 300 apps/stokes -exact 2 -cont0 1 -dim 20,20,20 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_rtol 1e-10 -ksp_max_it 400 \
     -vel_pc_factor_levels 2 -svel_pc_factor_levels 2 -ksp_monitor ) > $O/r02_stokes20_ilu2.log 2>&1
+( time timeout 300 apps/stokes -exact 2 -cont0 1 -dim 20,20,20 -schur_ksp_max_it 3 -vel_ksp_max_it 4 -svel_ksp_type preonly -ksp_rtol 1e-10 -ksp_max_it 400 \
+    -vel_pc_factor_levels 2 -svel_pc_factor_levels 2 -ksp_monitor -sb200_graph 1 ) > $O/r02_stokes20_ilu2_graph.log 2>&1
 ( time timeout 600 apps/elliptic -dim 128,128,128 -exact 2 -ksp_rtol 1e-10 -ksp_max_it 2000 -pc_type jacobi -ksp_monitor ) > $O/r02_elliptic128_device_jacobi.log 2>&1
 # 7. (only on a multi-GPU call: gpurun --gpus 2|4|8) the slab-partitioned Stokes shells with and without the two evaluation switches
 NG=$(python -c "import torch; print(torch.cuda.device_count())")
