@@ -41,16 +41,16 @@ def test_bench_extras_dry_run(libmock):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     ops = [row["op"] for row in d["p_sweep"]]
-    assert ops[:10] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesMatMult (trace divergence)",
-                        "StokesFunction (trace divergence)", "StokesMatMult (trace divergence + folded pressure)",
-                        "StokesFunction (trace divergence + folded pressure)", "StokesPCSetUp0 (device CSR)"]
+    assert ops[:10] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)",
+                        "StokesMatMult (trace divergence)", "StokesFunction (trace divergence)", "StokesMatMult (trace divergence + folded pressure)",
+                        "StokesFunction (trace divergence + folded pressure)"]
     cfg = [(row["op"], row["dim"], row["launches"]) for row in d["p_sweep"] if "dim" in row]
     cfg = [c for c in cfg if not c[0].startswith("Stokes")]
     st20 = [row["op"] for row in d["p_sweep"] if row.get("dim") == "20x20x20"]
     assert st20 == ["StokesMatMult", "StokesMatMult (CUDA graph)", "StokesMatMultVV", "StokesMatMultVV (CUDA graph)", "StokesMatMultPV",
                     "StokesMatMultPV (CUDA graph)", "StokesMatMultVP", "StokesMatMultVP (CUDA graph)"]
-    assert [c[:2] for c in cfg] == [("MatMult_Elliptic", "12x12x12x12x12"), ("MatMult_Elliptic (CUDA graph)", "12x12x12x12x12"), ("FormFunction", "12x12x12x12x12"),
-                                    ("MatMult_Elliptic", "16x16x16"), ("MatMult_Elliptic (CUDA graph)", "16x16x16"), ("FormFunction", "16x16x16")]
+    assert [c[:2] for c in cfg] == [("MatMult_Elliptic", "12x12x12x12x12"), ("FormFunction", "12x12x12x12x12"), ("MatMult_Elliptic (CUDA graph)", "12x12x12x12x12"),
+                                    ("MatMult_Elliptic", "16x16x16"), ("FormFunction", "16x16x16"), ("MatMult_Elliptic (CUDA graph)", "16x16x16")]
     ell = [(row["P"], row["path"]) for row in d["p_sweep"] if row["op"] == "MatMult_Elliptic" and "P" in row]
     assert ell == [(16, "generic"), (17, "generic"), (32, "generic"), (32, "chain per axis"), (32, "persistent chain")]
     assert sum(row["op"] == "ChebMult" for row in d["p_sweep"]) == 6 and sum(row["op"].startswith("FormJacobian") for row in d["p_sweep"]) == 3
