@@ -29,6 +29,9 @@ struct sb200_stokes {
 namespace {
 
 void drop_graphs(sb200_stokes* s) {  // the captured launch sequence depends on the evaluation switches
+  bool any = false;
+  for (auto& g : s->graph) any = any || g.exec;
+  if (any) cudaDeviceSynchronize();  // a replay may still be in flight
   for (auto& g : s->graph) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     g.exec = nullptr;

@@ -266,7 +266,10 @@ EllipticCtx::~EllipticCtx() {
   if (dirichlet) cudaFree(dirichlet);
   if (b) cudaFree(b);
   if (sync) cudaFree(sync);
-  if (gexec) cudaGraphExecDestroy(gexec);
+  if (gexec) {
+    cudaDeviceSynchronize();  // a replay may still be in flight
+    cudaGraphExecDestroy(gexec);
+  }
   if (gstream) cudaStreamDestroy(gstream);
   if (gU) cudaFree(gU);
   if (gV) cudaFree(gV);
