@@ -50,7 +50,13 @@ $(OBJDIR)/host_%.o: $(HOST)/%.cpp $(HDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
+# diagnostic build with the ablation / timeline switches compiled in (SB200_XFLAGS is read only by this library; the tools that
+# need it load it with SB200_ABLATE_LIB=1)
+ablate:
+	$(MAKE) OBJDIR=build_ablate LIB=spectral_petsc_b200/libspectral_b200_ablate.so EXTRA=-DSB200_ABLATE spectral_petsc_b200/libspectral_b200_ablate.so
+
 clean:
+	rm -rf build_ablate spectral_petsc_b200/libspectral_b200_ablate.so
 	rm -rf $(OBJDIR) $(LIB) $(DRIVER) $(DRIVER2) $(APP_ELL) $(APP_STK) $(APP_CHEB)
 
-.PHONY: all clean
+.PHONY: all clean ablate

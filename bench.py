@@ -28,7 +28,26 @@ METRIC = "spectral MatMult GDOF/s (fp64)"
 UNIT = "GDOF/s"
 DIM = [128, 128, 128]
 GAMMA, EXPONENT = 4.0, 2.0
-FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl)
+FP64_PEAK_FALLBACK_TFLOPS = 37.1  # round-1 measurement (profiles/r01_fp64_peak.jsonl); used only if the in-run measurement fails
+WORKLOAD = "elliptic 3D -dim 128,128,128 MatMult_Elliptic, variable coefficients (gamma=4, exponent=2)"
+PARITY_TOL = 1e-12  # BASELINE.json: MatMult output within 1e-12 relative (max norm) of the reference's FFT path
+
+
+def sb200_env():
+    """Every SB200_* variable the process sees (tuning / test hooks); recorded in the line so a run that set one says so."""
+    return {k: v for k, v in sorted(os.environ.items()) if k.startswith("SB200_")}
+
+
+def config_dict(world, extra=None):
+    """The `config` object: identical keys in both arms (the driver compares them)."""
+    m = int(np.prod(DIM))
+    g = int(np.prod([p - 2 for p in DIM]))
+    c = {"workload": WORKLOAD, "n_dof_per_step": m, "global_vec_len": g,
+         "l2": "256 MiB flush between timed steps (per-step CUDA events, flush untimed)",
+         "parallelism": ("slab%d: axis 0 cut over %d GPUs, axis-0 chain through NVLink peer memory inside the chain kernel" % (world, world)) if world > 1 else "single"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 def measured_peaks():
@@ -41,9 +60,14 @@ def measured_peaks():
 def ncu_traffic():
     """DRAM bytes per step of the two persistent launches from the committed ncu --set full capture (None if absent)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_step"]
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            f = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(f):
+                d = json.load(open(f))
+                return d["dram_bytes_per_step"], "profiles/%s (%s)" % (name, d.get("how", "ncu --set full, every launch of the step"))
     except Exception:
-        return None
+        pass
+    return None, None
 
 
 def alg_flops(dim):
@@ -143,44 +167,91 @@ def build_state_oracle(workers):
     return O, U
 
 
-def cpu_baseline(sample_steps=3):
+def _time_oracle(steps, warmup):
+    """Times `steps` full MatMult_Elliptic applications of the oracle port on all host cores (after `warmup` untimed ones)."""
     cores = os.cpu_count() or 1
     O, U = build_state_oracle(workers=cores)
-    O.mat_mult(U)
+    for _ in range(warmup):
+        O.mat_mult(U)
     t0 = time.perf_counter()
-    for _ in range(sample_steps):
+    for _ in range(steps):
         O.mat_mult(U)
     dt = time.perf_counter() - t0
-    return {"value": O.m * sample_steps / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+    return O.m * steps / dt / 1e9, dt / steps * 1e3, cores
+
+
+def _oracle_child(steps, warmup):
+    """Runs the oracle timing in a FRESH process whose environment lets scipy's FFT thread pool use every host core:
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which throttles the pool 3-4x (round 1's N>1 reference arm)."""
+    cores = os.cpu_count() or 1
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(cores)
+    env["SB200_REF_CHILD"] = "1"
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup)],
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("oracle child failed: " + (r.stderr or r.stdout)[-300:])
+    d = json.loads(lines[-1])
+    return d["value"], d["ms_per_step"], d["cores"]
+
+
+def cpu_baseline(sample_steps=3):
+    val, ms, cores = _oracle_child(sample_steps, 1)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d full MatMult_Elliptic applications at 128^3 by the numpy/scipy(pocketfft) restatement of the reference's FFT path "
                       "(FFTW/PETSc unavailable), scipy.fft workers=%d" % (sample_steps, cores),
-            "ms_per_step": dt / sample_steps * 1e3}
+            "ms_per_step": ms}
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's FFT path (oracle/, the one other place bench.py may execute it),
+    all host cores, each step one full MatMult_Elliptic at 128^3.  Under torchrun rank 0 alone measures."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    O, U = build_state_oracle(workers=cores)
-    for _ in range(min(args.warmup, 3)):
-        O.mat_mult(U)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.mat_mult(U)
-    dt = time.perf_counter() - t0
-    val = O.m * args.steps / dt / 1e9
+    if os.environ.get("SB200_REF_CHILD") == "1":
+        val, ms, cores = _time_oracle(args.steps, args.warmup)
+        print(json.dumps({"value": val, "ms_per_step": ms, "cores": cores}))
+        return 0
+    val, ms, cores = _oracle_child(args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": "elliptic 3D -dim 128,128,128 MatMult_Elliptic, variable coefficients (gamma=4, exponent=2)"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "each step = one full MatMult_Elliptic at 128^3 by the numpy/scipy(pocketfft) restatement of the reference's FFT path; "
-                                   "the reference binary itself cannot be built here (no FFTW/PETSc/MPI)"},
+                         "sample": "each step = one full MatMult_Elliptic at 128^3 by the numpy/scipy(pocketfft) restatement of the reference's FFT path "
+                                   "(a numpy port, not the reference binary: that cannot be built here - no FFTW/PETSc/MPI); timed in a child process "
+                                   "with OMP_NUM_THREADS = host cores so that the launcher's thread limit does not apply"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def parity_check(G, U, V, torch, dist, world, rank, dev):
+    """Hardware parity of the very vectors the timed loop used, at every N: V (the result of the last application) against the
+    oracle's single-domain MatMult_Elliptic (computed once on rank 0 - the oracle is the checker here, nothing timed - and
+    broadcast), max-norm relative error over all ranks; plus the count of device-side flag waits that timed out."""
+    O_g = G.gtotal
+    Vo = torch.empty(O_g, dtype=torch.float64, device=dev)
+    if rank == 0:
+        O, Uo = build_state_oracle(workers=os.cpu_count() or 1)
+        Vo.copy_(torch.from_numpy(O.mat_mult(Uo)))
+    if world > 1:
+        dist.broadcast(Vo, src=0)
+    sl = slice(G.goff, G.goff + G.g)
+    err = float((V - Vo[sl]).abs().max()) if G.g else 0.0
+    nonfinite = float((~torch.isfinite(V)).sum()) if G.g else 0.0
+    tmo = float(G.slab_timeouts()) if world > 1 else 0.0
+    t = torch.tensor([err, nonfinite, tmo], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err, nonfinite, tmo = t.tolist()
+    rel = err / float(Vo.abs().max())
+    ok = bool(rel < PARITY_TOL and nonfinite == 0 and tmo == 0)
+    return {"rel": rel, "tol": PARITY_TOL, "timeouts": int(tmo), "nonfinite": int(nonfinite), "ok": ok,
+            "checked": "V of the last timed application on every rank vs the oracle's single-domain MatMult_Elliptic (max-norm relative, max over ranks)"}
 
 
 def ksp_secondary(sp, torch, dev, G128, U128):
@@ -460,6 +531,15 @@ def run_cuda(args):
     hot_ms = e0.elapsed_time(e1) * args.steps / hot_steps
     clocks = sampler.stop() if sampler else None
 
+    # ---- hardware parity of the timed vectors (every N) and the FP64 tensor-pipe peak, both outside the timed regions ----------
+    parity = parity_check(G, U, V, torch, dist, world, rank, dev)
+    import ctypes as _ct
+    peak_tf, peak_ms = _ct.c_double(0.0), _ct.c_double(0.0)
+    peak_rc = sp.lib().sb200_fp64_dmma_peak(_ct.c_double(50.0), _ct.byref(peak_tf), _ct.byref(peak_ms))
+    fp64_peak = peak_tf.value if (peak_rc == 0 and peak_tf.value > 1.0) else FP64_PEAK_FALLBACK_TFLOPS
+    fp64_peak_source = ("measured in this run: sb200_fp64_dmma_peak, register-resident mma.sync.m8n8k4.f64 on every SM for %.0f ms (rank 0's GPU)" % peak_ms.value
+                        if fp64_peak == peak_tf.value else "fallback: round-1 measurement 37.1 TFLOP/s (the in-run measurement failed)")
+
     # ---- end-to-end through the host-buffer C-ABI calls (H2D + op + D2H every step, all inside the timed region) ----------
     # (1) one synchronous call per step (sb200_elliptic_matmult_host): copy in, run, copy out, synchronise;
     # (2) the queued form (sb200_elliptic_matmult_host_submit / _wait): the same per-step copies from / to pinned host
@@ -515,18 +595,18 @@ def run_cuda(args):
         achieved = fl * args.steps / (total_ms * 1e-3) / 1e12
         peaks = measured_peaks()
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "elliptic 3D -dim 128,128,128 MatMult_Elliptic, variable coefficients (gamma=4, exponent=2)",
-                       "n_dof_per_step": m_global, "global_vec_len": G.gtotal, "l2": "256 MiB flush between timed steps (per-step CUDA events, flush untimed)",
-                       "value_l2_warm": ndof * args.steps / (hot_ms * 1e-3) / 1e9,
-                       "parallelism": ("slab%d: axis 0 cut over %d GPUs, axis-0 chain through NVLink peer memory inside the chain kernel" % (world, world)) if world > 1 else "single"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS * world, "unit": "TFLOP/s", "frac": achieved / (FP64_PEAK_TFLOPS * world),
-                         "traffic": ncu_traffic() if world == 1 else None, "traffic_source": "profiles/r01_traffic.json (ncu --set full, both launches of the step)",
-                         "pipe": "fp64 DMMA", "peak_source": "tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.jsonl); MEASURED_PEAKS.json has no fp64 entry",
-                         "algorithmic_flops_per_step": fl, "kernel": "persist_kernel<128,8,1> phases A+B (the whole MatMult step: 2 PDL-linked launches)" if world == 1 else "slab step: stage + persist_kernel phases A+B per rank",
+            "config": config_dict(world, {"value_l2_warm": ndof * args.steps / (hot_ms * 1e-3) / 1e9}),
+            "parity": parity,
+            "env": sb200_env(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": achieved / (fp64_peak * world),
+                         "traffic": traffic if world == 1 else None, "traffic_source": traffic_src if world == 1 else None,
+                         "pipe": "fp64 DMMA", "peak_source": fp64_peak_source + "; MEASURED_PEAKS.json has no fp64 entry",
+                         "algorithmic_flops_per_step": fl, "kernel": G.kernel_name(),
                          "hbm": {"achieved": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
                                  "frac": alg_bytes(DIM) * args.steps / (total_ms * 1e-3) / 1e9 / (hbm_peak * world), "algorithmic_bytes_per_step": alg_bytes(DIM)}},
             "e2e": {"value": ndof * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": G.gtotal * 8, "d2h_bytes_per_step": G.gtotal * 8,
@@ -549,6 +629,9 @@ def run_cuda(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILURE: %s\n" % json.dumps(parity))
+        return 1
     return 0
 
 

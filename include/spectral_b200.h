@@ -49,6 +49,10 @@ int sb200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream)
 int sb200_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int sb200_memset0(void* d_dst, size_t bytes, void* stream);
 int sb200_stream_sync(void* stream);
+/* Measurement helper (bench.py roofline denominator): runs a register-resident mma.sync.m8n8k4.f64 (SASS DMMA)
+ * loop on every SM of the current device for about target_ms milliseconds (clamped to 1..500) and returns the FP64
+ * tensor-pipe rate in TFLOP/s; measured_ms (may be NULL) receives the timed kernel's duration. */
+int sb200_fp64_dmma_peak(double target_ms, double* tflops, double* measured_ms);
 
 /* ---- Chebyshev derivative: MatCreateCheb / ChebMult / ChebDestroy (chebyshev.h:31-34) ----- */
 /* MatCreateCheb(comm, rank, tr, dims, flag, vx, vy, &A) (chebyshev.c:89-138).  dims is row-major,
@@ -95,6 +99,8 @@ int sb200_elliptic_matmult_host_submit(sb200_elliptic* e, const double* h_U, dou
 int sb200_elliptic_matmult_host_wait(sb200_elliptic* e);
 int sb200_elliptic_matmult_host_pending(const sb200_elliptic* e, int* pending);
 /* FormFunction(snes, U, rhs, ctx) (elliptic.C:481-533): residual; refreshes eta/deta/gradu caches. */
+/* Name of the kernel path the last sb200_elliptic_matmult of this context ran (static string; bench.py's roofline.kernel). */
+const char* sb200_elliptic_last_kernel(const sb200_elliptic* e);
 int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream);
 int sb200_elliptic_function_host(sb200_elliptic* e, const double* h_U, double* h_F);
 /* Cached state read by FormJacobian (elliptic.C:550-553): which = 0 eta, 1 deta, 2+k gradu[k];

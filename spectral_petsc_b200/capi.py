@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libspectral_b200.so")
+# SB200_ABLATE_LIB=1 selects the diagnostic build (`make ablate`: ablation / timeline switches compiled in); the production library
+# has none of them.  bench.py records every SB200_* variable it sees.
+lib_path = os.path.join(_HERE, "libspectral_b200_ablate.so" if os.environ.get("SB200_ABLATE_LIB") == "1" else "libspectral_b200.so")
 
 
 class SB200Error(RuntimeError):
@@ -245,6 +247,12 @@ class Elliptic:
 
     def set_path(self, path):
         _ck(lib().sb200_elliptic_set_path(self._h, ctypes.c_int(path)))
+
+    def kernel_name(self):
+        """Which kernel path the last mat_mult ran (bench.py reports it as roofline.kernel)."""
+        f = lib().sb200_elliptic_last_kernel
+        f.restype = ctypes.c_char_p
+        return f(self._h).decode()
 
     def set_dirichlet(self, values):
         assert values.numel() == self.nd

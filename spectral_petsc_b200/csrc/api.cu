@@ -318,8 +318,11 @@ int sb200_elliptic_matmult(sb200_elliptic* e, const double* d_U, double* d_V, vo
   return e->c->matmult(d_U, d_V, (cudaStream_t)stream);
 }
 
+const char* sb200_elliptic_last_kernel(const sb200_elliptic* e) { return e ? e->c->last_kernel : "null context"; }
+
 int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream) {
   SB_CHECK(e, SB200_ERR_ARG, "null context");
+  SB_CHECK(!e->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier; the context refuses further work");
   return e->c->function(d_U, d_F, (cudaStream_t)stream);
 }
 

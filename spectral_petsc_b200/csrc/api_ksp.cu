@@ -47,6 +47,7 @@ int sb200_ksp_set_tolerances(sb200_ksp* k, double rtol, double atol, double dtol
 
 int sb200_ksp_solve(sb200_ksp* k, const double* d_b, double* d_x, int guess_nonzero, void* stream) {
   SB_CHECK(k, SB200_ERR_ARG, "null context");
+  SB_CHECK(!k->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   return k->c->solve(d_b, d_x, guess_nonzero != 0, (cudaStream_t)stream);
 }
 

@@ -176,6 +176,7 @@ int sb200_stokes_set_force(sb200_stokes* s, const double* d_force, void* stream)
 
 int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s, SB200_ERR_ARG, "null context");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   if (graphed(s)) {
     SB_CHECK(d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMult: x and y must be distinct non-null vectors");
     StokesCtx* c = s->c;
@@ -186,6 +187,7 @@ int sb200_stokes_matmult(sb200_stokes* s, const double* d_x, double* d_y, void* 
 
 int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVV: bad vectors");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   if (graphed(s)) {
     StokesCtx* c = s->c;
     return run_graphed(s, 1, c->gv, c->gv, d_x, d_y, (cudaStream_t)stream,
@@ -196,6 +198,7 @@ int sb200_stokes_matmult_vv(sb200_stokes* s, const double* d_x, double* d_y, voi
 
 int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultPV: bad vectors");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   if (graphed(s)) {
     StokesCtx* c = s->c;
     return run_graphed(s, 2, c->gv, c->gp, d_x, d_y, (cudaStream_t)stream,
@@ -206,6 +209,7 @@ int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, voi
 
 int sb200_stokes_matmult_vp(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y && d_x != d_y, SB200_ERR_ARG, "StokesMatMultVP: bad vectors");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   if (graphed(s)) {
     StokesCtx* c = s->c;
     return run_graphed(s, 3, c->gp, c->gv, d_x, d_y, (cudaStream_t)stream,
@@ -221,6 +225,7 @@ int sb200_stokes_get_diagonal_schur(sb200_stokes* s, double* d_y, void* stream) 
 
 int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s && d_x && d_y, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   return s->c->divergence_into(d_x, s->c->gd.d, 0, with_dirichlet != 0, d_y, 1, 0, (cudaStream_t)stream);
 }
 
@@ -246,11 +251,13 @@ int sb200_stokes_set_graph(sb200_stokes* s, int on) {
 
 int sb200_stokes_matmult_schur(sb200_stokes* s, const double* d_x, double* d_y, sb200_velocity_solve_fn solve, void* solve_ctx, void* stream) {
   SB_CHECK(s && d_x && d_y, SB200_ERR_ARG, "null pointer");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   return s->c->matmult_schur(d_x, d_y, solve, solve_ctx, (cudaStream_t)stream);
 }
 
 int sb200_stokes_function(sb200_stokes* s, const double* d_x, double* d_y, void* stream) {
   SB_CHECK(s, SB200_ERR_ARG, "null context");
+  SB_CHECK(!s->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");
   return s->c->function(d_x, d_y, (cudaStream_t)stream);
 }
 

@@ -338,17 +338,27 @@ int EllipticCtx::matmult(const double* U, double* V, cudaStream_t s) {
   SB_CHECK(U && V && U != V, SB200_ERR_ARG, "MatMult_Elliptic: U and V must be distinct non-null vectors");
   if (arena.nranks > 1) {
     SB_CHECK(arena.attached(), SB200_ERR_USER, "slab partition: peers are not attached (exchange the IPC handles first)");
-    if ((path == 0 || path == 3) && elliptic_slab_fused_supported(*this)) return elliptic_matmult_slab_fused(*this, U, V, s);
+    SB_CHECK(!arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); results are undefined, the context refuses further work");
+    if ((path == 0 || path == 3) && elliptic_slab_fused_supported(*this)) {
+      last_kernel = "slab step: stage_kernel + persist_kernel<P,8,1,SLAB> per rank (axis-0 chain on pencils exchanged through NVLink peer memory)";
+      return elliptic_matmult_slab_fused(*this, U, V, s);
+    }
     SB_CHECK(path <= 1, SB200_ERR_SUP, "slab partition: the fused path needs equal extents P in {32,64,128}");
   } else if (path == 3 || (path == 0 && elliptic_persist_supported(*this))) {
     SB_CHECK(elliptic_persist_supported(*this), SB200_ERR_SUP, "persistent path needs equal extents P in {32,64,128}");
+    last_kernel = "persist_kernel<P,8,1> phases A+B (the whole MatMult step: 2 PDL-linked launches)";
     return elliptic_matmult_persist(*this, U, V, s);
   }
   if (path == 2 && arena.nranks == 1) {
     SB_CHECK(elliptic_fused_supported(*this), SB200_ERR_SUP, "fused path needs equal extents P in {32,64,128}");
+    last_kernel = "chain_kernel per axis";
     return elliptic_matmult_fused(*this, U, V, s);
   }
-  if (path == 4 && arena.nranks == 1) return matmult_graph(U, V, s);
+  if (path == 4 && arena.nranks == 1) {
+    last_kernel = "generic path replayed from a CUDA graph";
+    return matmult_graph(U, V, s);
+  }
+  last_kernel = "generic path: pad + per-axis deriv_kernel / eo_deriv_kernel + pointwise kernels";
   return matmult_generic(U, V, s);
 }
 

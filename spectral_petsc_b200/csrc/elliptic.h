@@ -50,6 +50,7 @@ struct EllipticCtx {
   double* b = nullptr;          // ac->b
   double gamma = 0.0, exponent = 2.0;
   int path = 0;
+  const char* last_kernel = "none";  // which kernel path the last MatMult_Elliptic ran (reported by bench.py)
   long long* trace = nullptr;  // debug: phase time stamps (SB200_TRACE builds)
   unsigned* sync = nullptr;  // ticket / completion counters of the persistent kernel
   DiffMatrix* Dax[SB200_MAX_DIM] = {};

@@ -18,6 +18,14 @@
 #include "elliptic.h"
 #include "persist.h"
 
+// Ablation / timeline switches exist only in diagnostic builds (make ablate: -DSB200_ABLATE -> libspectral_b200_ablate.so);
+// the production library compiles every XF() to false and never reads SB200_XFLAGS.
+#ifdef SB200_ABLATE
+#define XF(p, bit) (((p).xflags & (bit)) != 0)
+#else
+#define XF(p, bit) false
+#endif
+
 #ifdef SB200_TRACE
 #define STAMP(k) do { if (lane == 0 && p.trace) tr[k] = clock64(); } while (0)
 #else
@@ -36,7 +44,7 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 __device__ __forceinline__ void tl_stamp(const PersistParams& p, int slot) {
-  if (!(p.xflags & 64) || p.epoch != p.tl_epoch) return;
+  if (!XF(p, 64) || p.epoch != p.tl_epoch) return;
   unsigned long long* ts = reinterpret_cast<unsigned long long*>(p.sync) + 16;
   const unsigned long long t = gtime();
   atomicMin(ts + 2 * slot, t);
@@ -128,7 +136,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   const double* __restrict__ g0 = PENCIL ? p.g0_p : p.g0[axis];
   const double* __restrict__ eta_a = PENCIL ? p.eta_p : p.eta;
   const double* __restrict__ deta_a = PENCIL ? p.deta_p : p.deta;
-  const double* __restrict__ etap = (p.xflags & 1) ? nullptr : eta_a;
+  const double* __restrict__ etap = XF(p, 1) ? nullptr : eta_a;
 #ifdef SB200_TRACE
   long long* tr = p.trace ? p.trace + ((long long)axis * (p.nlines / (8 * NT)) + n0 / (8 * NT)) * 8 : nullptr;
   if (lane == 0 && p.trace) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); tr[6] = smid; tr[7] = threadIdx.x >> 5; }
@@ -177,7 +185,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   __syncwarp();  // block free again (the caller refills it while the epilogue drains)
   STAMP(4);
 
-  if (p.xflags & 2) {
+  if (XF(p, 2)) {
     // experiment: no epilogue traffic (keep one dependent store so the GEMM is not dead code)
     if (a[0][0][0] + b[0][0][0] == 12345.678) p.V[0] = 1.0;
   } else if (PENCIL) {
@@ -189,7 +197,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
 #pragma unroll
       for (int i = 0; i < E::MT; i++) {
         const int mt = i * 8 + g, mb = P - 1 - mt;
-        const int qt = (p.xflags & 16) ? p.rank : mt >> p.lognloc, qb = (p.xflags & 16) ? p.rank : mb >> p.lognloc;
+        const int qt = XF(p, 16) ? p.rank : mt >> p.lognloc, qb = XF(p, 16) ? p.rank : mb >> p.lognloc;
         st2(p.part0peer[qt] + (long long)(mt - qt * nloc) * p.R0 + col, a[j][i][0] + b[j][i][0], a[j][i][1] + b[j][i][1]);
         st2(p.part0peer[qb] + (long long)(mb - qb * nloc) * p.R0 + col, b[j][i][0] - a[j][i][0], b[j][i][1] - a[j][i][1]);
       }
@@ -215,7 +223,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
         const long long t0 = clock64();
         while (*reinterpret_cast<volatile unsigned*>(p.sync + 6) < p.nlocal_items) {
           if (clock64() - t0 > SB200_SPIN_LIMIT) {
-            atomicAdd(p.sf.f[p.rank] + SYMM_TIMEOUT, 1ull);
+            symm_record_timeout(p.sf.f[p.rank]);
             break;
           }
         }
@@ -223,7 +231,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
       }
       __syncwarp();
     }
-    if (WAITDONE && !(p.xflags & 8)) {
+    if (WAITDONE && !XF(p, 8)) {
       if (lane == 0) tl_stamp(p, 6);
       if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_DONE + lane, p.epoch, p.sf.f[p.rank]);
       __syncwarp();
@@ -432,7 +440,7 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
       return;
     }
     if (SLAB && !LASTPHASE && tk >= nlocal) {
-      if (!peers_ready && !(p.xflags & 4)) {
+      if (!peers_ready && !XF(p, 4)) {
         // every rank must have pushed its planes of the padded input into this rank's pencil
         if (lane < p.nranks) spin_until(p.sf.f[p.rank] + SYMM_READY + lane, p.epoch, p.sf.f[p.rank]);
         __syncwarp();
@@ -573,7 +581,7 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (p.nranks > 1) {
-    if (!(p.xflags & 32)) {
+    if (!XF(p, 32)) {
       int blocks = sms;
       if (const char* mc = getenv("SB200_MAX_CTAS")) blocks = atoi(mc) > 0 ? atoi(mc) : blocks;
       stage_kernel<P><<<blocks, 128, 0, s>>>(p);
@@ -610,8 +618,12 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
     stg = g ? atoi(g) : 6000;
   }
   p.stagger = stg;
+#ifdef SB200_ABLATE
   const char* xf = getenv("SB200_XFLAGS");
   p.xflags = xf ? atoi(xf) : 0;
+#else
+  p.xflags = 0;
+#endif
   SB_CHECK(p.nlines % 16 == 0, SB200_ERR_SUP, "persistent path: line count must be a multiple of 16");
   switch (P) {
     case 32: return run_cfg<32, 16, 1>(p, s);

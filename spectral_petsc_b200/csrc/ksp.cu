@@ -459,6 +459,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
     if (done) break;
   }
   SB_CUDA(cudaStreamSynchronize(s));
+  SB_CHECK(!arena.failed(), SB200_ERR_CUDA, "KSPSolve: a device-side flag wait (all-reduce / barrier over the slab ranks) timed out; the result is undefined");
   return 0;
 }
 

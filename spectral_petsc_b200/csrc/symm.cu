@@ -34,6 +34,14 @@ int SymmArena::init(size_t nbytes, int rank_, int nranks_) {
   bytes = nbytes + SYMM_NFLAGS * sizeof(unsigned long long) + 4096;
   SB_CUDA(cudaMalloc((void**)&base, bytes));
   SB_CUDA(cudaMemset(base, 0, SYMM_NFLAGS * sizeof(unsigned long long)));
+  SB_CUDA(cudaHostAlloc((void**)&h_fail, sizeof(unsigned long long), cudaHostAllocMapped));
+  *h_fail = 0;
+  {
+    unsigned long long* d_fail = nullptr;
+    SB_CUDA(cudaHostGetDevicePointer((void**)&d_fail, h_fail, 0));
+    const unsigned long long v = (unsigned long long)(uintptr_t)d_fail;
+    SB_CUDA(cudaMemcpy(base + SYMM_HOSTFAIL * sizeof(unsigned long long), &v, sizeof(v), cudaMemcpyHostToDevice));
+  }
   SB_CUDA(cudaDeviceSynchronize());
   used = (SYMM_NFLAGS * sizeof(unsigned long long) + 255) / 256 * 256;
   for (int q = 0; q < SB200_MAX_RANKS; q++) {
@@ -49,6 +57,8 @@ void SymmArena::destroy() {
     if (opened[q] && peer[q]) cudaIpcCloseMemHandle(peer[q]);
   if (base) cudaFree(base);
   base = nullptr;
+  if (h_fail) cudaFreeHost(h_fail);
+  h_fail = nullptr;
 }
 
 void* SymmArena::alloc(size_t nbytes) {

@@ -20,6 +20,7 @@ enum SymmFlag {
   SYMM_READY = 8,   // [8..15]  fused MatMult: peer q's staged input vector is ready
   SYMM_DONE = 16,   // [16..23] fused MatMult: peer q has pushed all its axis-0 results
   SYMM_TIMEOUT = 24,  // number of flag waits that gave up (0 in a healthy run)
+  SYMM_HOSTFAIL = 25, // device address of a host-mapped word that a timed-out wait sets (sticky failure seen by the host without a sync)
   SYMM_AR = 32,       // [32..39] small all-reduce (KSP dot products): peer q's contribution is in my slot q
   SYMM_NFLAGS = 48,
 };
@@ -31,6 +32,7 @@ struct SymmArena {
   char* peer[SB200_MAX_RANKS] = {};  // peer[rank] == base; others set by attach()
   bool opened[SB200_MAX_RANKS] = {};
   unsigned long long bar_epoch = 0;
+  unsigned long long* h_fail = nullptr;  // pinned, device-mapped: non-zero once any device-side flag wait of this rank has timed out
 
   int init(size_t bytes, int rank, int nranks);
   void destroy();
@@ -51,6 +53,10 @@ struct SymmArena {
   int barrier(cudaStream_t s);
   // Synchronises `s` and returns the number of device-side flag waits that timed out so far.
   int timeouts(cudaStream_t s, unsigned long long* n);
+  // Sticky failure, readable without synchronising: true once a device-side wait has given up (a peer never arrived, or the
+  // ranks' collective calls went out of step).  Every slab entry point checks it first and refuses to run: results after a
+  // timed-out wait are undefined.
+  bool failed() const { return h_fail && *(volatile unsigned long long*)h_fail != 0; }
 };
 
 // Device helpers -----------------------------------------------------------------------------------
@@ -73,13 +79,18 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
 // must not hang the GPU.  After ~4 s the wait gives up and records the failure in the flag block's
 // SYMM_TIMEOUT word (sb200_*_slab_status reports it); results are then undefined but the kernel exits.
 #define SB200_SPIN_LIMIT (1ll << 33)
+__device__ __forceinline__ void symm_record_timeout(unsigned long long* local_flags) {
+  atomicAdd(local_flags + SYMM_TIMEOUT, 1ull);
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(local_flags[SYMM_HOSTFAIL]);
+  if (h) *(volatile unsigned long long*)h = 1ull;  // host-mapped: the next API call on this context fails loudly
+}
 __device__ __forceinline__ void spin_until(const unsigned long long* f, unsigned long long epoch,
                                            unsigned long long* local_flags) {
   if (ld_acquire_sys(f) >= epoch) return;
   const long long t0 = clock64();
   while (ld_acquire_sys(f) < epoch) {
     if (clock64() - t0 > SB200_SPIN_LIMIT) {
-      atomicAdd(local_flags + SYMM_TIMEOUT, 1ull);
+      symm_record_timeout(local_flags);
       return;
     }
   }

@@ -279,6 +279,13 @@ int sb200_vec_remove_mean(long long n, int stride, int offset, double* x, double
   return 0;
 }
 int sb200_stream_sync(void*) { return 0; }
+// measurement helper: the double has no tensor pipe; a nominal figure keeps bench.py's dry run going
+int sb200_fp64_dmma_peak(double, double* tflops, double* measured_ms) {
+  if (!tflops) FAIL(SB200_ERR_ARG, "null pointer");
+  *tflops = 37.1;
+  if (measured_ms) *measured_ms = 0.0;
+  return 0;
+}
 
 // ---- ChebMult -------------------------------------------------------------------------------------------------------------
 int sb200_cheb_create(int rank, int tr, const int* dims, long long n_total, sb200_cheb** out) {
@@ -385,6 +392,7 @@ int sb200_elliptic_matmult(sb200_elliptic* e, const double* U, double* V, void*)
   for (long long q = 0; q < e->g; q++) V[q] = out[e->ixG[q]];
   return 0;
 }
+const char* sb200_elliptic_last_kernel(const sb200_elliptic*) { return "cpu test double"; }
 int sb200_elliptic_function(sb200_elliptic* e, const double* U, double* F, void*) {
   if (!U || !F || U == F) FAIL(SB200_ERR_ARG, "FormFunction: U and F must be distinct non-null vectors");
   const long long m = e->m;
