@@ -104,3 +104,34 @@ def test_errors(cuda):
     G = sp.Stokes([6, 6])
     with pytest.raises(sp.SB200Error):
         G.set_rheology(2)
+
+
+@pytest.mark.parametrize("rheology", [0, 1])
+def test_full_size_128(cuda, rheology):
+    """BASELINE config 5's grid (stokes -rheology 1 -exponent 3 -eps 1e-4 at -dim 128,128,128): StokesFunction (with its cached
+    eta / deta / strain) and StokesMatMult against the oracle at the full size - the eo_deriv_kernel<128,...> instantiations on the
+    AoS velocity layout inside the Stokes composition."""
+    dim = [128, 128, 128]
+    O, G, U, U2 = make_pair(dim, cuda, rheology=rheology, exponent=3.0, eps=1e-4)
+    xs = 0.3 * np.random.default_rng(1).standard_normal(O.g)
+    Fo = O.function(xs)
+    Fg = G.function(torch.from_numpy(xs).to(cuda))
+    assert rel_max(Fg.cpu().numpy(), Fo) < TOL
+    assert rel_max(G.get_state(0).cpu().numpy(), O.eta) < 1e-12
+    for j in range(O.d):
+        assert rel_max(G.get_state(2 + j).cpu().numpy(), O.strain[j].reshape(-1)) < TOL
+    x = np.random.default_rng(0).standard_normal(O.g)
+    yo = O.mat_mult(x)
+    xd = torch.from_numpy(x).to(cuda)
+    y0 = G.mat_mult(xd).clone()
+    assert rel_max(y0.cpu().numpy(), yo) < TOL
+    # the two evaluation switches at the full size (same operator: tests/test_zz4_gpu_optins.py has the small grids)
+    for trace, fold in ((True, False), (False, True), (True, True)):
+        G.set_trace_divergence(trace)
+        G.set_fold_pressure(fold)
+        assert rel_max(G.mat_mult(xd).cpu().numpy(), yo) < TOL
+        assert rel_max(G.function(torch.from_numpy(xs).to(cuda)).cpu().numpy(), Fo) < TOL
+    G.set_trace_divergence(False)
+    G.set_fold_pressure(False)
+    assert torch.equal(G.mat_mult(xd), y0)
+    G.destroy()
