@@ -392,8 +392,8 @@ int main(int argc, char** argv) {
   CHK(StokesCreate(PETSC_COMM_SELF, &opt, &F.A, &x, &F.ctx));
   F.d = d;
   // not options of the reference: how this implementation evaluates StokesMatMult / StokesFunction (same operator either way)
-  CHK(sb200_stokes_set_trace_divergence(StokesGetHandle(F.ctx), o.integer("sb200_trace_divergence", 0)));
-  CHK(sb200_stokes_set_fold_pressure(StokesGetHandle(F.ctx), o.integer("sb200_fold_pressure", 0)));
+  CHK(sb200_stokes_set_trace_divergence(StokesGetHandle(F.ctx), o.integer("sb200_trace_divergence", 1)));
+  CHK(sb200_stokes_set_fold_pressure(StokesGetHandle(F.ctx), o.integer("sb200_fold_pressure", 1)));
   CHK(sb200_stokes_set_graph(StokesGetHandle(F.ctx), o.integer("sb200_graph", 0)));  // shells replayed from CUDA graphs (small grids)
   CHK(StokesGetSizes(F.ctx, &F.m, &F.g, &F.gp, &F.gv, &F.dv));
   CHK(StokesGetShells(F.ctx, &F.MatVV, &F.MatPV, &F.MatVP, &F.MatSchur));

@@ -254,6 +254,101 @@ def parity_check(G, U, V, torch, dist, world, rank, dev):
             "checked": "V of the last timed application on every rank vs the oracle's single-domain MatMult_Elliptic (max-norm relative, max over ranks)"}
 
 
+STOKES_WORKLOAD = "stokes -rheology 1 -exponent 3 -eps 1e-4 at -dim 128,128,128: StokesMatMult (BASELINE config 5's operator)"
+
+
+def stokes_secondary(sp, torch, dist, world, rank, dev, steps):
+    """BASELINE config 5 at EVERY N (row g1 of the round-1 verdict): StokesMatMult (stokes.C:499-519) on the 128^3 grid with the
+    power-law rheology state of one StokesFunction call, slab-partitioned over the N ranks; device-resident GDOF/s (4 DOF per node,
+    per-step CUDA events, L2 flushed between steps, max over ranks) and hardware parity of the timed result against the oracle's
+    single-domain StokesMatMult (rank 0 computes it once - the oracle is the checker, nothing timed - and broadcasts it).
+    Every rank reaches every collective whatever fails locally (a failure is reported in the object, never raised)."""
+    out = {"workload": STOKES_WORKLOAD, "n_gpus": world}
+    dim, err, S = DIM, None, None
+    m = int(np.prod(dim))
+    gtot = 4 * int(np.prod([p - 2 for p in dim]))
+    ms_local, rel_local, tmo_local = 1e30, 1e30, 0.0
+    y = None
+    try:
+        S = sp.Stokes(dim, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0, rank=rank, nranks=world)
+        if world > 1:
+            from spectral_petsc_b200 import dist as spd
+
+            spd.attach_peers(S)
+        S.set_dirichlet(torch.zeros(S.dv, dtype=torch.float64, device=dev))
+        S.set_force(torch.zeros(S.g, dtype=torch.float64, device=dev))
+        sl = slice(4 * S.goff, 4 * S.goff + S.g) if world > 1 else slice(0, S.g)
+        xs = torch.from_numpy(0.1 * np.random.default_rng(1).standard_normal(gtot)[sl].copy()).to(dev)
+        x = torch.from_numpy(np.random.default_rng(0).standard_normal(gtot)[sl].copy()).to(dev)
+        y = torch.empty_like(x)
+        S.function(xs, y)  # eta / deta / strain of the power-law state
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            S.mat_mult(x, y)
+        torch.cuda.synchronize()
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, e)
+    if world > 1:
+        dist.barrier()
+    if err is None:
+        try:
+            l0 = sp.launch_count()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a, b in ev:
+                flush.zero_()
+                a.record()
+                S.mat_mult(x, y)
+                b.record()
+            torch.cuda.synchronize()
+            ms_local = sum(a.elapsed_time(b) for a, b in ev) / steps
+            out["launches_per_step"] = (sp.launch_count() - l0) // steps
+            tmo_local = float(S.slab_timeouts()) if world > 1 else 0.0
+        except Exception as e:
+            err = "%s: %s" % (type(e).__name__, e)
+    # parity: the oracle's single-domain result of the same application
+    yo = torch.zeros(gtot, dtype=torch.float64, device=dev)
+    oerr = None
+    if rank == 0:
+        try:
+            # in a fresh process whose environment lets the FFT thread pool use every host core (see _oracle_child)
+            with tempfile.TemporaryDirectory() as td:
+                f = os.path.join(td, "stokes_oracle.npy")
+                env = dict(os.environ)
+                env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "stokes_oracle", "--out", f], capture_output=True, text=True,
+                                   env=env, cwd=ROOT, timeout=600)
+                if r.returncode != 0:
+                    raise RuntimeError("oracle child failed: " + (r.stderr or r.stdout)[-300:])
+                yo.copy_(torch.from_numpy(np.load(f)))
+        except Exception as e:
+            oerr = "%s: %s" % (type(e).__name__, e)
+    if world > 1:
+        dist.broadcast(yo, src=0)
+    scale = float(yo.abs().max())
+    if err is None and scale > 0:
+        rel_local = float((y - yo[sl]).abs().max()) / scale if y.numel() else 0.0
+        if not bool(torch.isfinite(y).all()):
+            rel_local = 1e30
+    t = torch.tensor([ms_local, rel_local, tmo_local, 1.0 if err else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, rel, tmo, bad = t.tolist()
+    if S is not None:
+        try:
+            S.destroy()
+        except Exception:
+            pass
+    if bad or oerr or scale == 0:
+        out["error"] = err or oerr or "a rank failed (see its stderr)"
+        return out
+    fl = 24 * 2.0 * dim[0] * m  # SURVEY 8(d): 24 scalar axis-derivatives of 2P flop per node (18 executed: trace + folded pressure)
+    out.update({"value": 4 * m / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps, "n_dof_per_step": 4 * m,
+                "algorithmic_flops_per_step": fl, "achieved_tflops": fl / ms / 1e9,
+                "parity": {"rel": rel, "tol": PARITY_TOL, "timeouts": int(tmo), "ok": bool(rel < PARITY_TOL and tmo == 0),
+                           "checked": "y of the last timed StokesMatMult on every rank vs the oracle's single-domain StokesMatMult (max-norm relative, max over ranks)"}})
+    return out
+
+
 def ksp_secondary(sp, torch, dev, G128, U128):
     """Secondary metric of BASELINE.json: 'KSP time to rtol 1e-10'.
     (a) config 1, ./elliptic -dim 16,16,16 -exact 2 -ksp_rtol 1e-10: device FGMRES(30) on the MatShell; the preconditioning
@@ -422,8 +517,17 @@ def run_child(name, limit_s):
         return {"error": "child '%s' printed no JSON: %s" % (name, e)}
 
 
-def child_main(name):
+def child_main(name, out=None):
     """The body of `bench.py --child NAME` (N = 1 only): prints ONE JSON value."""
+    if name == "stokes_oracle":
+        # the checker of stokes_secondary: the oracle's single-domain StokesMatMult on the bench's synthetic vectors (CPU only)
+        from oracle.stokes import StokesCtx
+
+        gtot = 4 * int(np.prod([p - 2 for p in DIM]))
+        O = StokesCtx(DIM, rheology=1, hardness=1.0, exponent=3.0, regularization=1e-4, gamma0=1.0, workers=os.cpu_count() or 1)
+        O.function(0.1 * np.random.default_rng(1).standard_normal(gtot))
+        np.save(out, O.mat_mult(np.random.default_rng(0).standard_normal(gtot)))
+        return 0
     import torch
 
     import spectral_petsc_b200 as sp
@@ -588,6 +692,16 @@ def run_cuda(args):
     if any_queue_bad:  # some rank fell back: the job-wide figure is the blocking call's
         e2e_ms, queue_ok = e2e_sync_ms, False
 
+    # ---- BASELINE config 5's operator at this N (after and outside the headline's timed regions; collective: every rank takes part) ----
+    stokes = None
+    if not getattr(args, "no_stokes", False):
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            stokes = stokes_secondary(sp, torch, dist, world, rank, dev, max(args.steps // 2, 5))
+        except Exception as e:  # (only a failure of a collective itself lands here)
+            stokes = {"workload": STOKES_WORKLOAD, "error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         ndof = m_global  # one global operator application per step, whatever the number of ranks
         value = ndof * args.steps / (total_ms * 1e-3) / 1e9
@@ -617,6 +731,10 @@ def run_cuda(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if stokes is not None:
+            if "value" in stokes:
+                stokes["frac_of_fp64_roofline"] = stokes["achieved_tflops"] / (fp64_peak * world)
+            line["stokes"] = stokes
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         # The per-P table of SURVEY 8d + set-up kernels (tools/p_sweep.py) and the secondary KSP metric run AFTER and OUTSIDE every timed
@@ -645,10 +763,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-P sweep (ChebMult, MatMult_Elliptic on every path, device FormJacobian)")
     ap.add_argument("--no-ksp", action="store_true", help="skip the secondary 'KSP time to rtol 1e-10' measurement")
-    ap.add_argument("--child", default=None, choices=["p_sweep", "ksp"], help=argparse.SUPPRESS)
+    ap.add_argument("--no-stokes", action="store_true", help="skip the StokesMatMult 128^3 object (BASELINE config 5's operator at this N, with its parity check)")
+    ap.add_argument("--child", default=None, choices=["p_sweep", "ksp", "stokes_oracle"], help=argparse.SUPPRESS)
+    ap.add_argument("--out", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.child:
-        return child_main(args.child)
+        return child_main(args.child, args.out)
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)

@@ -178,11 +178,11 @@ int sb200_stokes_matmult_pv(sb200_stokes* s, const double* d_x, double* d_y, voi
 /* StokesDivergence(ctx, withDirichlet, xG, yG) (stokes.C:570-595): the same with the Dirichlet velocities inserted on the boundary
  * when with_dirichlet != 0 (what the residual uses, :746); with_dirichlet = 0 is StokesMatMultPV. */
 int sb200_stokes_divergence(sb200_stokes* s, int with_dirichlet, const double* d_x, double* d_y, void* stream);
-/* Opt-in (default 0): StokesMatMult and StokesFunction take their pressure rows  sum_i D_i v_i  from the trace of the velocity
+/* Evaluation switch (default 1 since round 2; 0 = the reference's literal sequence): StokesMatMult and StokesFunction take their pressure rows  sum_i D_i v_i  from the trace of the velocity
  * gradient their viscous part computes anyway, instead of running StokesDivergence on the same input a second time
  * (stokes.C:509,746); same values bit for bit, one pad pass and d derivative passes fewer per application. */
 int sb200_stokes_set_trace_divergence(sb200_stokes* s, int on);
-/* Opt-in (default 0): StokesMatMult and StokesFunction subtract the boundary-extrapolated pressure from the diagonal of the viscous
+/* Evaluation switch (default 1 since round 2): StokesMatMult and StokesFunction subtract the boundary-extrapolated pressure from the diagonal of the viscous
  * flux (the stress eta*eps - p I), so the divergence of the viscous part also produces the pressure gradient of StokesMatMultVP
  * (stokes.C:512-513,747-750): d derivative passes and one read-modify-write crop fewer.  Same operator, ~1e-15 relative rounding
  * difference (the two terms are summed before the derivative instead of after). */

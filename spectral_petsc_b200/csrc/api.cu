@@ -162,8 +162,9 @@ int sb200_cheb_apply(sb200_cheb* c, const double* d_x, double* d_y, void* stream
   SB_CHECK(c && d_x && d_y, SB200_ERR_ARG, "null pointer");
   DerivParams p;
   p.D = c->D.d_D;
-  p.Ae = c->D.d_Ae;
-  p.Bo = c->D.d_Bo;
+  p.Ae = c->D.d_Aep;
+  p.Bo = c->D.d_Bop;
+  p.HP = c->D.HP;
   p.sync = c->sync;
   p.P = c->D.P;
   p.Pp = c->D.Pp;

@@ -55,4 +55,25 @@ void cgl_even_odd(int P, std::vector<double>& Ae, std::vector<double>& Bo) {
     }
 }
 
+// Any P >= 2: hh = ceil(P/2) pair rows (pair j couples nodes j and n-j; for odd P the last pair is the middle node
+// with itself), zero padded to HP x HP.  With s_j = u_j + u_{n-j}, d_j = u_j - u_{n-j} formed for EVERY pair the same way, the
+// self-paired middle node gives s = 2 u_c, d = 0, so its column of Ae carries D[i][c]/2 (an exact scaling) and its column of Bo
+// is zero; the middle ROW has a = 0 identically (D[c][n-j] = -D[c][j]) and is set to zero, its value is b alone.
+void cgl_even_odd_padded(int P, int HP, std::vector<double>& Ae, std::vector<double>& Bo) {
+  const int n = P - 1, hh = (P + 1) / 2;
+  std::vector<long double> L = cgl_diff_matrix_ld(P);
+  Ae.assign((size_t)HP * HP, 0.0);
+  Bo.assign((size_t)HP * HP, 0.0);
+  for (int i = 0; i < hh; i++)
+    for (int j = 0; j < hh; j++) {
+      const long double p = L[(size_t)i * P + j], q = L[(size_t)i * P + (n - j)];
+      const bool midcol = (j == n - j), midrow = (i == n - i);
+      long double a = 0.5L * (p + q), b = 0.5L * (p - q);
+      if (midcol) { a = 0.5L * p; b = 0.0L; }
+      if (midrow) a = 0.0L;
+      Ae[(size_t)i * HP + j] = (double)a;
+      Bo[(size_t)i * HP + j] = (double)b;
+    }
+}
+
 }  // namespace sb200

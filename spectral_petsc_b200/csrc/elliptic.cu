@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/spectral_b200.h"
@@ -110,6 +111,23 @@ __global__ void flux_kernel(long long m, int d, const double* __restrict__ u, co
   }
 }
 
+// The same with u taken from the GLOBAL vector (zero on the boundary): the fused generic path never materialises the padded field.
+__global__ void flux_global_kernel(GridDesc gd, int d, const double* __restrict__ U, const double* __restrict__ eta,
+                                   const double* __restrict__ deta, FluxPtrs fp) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int PL = gd.dim[d - 1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < gd.m; i += stride) {
+    const long long line = i / PL;
+    const int k = (int)(i - line * PL);
+    const LineInfo li = decode_line(gd, line);
+    const double ui = (li.interior && k > 0 && k < PL - 1) ? U[li.gid0 + k - 1] : 0.0;
+    const double e = eta[i], de = deta[i];
+    for (int q = 0; q < d; q++) {
+      fp.w[q][i] = __dadd_rn(__dmul_rn(e, fp.w[q][i]), __dmul_rn(__dmul_rn(de, ui), fp.g0[q][i]));
+    }
+  }
+}
+
 // elliptic.C:507-513: eta = 1 + gamma*pow(u,p); deta = p*gamma*pow(u,p-1); w[d] = eta*gradu[d]
 __global__ void coef_flux_kernel(long long m, int d, double gamma, double expo, const double* __restrict__ u,
                                  double* __restrict__ eta, double* __restrict__ deta, FluxPtrs fp) {
@@ -149,6 +167,15 @@ int DiffMatrix::create(int P, DiffMatrix* out) {
     SB_CUDA(cudaMemcpy(out->d_Ae, Ae.data(), Ae.size() * sizeof(double), cudaMemcpyHostToDevice));
     SB_CUDA(cudaMemcpy(out->d_Bo, Bo.data(), Bo.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
+  if (P <= SB200_EO_MAX_P) {
+    out->HP = ((P + 1) / 2 + 7) / 8 * 8;
+    std::vector<double> Ae, Bo;
+    cgl_even_odd_padded(P, out->HP, Ae, Bo);
+    SB_CUDA(cudaMalloc((void**)&out->d_Aep, Ae.size() * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&out->d_Bop, Bo.size() * sizeof(double)));
+    SB_CUDA(cudaMemcpy(out->d_Aep, Ae.data(), Ae.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(out->d_Bop, Bo.data(), Bo.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -156,7 +183,9 @@ void DiffMatrix::destroy() {
   if (d_D) cudaFree(d_D);
   if (d_Ae) cudaFree(d_Ae);
   if (d_Bo) cudaFree(d_Bo);
-  d_D = d_Ae = d_Bo = nullptr;
+  if (d_Aep) cudaFree(d_Aep);
+  if (d_Bop) cudaFree(d_Bop);
+  d_D = d_Ae = d_Bo = d_Aep = d_Bop = nullptr;
 }
 
 int GridDesc::init(int d_, const int* dim_) {
@@ -279,11 +308,81 @@ EllipticCtx::~EllipticCtx() {
   }
 }
 
+// Single GPU, rank <= SB200_EO_MAX_JOBS, every extent within the even-odd kernel's reach: the generic path runs as
+// [gradient batch with the pad in its loader] -> flux -> [divergence batch with the "-=" chain and the crop in its epilogue].
+bool EllipticCtx::fusable() const {
+  static int use = -1;
+  if (use < 0) {
+    const char* c = getenv("SB200_NO_EO");
+    const char* f = getenv("SB200_NO_FUSE");
+    use = ((c && atoi(c)) || (f && atoi(f))) ? 0 : 1;
+  }
+  if (!use || arena.nranks > 1 || gd.d > SB200_EO_MAX_JOBS) return false;
+  for (int k = 0; k < gd.d; k++)
+    if (!deriv_eo_supported(job(k, w[0], w[1], nullptr, DERIV_STORE))) return false;
+  return true;
+}
+
+EoLineMap EllipticCtx::line_map(int axis) const {
+  EoLineMap lm;
+  lm.d = gd.d;
+  lm.nc = 1;
+  lm.axis = axis;
+  for (int j = 0; j < gd.d; j++) {
+    lm.dim[j] = gd.dim[j];
+    lm.istride[j] = gd.istride[j];
+  }
+  return lm;
+}
+
+DerivParams EllipticCtx::job(int axis, const double* x, double* y, const double* yin, int mode) const {
+  DerivParams p;
+  p.D = Dax[axis]->d_D;
+  p.Ae = Dax[axis]->d_Aep;
+  p.Bo = Dax[axis]->d_Bop;
+  p.HP = Dax[axis]->HP;
+  p.sync = sync + 10;  // counters of the even-odd derivative kernel ([0..5]: persistent chain phases, [8]: stage)
+  p.P = Dax[axis]->P;
+  p.Pp = Dax[axis]->Pp;
+  p.x = x;
+  p.y = y;
+  p.yin = yin;
+  p.O = gd.m / (gd.stride[axis] * gd.dim[axis]);
+  p.R = gd.stride[axis];
+  p.xs = p.ys = 1;
+  p.xoff = p.yoff = 0;
+  p.mode = mode;
+  return p;
+}
+
+// The divergence half of both shells on the fused path: T_k = D_k w[1+k] in place for k < d-1, the last axis' epilogue forms
+// ((0 - T_0) - T_1 ...) - D_{d-1} w[d] (elliptic.C:329-334 / 520-524), subtracts rhs when given (:530) and scatters (:336-337).
+int EllipticCtx::fused_tail(const double* rhs, double* V, cudaStream_t s) {
+  const int d = gd.d;
+  DerivParams jobs[SB200_EO_MAX_JOBS];
+  for (int k = 0; k < d - 1; k++) {
+    jobs[k] = job(k, w[1 + k], w[1 + k], nullptr, DERIV_STORE);
+    jobs[k].inplace_ok = 1;
+  }
+  DerivParams& f = jobs[d - 1] = job(d - 1, w[d], nullptr, nullptr, DERIV_STORE);
+  f.lm = line_map(d - 1);
+  f.gdst = V;
+  f.gd_stride = 1;
+  f.gd_off = 0;
+  f.fin = EO_FIN_SUM;
+  f.nterms = d - 1;
+  for (int k = 0; k < d - 1; k++) f.term[k] = w[1 + k];
+  f.sign = -1.0;
+  f.sub = rhs;
+  return deriv_eo_jobs(jobs, d, sync + 10, s);
+}
+
 int EllipticCtx::deriv(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s) {
   DerivParams p;
   p.D = Dax[axis]->d_D;
-  p.Ae = Dax[axis]->d_Ae;
-  p.Bo = Dax[axis]->d_Bo;
+  p.Ae = Dax[axis]->d_Aep;
+  p.Bo = Dax[axis]->d_Bop;
+  p.HP = Dax[axis]->HP;
   p.sync = sync + 10;  // counters of the even-odd derivative kernel ([0..5]: persistent chain phases, [8]: stage)
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
@@ -400,6 +499,31 @@ int EllipticCtx::matmult_graph(const double* U, double* V, cudaStream_t s) {
 
 int EllipticCtx::matmult_generic(const double* U, double* V, cudaStream_t s) {
   const int d = gd.d;
+  if (fusable()) {
+    // 3 launches whatever the rank on small (launch-bound) grids: the gradient's loaders read U itself with the zero Dirichlet
+    // rows filled in (:305-311); large grids keep the padded copy (4 launches)
+    const bool fuse_pad = gd.m <= SB200_FUSE_PAD_MAX_NODES;
+    if (!fuse_pad) SB_TRY(pad(U, false, w[0], s));
+    DerivParams jobs[SB200_EO_MAX_JOBS];
+    FluxPtrs fp;
+    for (int k = 0; k < d; k++) {
+      jobs[k] = job(k, fuse_pad ? nullptr : w[0], w[1 + k], nullptr, DERIV_STORE);
+      if (fuse_pad) {
+        jobs[k].lm = line_map(k);
+        jobs[k].gsrc = U;
+        jobs[k].gs_stride = 1;
+        jobs[k].gs_off = 0;
+      }
+      fp.w[k] = w[1 + k];
+      fp.g0[k] = gradu[k];
+    }
+    SB_TRY(deriv_eo_jobs(jobs, d, sync + 10, s));
+    if (fuse_pad) flux_global_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, d, U, eta, deta, fp);  // :319-323
+    else flux_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd.m, d, w[0], eta, deta, fp);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+    return fused_tail(nullptr, V, s);  // :329-337
+  }
   SB_TRY(pad(U, false, w[0], s));                                              // :305-308
   for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], w[1 + k], nullptr, DERIV_STORE, s));  // :309-311
   FluxPtrs fp;
@@ -420,7 +544,14 @@ int EllipticCtx::function(const double* U, double* F, cudaStream_t s) {
   SB_CHECK(U && F && U != F, SB200_ERR_ARG, "FormFunction: U and F must be distinct non-null vectors");
   const int d = gd.d;
   SB_TRY(pad(U, true, w[0], s));                                                   // :489-492
-  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], gradu[k], nullptr, DERIV_STORE, s));  // :497-499
+  const bool fused = fusable();
+  if (fused) {
+    DerivParams jobs[SB200_EO_MAX_JOBS];
+    for (int k = 0; k < d; k++) jobs[k] = job(k, w[0], gradu[k], nullptr, DERIV_STORE);
+    SB_TRY(deriv_eo_jobs(jobs, d, sync + 10, s));
+  } else {
+    for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[0], gradu[k], nullptr, DERIV_STORE, s));  // :497-499
+  }
   FluxPtrs fp;
   for (int k = 0; k < d; k++) {
     fp.w[k] = w[1 + k];
@@ -429,8 +560,12 @@ int EllipticCtx::function(const double* U, double* F, cudaStream_t s) {
   coef_flux_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd.m, d, gamma, exponent, w[0], eta, deta, fp);  // :506-513
   count_launch();
   SB_CUDA(cudaGetLastError());
-  for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[1 + k], w[0], k == 0 ? nullptr : w[0], DERIV_SUB, s));  // :520-524
-  SB_TRY(crop(w[0], b, F, s));  // :528-531
+  if (fused) {
+    SB_TRY(fused_tail(b, F, s));  // :520-531
+  } else {
+    for (int k = 0; k < d; k++) SB_TRY(deriv(k, w[1 + k], w[0], k == 0 ? nullptr : w[0], DERIV_SUB, s));  // :520-524
+    SB_TRY(crop(w[0], b, F, s));  // :528-531
+  }
   pencil_valid = false;         // eta / deta / gradu[0] changed: the axis-0 pencil copies are stale
   return 0;
 }

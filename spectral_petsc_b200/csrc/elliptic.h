@@ -7,6 +7,7 @@
 #include "symm.h"
 
 #define SB200_MAX_DIM 10  // elliptic.C:138 "Maximum number of dimensions"
+#define SB200_EO_MAX_P 160  // largest extent the generalised even-odd derivative kernel holds in shared memory (deriv_eo.cu)
 
 namespace sb200 {
 
@@ -16,6 +17,11 @@ struct DiffMatrix {
   double* d_D = nullptr;
   double* d_Ae = nullptr;  // even-odd halves (P even), [P/2][P/2] row-major
   double* d_Bo = nullptr;
+  // any P <= SB200_EO_MAX_P: the even-odd halves zero padded to HP x HP, HP = 8 * ceil(ceil(P/2) / 8) (cheb_matrix.h); for
+  // P % 16 == 0 the same numbers as d_Ae / d_Bo
+  int HP = 0;
+  double* d_Aep = nullptr;
+  double* d_Bop = nullptr;
   static int create(int P, DiffMatrix* out);
   void destroy();
 };
@@ -73,6 +79,10 @@ struct EllipticCtx {
   ~EllipticCtx();
   int refresh_pencils(cudaStream_t s);
   int deriv(int axis, const double* x, double* y, const double* yin, int mode, cudaStream_t s);
+  bool fusable() const;
+  struct EoLineMap line_map(int axis) const;
+  struct DerivParams job(int axis, const double* x, double* y, const double* yin, int mode) const;
+  int fused_tail(const double* rhs, double* V, cudaStream_t s);
   int pad(const double* U, bool with_dirichlet, double* local, cudaStream_t s);
   int crop(const double* local, const double* rhs, double* V, cudaStream_t s);
   int matmult(const double* U, double* V, cudaStream_t s);

@@ -32,9 +32,10 @@ __device__ __forceinline__ NodeInfo decode_node(const GridDesc& gd, long long id
   // view axis-0 indices are global (offset gd.i0 inside gd.n0g) and the ordinals are local to this rank
   long long rem = idx, cnt = -gd.goff;
   bool prefix_int = true, bdy = false;
+  const bool small = gd.m < (1ll << 31);  // 32-bit divisions are several times cheaper than 64-bit ones
   for (int j = 0; j < gd.d; j++) {
     const long long s = gd.stride[j];
-    const int il = (int)(rem / s);
+    const int il = small ? (int)((unsigned)rem / (unsigned)s) : (int)(rem / s);
     rem -= (long long)il * s;
     const int i = gd.gidx(j, il), ext = gd.gext(j);
     const bool b = (i == 0) || (i == ext - 1);
@@ -54,16 +55,31 @@ __device__ __forceinline__ NodeInfo decode_node(const GridDesc& gd, long long id
 }
 
 // local[node*nc + k] = interior ? src[gid*sstride + soff + k] : (dir ? dir[did*nc + k] : 0)
-__global__ void pad_nodes_kernel(GridDesc gd, int nc, const double* __restrict__ src, int sstride, int soff,
+// Four nodes per thread and pass, all their loads issued before the first store (the kernel is latency bound otherwise).
+template <int NC>
+__global__ void pad_nodes_kernel(GridDesc gd, const double* __restrict__ src, int sstride, int soff,
                                  const double* __restrict__ dir, double* __restrict__ local) {
+  constexpr int U = 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
-    const NodeInfo n = decode_node(gd, idx);
-    for (int k = 0; k < nc; k++) {
-      double v;
-      if (n.interior) v = src[n.gid * sstride + soff + k];
-      else v = dir ? dir[n.did * nc + k] : 0.0;
-      local[idx * nc + k] = v;
+  for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < gd.m; idx0 += U * stride) {
+    double v[U][NC];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long idx = idx0 + u * stride;
+      if (idx >= gd.m) continue;
+      const NodeInfo n = decode_node(gd, idx);
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        if (n.interior) v[u][k] = src[n.gid * sstride + soff + k];
+        else v[u][k] = dir ? dir[n.did * NC + k] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long idx = idx0 + u * stride;
+      if (idx >= gd.m) continue;
+#pragma unroll
+      for (int k = 0; k < NC; k++) local[idx * NC + k] = v[u][k];
     }
   }
 }
@@ -128,9 +144,16 @@ struct VPtrs {
 // FOLD (opt-in, StokesCtx::fold_pressure): v_jj -= pl, the boundary-extrapolated local pressure, so that the viscous tail
 // -sum_j D_j V_j also produces the pressure gradient D_i p of StokesMatMultVP (stokes.C:611-614).  FOLD = false compiles to the
 // kernel as it was.
+// Fused divergence rows (StokesCtx::trace_divergence): div[gid*div_stride + div_off] = ((0 + g_00) + g_11) + g_22 at interior nodes,
+// the arithmetic of crop_trace_kernel, taken from the gradient in registers before the flux overwrites it.
+struct DivDst {
+  double* dst;
+  int stride, off;
+};
+
 template <int D, bool FOLD = false>
 __global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, const double* __restrict__ deta, VPtrs<D> p,
-                               const double* __restrict__ pl = nullptr) {
+                               const double* __restrict__ pl, GridDesc gd, DivDst dv) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
     double g[D][D], st[D][D], S0[D][D];
@@ -141,6 +164,15 @@ __global__ void vv_flux_kernel(long long m, const double* __restrict__ eta, cons
         g[j][k] = p.v[j][i * D + k];
         S0[j][k] = p.s[j][i * D + k];
       }
+    if (dv.dst) {
+      const NodeInfo nd = decode_node(gd, i);
+      if (nd.interior) {
+        double tr = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) tr = __dadd_rn(tr, __dmul_rn(1.0, g[j][j]));
+        dv.dst[nd.gid * dv.stride + dv.off] = tr;
+      }
+    }
     double z = 0.0;
 #pragma unroll
     for (int j = 0; j < D; j++)
@@ -192,7 +224,7 @@ __device__ __forceinline__ double atomicMaxD(double* addr, double v) {
 // stokes.C:708-725 + rheology (stokes.C:1920-1944): s = sym(grad v), gamma = 1/2 s:s, eta/deta, V = eta*s, strain = s
 template <int D, bool FOLD = false>
 __global__ void rheology_kernel(long long m, Rheo r, double* __restrict__ eta, double* __restrict__ deta, VPtrs<D> p,
-                                double* __restrict__ minmax, const double* __restrict__ pl = nullptr) {
+                                double* __restrict__ minmax, const double* __restrict__ pl, GridDesc gd, DivDst dv) {
   // p.s[j] (const view) and the written strain are the same arrays: strain is read raw and overwritten
   const long long stride = (long long)gridDim.x * blockDim.x;
   double lmin = DBL_MAX, lmax = -DBL_MAX;
@@ -202,6 +234,15 @@ __global__ void rheology_kernel(long long m, Rheo r, double* __restrict__ eta, d
     for (int j = 0; j < D; j++)
 #pragma unroll
       for (int k = 0; k < D; k++) g[j][k] = p.s[j][i * D + k];
+    if (dv.dst) {
+      const NodeInfo nd = decode_node(gd, i);
+      if (nd.interior) {
+        double tr = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) tr = __dadd_rn(tr, __dmul_rn(1.0, g[j][j]));
+        dv.dst[nd.gid * dv.stride + dv.off] = tr;
+      }
+    }
     double gamma = 0.0;
 #pragma unroll
     for (int j = 0; j < D; j++)
@@ -515,8 +556,9 @@ DerivParams StokesCtx::job_v(int axis, const double* x, double* y, const double*
   // DV[axis]: rank d+1 with trailing component axis of extent d (stokes.C:284-289)
   DerivParams p;
   p.D = Dax[axis]->d_D;
-  p.Ae = Dax[axis]->d_Ae;
-  p.Bo = Dax[axis]->d_Bo;
+  p.Ae = Dax[axis]->d_Aep;
+  p.Bo = Dax[axis]->d_Bop;
+  p.HP = Dax[axis]->HP;
   p.sync = sync;
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
@@ -536,8 +578,9 @@ DerivParams StokesCtx::job_p(int axis, const double* x, int xs, int xoff, double
   // DP[axis] on a scalar field that may live inside an AoS vector (VecStrideGather/Scatter, stokes.C:585,613)
   DerivParams p;
   p.D = Dax[axis]->d_D;
-  p.Ae = Dax[axis]->d_Ae;
-  p.Bo = Dax[axis]->d_Bo;
+  p.Ae = Dax[axis]->d_Aep;
+  p.Bo = Dax[axis]->d_Bop;
+  p.HP = Dax[axis]->HP;
   p.sync = sync;
   p.P = Dax[axis]->P;
   p.Pp = Dax[axis]->Pp;
@@ -580,10 +623,41 @@ bool StokesCtx::batchable() const {
   return deriv_eo_supported(p);
 }
 
-// The d independent derivatives of one stage (all DERIV_STORE).  Single GPU: one batched even-odd launch.  Slab: axis 0
-// goes through the pencils (two pushes over NVLink), the local axes run as one batch.
+// Single GPU, every axis within the even-odd kernel's reach (P <= SB200_EO_MAX_P): the scatters and AXPY chains around the
+// derivatives run inside the derivative launches (fused pad loader, fused crop-sum epilogue; deriv.h), whatever the extents.
+bool StokesCtx::fusable() const {
+  static int use = -1;
+  if (use < 0) {
+    const char* c = getenv("SB200_NO_EO");
+    const char* b = getenv("SB200_NO_BATCH");
+    const char* f = getenv("SB200_NO_FUSE");
+    use = ((c && atoi(c)) || (b && atoi(b)) || (f && atoi(f))) ? 0 : 1;
+  }
+  if (!use || arena.nranks > 1) return false;
+  for (int k = 0; k < gd.d; k++) {
+    DerivParams p = job_p(k, workP[0], 1, 0, workP[1], 1, 0, nullptr, DERIV_STORE);
+    if (!deriv_eo_supported(p)) return false;
+  }
+  return true;
+}
+
+EoLineMap StokesCtx::line_map(int axis, int nc) const {
+  EoLineMap lm;
+  lm.d = gd.d;
+  lm.nc = nc;
+  lm.axis = axis;
+  for (int j = 0; j < gd.d; j++) {
+    lm.dim[j] = gd.dim[j];
+    lm.istride[j] = gd.istride[j];
+  }
+  return lm;
+}
+
+// The d independent derivatives of one stage.  Single GPU: one batched even-odd launch when the axes share the matrix (equal
+// extents), else one launch per axis in order (a job's terms then come from earlier launches).  Slab: axis 0 goes through the
+// pencils (two pushes over NVLink), the local axes run as one batch.
 int StokesCtx::run_jobs(DerivParams* jobs, int d, cudaStream_t s) {
-  if (arena.nranks == 1) return deriv_eo_batch(jobs, d, sync, s);
+  if (arena.nranks == 1) return deriv_eo_jobs(jobs, d, sync, s);
   if (!slab_deriv0_pencil_supported(arena, jobs[0])) {
     SB_TRY(deriv_common(jobs[0], 0, s));
     if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
@@ -614,14 +688,15 @@ int StokesCtx::crop_trace(double* const* grads, double* dst, int dstride, int do
 }
 
 int StokesCtx::pad_vel(const double* src, int sstride, int soff, bool with_dirichlet, double* local, cudaStream_t s) {
-  pad_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, gd.d, src, sstride, soff, with_dirichlet ? dirichlet : nullptr, local);
+  if (gd.d == 2) pad_nodes_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd, src, sstride, soff, with_dirichlet ? dirichlet : nullptr, local);
+  else pad_nodes_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd, src, sstride, soff, with_dirichlet ? dirichlet : nullptr, local);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;
 }
 
 int StokesCtx::pad_pres(const double* src, int sstride, int soff, double* local, cudaStream_t s) {
-  pad_nodes_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, 1, src, sstride, soff, nullptr, local);
+  pad_nodes_kernel<1><<<grid_for(gd.m), 256, 0, s>>>(gd, src, sstride, soff, nullptr, local);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;
@@ -637,6 +712,25 @@ int StokesCtx::crop(int nc, const double* local, double* dst, int dstride, int d
 // y_vel[interior] (=|+=) -sum_j D_j V_j   with V from the pointwise step; shared tail of VV and Function
 int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) {
   const int d = gd.d;
+  if (fusable()) {
+    // one launch: axes 1..d-1 store their terms D_i V_i, then axis 0 - whose 8-line blocks are contiguous in the AoS fields, so its
+    // epilogue reads the terms with 16-byte loads - applies the "-=" chain (stokes.C:668-671) in AXIS order, its own value first,
+    // and scatters into the global vector (:673): the arithmetic of crop_sum_kernel, no separate crop pass
+    double* terms[2] = {workV[0], workV[1]};
+    DerivParams jobs[3];
+    for (int i = 1; i < d; i++) jobs[i - 1] = job_v(i, workV[2 + i], terms[i - 1], nullptr, DERIV_STORE);
+    DerivParams& f = jobs[d - 1] = job_v(0, workV[2], nullptr, nullptr, DERIV_STORE);
+    f.lm = line_map(0, d);
+    f.gdst = dst;
+    f.gd_stride = dstride;
+    f.gd_off = doff;
+    f.fin = EO_FIN_SUM;
+    f.nterms = d - 1;
+    f.self_pos = 0;
+    for (int i = 0; i < d - 1; i++) f.term[i] = terms[i];
+    f.sign = -1.0;
+    return run_jobs(jobs, d, s);
+  }
   if (batchable()) {
     // one launch for the d terms D_i V_i, the "-=" chain (stokes.C:668-671) is applied by the crop in axis order
     double* terms[3] = {workV[0], workV[1], workV[2 + d]};
@@ -654,6 +748,24 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
                                double* div_dst, int div_stride, int div_off, const double* p_local) {
   const int d = gd.d;
   double* xL = workV[0];
+  const bool fused = fusable();
+  if (fused) {
+    // small grids (launch bound): the gradient's loader reads the global vector itself, zero Dirichlet rows filled on the fly
+    // (:635-637 + :639 in one launch); large grids keep the padded copy, whose 16-byte block loads are cheaper than the gather
+    const bool fuse_pad = gd.m <= SB200_FUSE_PAD_MAX_NODES;
+    if (!fuse_pad) SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) {
+      jobs[i] = job_v(i, fuse_pad ? nullptr : xL, workV[2 + i], nullptr, DERIV_STORE);
+      if (fuse_pad) {
+        jobs[i].lm = line_map(i, d);
+        jobs[i].gsrc = x;
+        jobs[i].gs_stride = xstride;
+        jobs[i].gs_off = xoff;
+      }
+    }
+    SB_TRY(run_jobs(jobs, d, s));
+  } else {
   SB_TRY(pad_vel(x, xstride, xoff, false, xL, s));                                             // :635-637
   if (batchable()) {
     DerivParams jobs[3];
@@ -662,17 +774,22 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, workV[2 + i], nullptr, DERIV_STORE, s));  // :639
   }
-  if (div_dst) SB_TRY(crop_trace(&workV[2], div_dst, div_stride, div_off, s));  // before the flux overwrites the gradient
+  }
+  // the divergence rows: inside the flux kernel (from the gradient in its registers) on the fused path, else a pass of their own
+  // before the flux overwrites the gradient - the same arithmetic either way
+  DivDst dv{nullptr, 0, 0};
+  if (div_dst && fused) dv = DivDst{div_dst, div_stride, div_off};
+  else if (div_dst) SB_TRY(crop_trace(&workV[2], div_dst, div_stride, div_off, s));
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    if (p_local) vv_flux_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local);
-    else vv_flux_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+    if (p_local) vv_flux_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local, gd, dv);
+    else vv_flux_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, nullptr, gd, dv);
   } else {
     VPtrs<3> p;
     for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    if (p_local) vv_flux_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local);
-    else vv_flux_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p);
+    if (p_local) vv_flux_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, p_local, gd, dv);
+    else vv_flux_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, eta, deta, p, nullptr, gd, dv);
   }
   count_launch();
   SB_CUDA(cudaGetLastError());
@@ -683,6 +800,33 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
                                int doff, cudaStream_t s) {
   const int d = gd.d;
   double* xL = workV[0];
+  if (fusable()) {
+    // one launch: D_i v_i for i < d-1 stored as terms, the last axis' epilogue applies the "+=" chain (:584-590) and scatters (:592);
+    // with zero boundary rows the loaders read the global vector directly, with Dirichlet data the padded copy is made first
+    const bool fuse_pad = !with_dirichlet && gd.m <= SB200_FUSE_PAD_MAX_NODES;
+    if (!fuse_pad) SB_TRY(pad_vel(x, xstride, xoff, with_dirichlet, xL, s));  // :574-581
+    double* terms[2] = {workP[1], workP[2]};  // (workP[0] may hold the folded pressure of the caller)
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) {
+      jobs[i] = job_p(i, xL, d, i, i < d - 1 ? terms[i] : nullptr, 1, 0, nullptr, DERIV_STORE);
+      if (fuse_pad) {
+        jobs[i].lm = line_map(i, 1);
+        jobs[i].gsrc = x;
+        jobs[i].gs_stride = xstride;
+        jobs[i].gs_off = xoff + i;
+      }
+    }
+    DerivParams& f = jobs[d - 1];
+    f.lm = line_map(d - 1, 1);
+    f.gdst = dst;
+    f.gd_stride = dstride;
+    f.gd_off = doff;
+    f.fin = EO_FIN_SUM;
+    f.nterms = d - 1;
+    for (int i = 0; i < d - 1; i++) f.term[i] = terms[i];
+    f.sign = 1.0;
+    return run_jobs(jobs, d, s);
+  }
   SB_TRY(pad_vel(x, xstride, xoff, with_dirichlet, xL, s));  // :574-581
   if (batchable()) {
     // one launch for the d terms D_i v_i; the "+=" chain (stokes.C:584-590) is applied by the crop in axis order
@@ -771,6 +915,21 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
   SB_TRY(pad_pres(x, xstride, xoff, pL, s));  // :606-608
   SB_TRY(pressure_reduce_order(pL, s));       // :609
   double* vL = workV[0];
+  if (fusable()) {
+    // D_i p goes straight into component i of the global velocity rows (:611-617), with the caller's "+=" / "- force" applied there
+    DerivParams jobs[3];
+    for (int i = 0; i < d; i++) {
+      jobs[i] = job_p(i, pL, 1, 0, nullptr, 1, 0, nullptr, DERIV_STORE);
+      jobs[i].lm = line_map(i, 1);
+      jobs[i].gdst = dst;
+      jobs[i].gd_stride = dstride;
+      jobs[i].gd_off = doff + i;
+      jobs[i].fin = EO_FIN_RAW;
+      jobs[i].add = add ? 1 : 0;
+      jobs[i].sub = sub;
+    }
+    return run_jobs(jobs, d, s);
+  }
   if (batchable()) {
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_p(i, pL, 1, 0, vL, d, i, nullptr, DERIV_STORE);
@@ -805,14 +964,16 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   const int d = gd.d;
   double* xL = workV[0];
   SB_TRY(pad_vel(xG, d + 1, 0, true, xL, s));                                                 // :691-699
-  if (batchable()) {
+  if (fusable() || batchable()) {
     DerivParams jobs[3];
     for (int i = 0; i < d; i++) jobs[i] = job_v(i, xL, strain[i], nullptr, DERIV_STORE);
     SB_TRY(run_jobs(jobs, d, s));
   } else {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
   }
-  if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));  // :746 from the gradient above (same Dirichlet-padded input)
+  DivDst dv{nullptr, 0, 0};  // :746 from the gradient above (same Dirichlet-padded input): inside the rheology kernel on the fused path
+  if (trace_divergence && fusable()) dv = DivDst{yG, d + 1, d};
+  else if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));
   const double* pfold = nullptr;
   if (fold_pressure) {  // opt-in, as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750)
     SB_TRY(pad_pres(xG, d + 1, d, workP[0], s));
@@ -825,13 +986,13 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    if (pfold) rheology_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold);
-    else rheology_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+    if (pfold) rheology_kernel<2, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold, gd, dv);
+    else rheology_kernel<2><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, nullptr, gd, dv);
   } else {
     VPtrs<3> p;
     for (int j = 0; j < 3; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
-    if (pfold) rheology_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold);
-    else rheology_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax);
+    if (pfold) rheology_kernel<3, true><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, pfold, gd, dv);
+    else rheology_kernel<3><<<grid_for(gd.m), 256, 0, s>>>(gd.m, r, eta, deta, p, minmax, nullptr, gd, dv);
   }
   count_launch();
   SB_CUDA(cudaGetLastError());

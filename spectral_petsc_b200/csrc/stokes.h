@@ -47,6 +47,9 @@ struct StokesCtx {
   DerivParams job_p(int axis, const double* x, int xs, int xoff, double* y, int ys, int yoff, const double* yin, int mode) const;
   // true when the d derivatives can run as one even-odd launch (single GPU, equal extents in {16,32,64,128})
   bool batchable() const;
+  // single GPU and every extent <= SB200_EO_MAX_P: pad / crop / AXPY chains run inside the derivative launches (deriv.h)
+  bool fusable() const;
+  EoLineMap line_map(int axis, int nc) const;
   int run_jobs(DerivParams* jobs, int d, cudaStream_t s);
   int crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s);
 
@@ -62,15 +65,16 @@ struct StokesCtx {
   int matmult_vv_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, cudaStream_t s,
                       double* div_dst = nullptr, int div_stride = 0, int div_off = 0, const double* p_local = nullptr);
   int crop_trace(double* const* grads, double* dst, int dstride, int doff, cudaStream_t s);
-  // Opt-in (sb200_stokes_set_trace_divergence; off by default until measured on a GPU): StokesMatMult and StokesFunction take
+  // Evaluation switch (sb200_stokes_set_trace_divergence; ON by default since round 2: measured and parity-tested at 128^3,
+  // profiles/r02_notes.md; off = the reference's literal sequence of shells): StokesMatMult and StokesFunction take
   // their pressure rows from the trace of the velocity gradient of the viscous block instead of padding the same velocity and
   // differentiating its components again (stokes.C:509,746 call StokesDivergence on the input the gradient was just taken of).
-  bool trace_divergence = false;
-  // Opt-in (sb200_stokes_set_fold_pressure; off by default until measured): StokesMatMult and StokesFunction subtract the padded,
+  bool trace_divergence = true;
+  // Evaluation switch (sb200_stokes_set_fold_pressure; ON by default since round 2): StokesMatMult and StokesFunction subtract the padded,
   // boundary-extrapolated pressure from the diagonal of the viscous flux (V = eta*eps - p I, the stress), so the one divergence
   // of the viscous tail also yields the pressure gradient and StokesMatMultVP's d derivative passes and its add-crop disappear.
   // Same operator; the sum -D_j V_jj + D_j p is rounded once instead of twice (differences ~1e-15 relative).
-  bool fold_pressure = false;
+  bool fold_pressure = true;
   int divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride, int doff,
                       cudaStream_t s);
   int pressure_reduce_order(double* pL, cudaStream_t s);

@@ -17,9 +17,10 @@ from spectral_petsc_b200 import dist as spd  # noqa: E402
 
 
 def apply_switches(S):
-    """SB200_STOKES_OPTS=trace,fold turns on the two evaluation switches (sb200_stokes_set_trace_divergence / _set_fold_pressure):
-    in slab mode they also remove 2 of the 8 axis-0 derivative exchanges of a StokesMatMult."""
-    opts = os.environ.get("SB200_STOKES_OPTS", "").split(",")
+    """SB200_STOKES_OPTS=trace,fold selects the two evaluation switches (sb200_stokes_set_trace_divergence / _set_fold_pressure;
+    both on by default since round 2, SB200_STOKES_OPTS=none turns them off): in slab mode they also remove 2 of the 8 axis-0
+    derivative exchanges of a StokesMatMult."""
+    opts = os.environ.get("SB200_STOKES_OPTS", "trace,fold").split(",")
     S.set_trace_divergence("trace" in opts)
     S.set_fold_pressure("fold" in opts)
     return [o for o in opts if o in ("trace", "fold")]

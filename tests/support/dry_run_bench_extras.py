@@ -50,7 +50,7 @@ def main():
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        bench.run_cuda(argparse.Namespace(gpus=1, steps=3, warmup=3, path=None, no_cpu_baseline=True, no_extras=True, no_ksp=True))
+        bench.run_cuda(argparse.Namespace(gpus=1, steps=3, warmup=3, path=None, no_cpu_baseline=True, no_extras=True, no_ksp=True, no_stokes=True))
     line = json.loads([l for l in buf.getvalue().splitlines() if l.startswith("{")][-1])
     print(json.dumps({"p_sweep": rows, "ksp": ksp, "line": line}))
     return 0

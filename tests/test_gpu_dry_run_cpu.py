@@ -41,9 +41,8 @@ def test_bench_extras_dry_run(libmock):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     ops = [row["op"] for row in d["p_sweep"]]
-    assert ops[:10] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)",
-                        "StokesMatMult (trace divergence)", "StokesFunction (trace divergence)", "StokesMatMult (trace divergence + folded pressure)",
-                        "StokesFunction (trace divergence + folded pressure)"]
+    assert ops[:8] == ["StokesMatMult", "StokesMatMultVV", "StokesMatMultVP", "StokesMatMultPV", "StokesFunction", "StokesPCSetUp0 (device CSR)",
+                       "StokesMatMult (evaluation switches off: three separate shells)", "StokesFunction (evaluation switches off: three separate shells)"]
     cfg = [(row["op"], row["dim"], row["launches"]) for row in d["p_sweep"] if "dim" in row]
     cfg = [c for c in cfg if not c[0].startswith("Stokes")]
     st20 = [row["op"] for row in d["p_sweep"] if row.get("dim") == "20x20x20"]

@@ -125,13 +125,13 @@ def test_full_size_128(cuda, rheology):
     xd = torch.from_numpy(x).to(cuda)
     y0 = G.mat_mult(xd).clone()
     assert rel_max(y0.cpu().numpy(), yo) < TOL
-    # the two evaluation switches at the full size (same operator: tests/test_zz4_gpu_optins.py has the small grids)
-    for trace, fold in ((True, False), (False, True), (True, True)):
+    # the two evaluation switches at the full size (both on by default; same operator: tests/test_zz4_gpu_optins.py has the small grids)
+    for trace, fold in ((True, False), (False, True), (False, False)):
         G.set_trace_divergence(trace)
         G.set_fold_pressure(fold)
         assert rel_max(G.mat_mult(xd).cpu().numpy(), yo) < TOL
         assert rel_max(G.function(torch.from_numpy(xs).to(cuda)).cpu().numpy(), Fo) < TOL
-    G.set_trace_divergence(False)
-    G.set_fold_pressure(False)
+    G.set_trace_divergence(True)
+    G.set_fold_pressure(True)
     assert torch.equal(G.mat_mult(xd), y0)
     G.destroy()

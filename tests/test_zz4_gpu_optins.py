@@ -17,6 +17,8 @@ def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
     """Opt-in sb200_stokes_set_trace_divergence: the pressure rows of StokesMatMult / StokesFunction taken from the trace of the
     velocity gradient the viscous part computes, instead of a second StokesDivergence pass on the same input (stokes.C:509,746)."""
     S = _state(cuda, dim, rheology)
+    S.set_trace_divergence(False)  # (both switches are on by default since round 2: start from the literal three-shell sequence)
+    S.set_fold_pressure(False)
     d = len(dim)
     rng = np.random.default_rng(3)
     x = torch.from_numpy(rng.standard_normal(S.g)).to(cuda)
@@ -55,6 +57,10 @@ def test_trace_divergence_option_gives_the_same_operator(cuda, dim, rheology):
         print("fold-pressure (trace %s) %s: launches %d -> %d, max rel diff %.2e" % (trace, dim, n_off, n_fold, float((y2 - y0).abs().max() / y0.abs().max())))
     # the switches leave no state behind
     assert torch.equal(S.mat_mult(x), y0) and torch.equal(S.function(xs), F0)
+    # the default (both on) is the combination tested last above
+    S.set_trace_divergence(True)
+    S.set_fold_pressure(True)
+    assert torch.equal(S.mat_mult(x), y2)
     S.destroy()
 
 
@@ -106,8 +112,8 @@ def test_graph_replayed_stokes_shells_equal_the_launched_ones(cuda, dim, rheolog
                 assert torch.equal(a, b)
             for a, b in zip(shells(), ref):  # replay
                 assert torch.equal(a, b)
-    S.set_trace_divergence(False)
-    S.set_fold_pressure(False)
+    S.set_trace_divergence(True)
+    S.set_fold_pressure(True)
     S.set_graph(False)
     pc = sp.StokesSaddle(S, 0, velocity_pc=None, vel_max_it=4, schur_max_it=3, svel_preonly=True)
     y_ref = pc.apply(x).clone()

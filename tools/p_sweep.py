@@ -165,27 +165,20 @@ def stokes_rows(steps=10, P=128, dev=None, flush=None):
     by_vals = 8.0 * m + 8.0 * nnz  # eta once, values written
     yield {"op": "StokesPCSetUp0 (device CSR)", "P": P, "rows": S.gv, "nnz": nnz, "ms_values_only": ms_vals, "t_hbm_ms_values_only": by_vals / bw / 1e6,
            "frac_of_hbm_roofline": by_vals / bw / 1e6 / ms_vals}
-    # the opt-in that takes the pressure rows from the trace of the viscous part's velocity gradient (one pad pass and d
-    # derivative passes fewer; sb200_stokes_set_trace_divergence) - measured beside the default so the switch can be decided
-    S.set_trace_divergence(True)
-    for name, fn, ndof, nder in (ops[0], ops[4]):
-        l0 = sp.launch_count()
-        fn()
-        nl = sp.launch_count() - l0
-        ms = timeit(fn, steps, flush)
-        t_fp64 = (nder - 3) * 2.0 * P * m / FP64_TFLOPS / 1e9  # 21 scalar derivatives instead of 24
-        yield {"op": name + " (trace divergence)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64, "frac_of_fp64_roofline": t_fp64 / ms}
-    S.set_fold_pressure(True)  # ... and the pressure gradient out of the same viscous divergence: 18 scalar derivatives
-    for name, fn, ndof, nder in (ops[0], ops[4]):
-        l0 = sp.launch_count()
-        fn()
-        nl = sp.launch_count() - l0
-        ms = timeit(fn, steps, flush)
-        t_fp64 = (nder - 6) * 2.0 * P * m / FP64_TFLOPS / 1e9
-        yield {"op": name + " (trace divergence + folded pressure)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64,
-               "frac_of_fp64_roofline": t_fp64 / ms}
-    S.set_fold_pressure(False)
+    # the reference's literal sequence of shells (VV, PV, VP each padding and differentiating their input: 24 scalar derivatives)
+    # beside the default (pressure rows from the trace of the viscous gradient, pressure folded into the viscous flux: 18)
     S.set_trace_divergence(False)
+    S.set_fold_pressure(False)
+    for name, fn, ndof, nder in (ops[0], ops[4]):
+        l0 = sp.launch_count()
+        fn()
+        nl = sp.launch_count() - l0
+        ms = timeit(fn, steps, flush)
+        t_fp64 = nder * 2.0 * P * m / FP64_TFLOPS / 1e9
+        yield {"op": name + " (evaluation switches off: three separate shells)", "P": P, "launches": nl, "ms": ms, "gdof_s": ndof / ms / 1e6, "t_fp64_ms": t_fp64,
+               "frac_of_fp64_roofline": t_fp64 / ms}
+    S.set_fold_pressure(True)
+    S.set_trace_divergence(True)
     S.function(xs)  # back to the state the default path leaves
     S.destroy()
 
