@@ -10,6 +10,9 @@ enum DerivMode { DERIV_STORE = 0, DERIV_SUB = 1, DERIV_ADD = 2 };
 // The fused pad (loader gathers from the global vector) pays on launch-bound grids; beyond this many nodes the padded copy + 16-byte
 // block loads are faster (measured at 128^3: 145 us fused against 26 + 100 us, profiles/r02_notes.md)
 #define SB200_FUSE_PAD_MAX_NODES (1ll << 18)
+// Likewise the fused crop-sum epilogue (its term loads are dependent L2 round trips of the finishing job's warps): 180 us against
+// 100 + 55 us at 128^3 for the Stokes viscous tail; small grids gain the launch
+#define SB200_FUSE_CROP_MAX_NODES (1ll << 18)
 // Grid geometry behind the lines of a job of the even-odd kernel (only needed by its fused pad / crop modes).
 struct EoLineMap {
   int d = 0, nc = 1, axis = 0;

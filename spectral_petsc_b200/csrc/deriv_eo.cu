@@ -129,7 +129,9 @@ __device__ __forceinline__ void eo_gemm_g(const double* __restrict__ Ae, const d
   }
 }
 
-template <int MT, int NWARPS, bool EXACT>
+// FUSED = false compiles the plain derivative alone (no pad loader, no crop epilogue, no item counting): the launches of the large
+// grids, whose inner loop must not share registers with the scatter code.
+template <int MT, int NWARPS, bool EXACT, bool FUSED>
 __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   using E = EOG<MT>;
   extern __shared__ double sm[];
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
     const EoJob& p = q.job[j];
     const long long R = p.R;
     const long long n0 = (long long)(tk - (j ? q.job[j - 1].end : 0u)) * 8;
-    if (p.gsrc) {
+    if (FUSED && p.gsrc) {
       // fused pad: lane c = lane & 7 owns line n0 + c; boundary nodes (and lines beyond the end) are zero filled
       const int c = lane & 7;
       const bool ok = (n0 + c) < p.nlines;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
     issue_load(nxt);
 
     // thread-owned outputs: lines 2t, 2t+1; rows mt = i*8+g (a+b) and mb = n-mt (b-a); the middle row of an odd P is its own mirror
-    if (p.gdst) {
+    if (FUSED && p.gdst) {
       if (p.nterms > 0) {
         // the terms are complete once every item of the earlier jobs has checked in
         if (lane == 0) {
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
         }
       }
     }
-    if (q.count_done && !(p.gdst && p.nterms > 0)) {
+    if (FUSED && q.count_done && !(p.gdst && p.nterms > 0)) {
       // this item's term rows are visible device-wide before it checks in
       __threadfence();
       __syncwarp();
@@ -411,10 +413,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
   }
 }
 
-template <int MT, int NWARPS, bool EXACT>
+template <int MT, int NWARPS, bool EXACT, bool FUSED>
 int launch_eo(const EoParams& q, cudaStream_t s) {
   using E = EOG<MT>;
-  auto kern = eo_deriv_kernel<MT, NWARPS, EXACT>;
+  auto kern = eo_deriv_kernel<MT, NWARPS, EXACT, FUSED>;
   const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * E::BLOCK_ELEMS) * sizeof(double);
   // the opt-in above 48 KB is per device: remembered per device (a small grid's launch costs more on the host than on the GPU)
   static bool attr[64] = {};
@@ -441,8 +443,10 @@ int launch_eo(const EoParams& q, cudaStream_t s) {
 
 template <int MT, int NWARPS>
 int launch_mt(const EoParams& q, cudaStream_t s) {
-  if (q.P == 16 * MT) return launch_eo<MT, NWARPS, true>(q, s);
-  return launch_eo<MT, NWARPS, false>(q, s);
+  bool fused = false;
+  for (int j = 0; j < q.njobs; j++) fused = fused || q.job[j].gsrc || q.job[j].gdst;
+  if (q.P == 16 * MT) return fused ? launch_eo<MT, NWARPS, true, true>(q, s) : launch_eo<MT, NWARPS, true, false>(q, s);
+  return fused ? launch_eo<MT, NWARPS, false, true>(q, s) : launch_eo<MT, NWARPS, false, false>(q, s);
 }
 
 }  // namespace

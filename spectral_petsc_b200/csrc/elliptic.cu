@@ -291,6 +291,7 @@ int EllipticCtx::init(int d, const int* dim, int rank, int nranks) {
 }
 
 EllipticCtx::~EllipticCtx() {
+  free_slab_maps(tmaps);
   arena.destroy();
   if (dirichlet) cudaFree(dirichlet);
   if (b) cudaFree(b);

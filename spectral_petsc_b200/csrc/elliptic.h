@@ -73,6 +73,8 @@ struct EllipticCtx {
   double* Yp = nullptr;
   bool pencil_valid = false;
   unsigned long long mm_epoch = 0;  // fused MatMult epoch (SYMM_READY / SYMM_DONE flags)
+  struct SlabMaps* tmaps = nullptr; // TMA descriptors of every rank's part[0] field (persist.h), built at the first fused slab MatMult
+  bool tmaps_tried = false;
 
   static int create(int d, const int* dim, int rank, int nranks, EllipticCtx** out);
   int init(int d, const int* dim, int rank, int nranks);
@@ -102,6 +104,7 @@ bool elliptic_fused_supported(const EllipticCtx& e);
 int elliptic_matmult_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
 bool elliptic_persist_supported(const EllipticCtx& e);
 int elliptic_matmult_persist(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
+void free_slab_maps(struct SlabMaps* m);
 bool elliptic_slab_fused_supported(const EllipticCtx& e);
 int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cudaStream_t s);
 // x_pencil[m][nl] = x_slab(plane m, line rank*R/G + nl) pulled from the owners of the planes

@@ -111,9 +111,14 @@ __device__ __forceinline__ void flux_apply(const FluxBuf& f, const Own<P, RIGHT>
 // PENCIL (slab mode, axis 0): n0 is the line index inside this rank's pencil; the flux operands come
 // from the pencil-layout state and the result rows are pushed to the part[0] array of the planes' owners.
 // WAITDONE (slab mode, last axis): part[0] is complete once every rank has raised its DONE flag.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(s) : "memory");
+}
+
 template <int P, int NT, bool RIGHT, bool DEEP, bool PENCIL = false, bool WAITDONE = false>
 __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long long n0, const double* Ae,
-                                         const double* Bo, double* Xw, int lane) {
+                                         const double* Bo, double* Xw, int lane, const SlabMaps* maps = nullptr, double* stage = nullptr) {
   using E = EO<P>;
   static_assert(!(PENCIL && RIGHT), "pencil items are strided-axis items");
   constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
@@ -188,6 +193,26 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   if (XF(p, 2)) {
     // experiment: no epilogue traffic (keep one dependent store so the GEMM is not dead code)
     if (a[0][0][0] + b[0][0][0] == 12345.678) p.V[0] = 1.0;
+  } else if (PENCIL && NT == 1 && p.bulk) {
+    // axis 0 of the slab partition: the item's P x 8 result block is staged in shared memory ([row][8 lines], 64 bytes per row) and
+    // leaves as ONE TMA tensor store per destination rank (box = 8 lines x nloc planes of that rank's part[0] field): the rows
+    // cross NVLink while this warp goes on with its next item
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous item's rows have been read out of the staging block
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E::MT; i++) {
+      const int mt = i * 8 + g, mb = P - 1 - mt;
+      st2(stage + mt * 8 + 2 * t, a[0][i][0] + b[0][i][0], a[0][i][1] + b[0][i][1]);
+      st2(stage + mb * 8 + 2 * t, b[0][i][0] - a[0][i][0], b[0][i][1] - a[0][i][1]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes visible to the TMA engine
+    __syncwarp();
+    if (lane < p.nranks) {
+      const int nloc = 1 << p.lognloc;
+      const int col = (int)((long long)p.rank * p.Rp + n0);  // first line of the block inside a plane
+      tma_store_2d(&maps->m[lane], col, 0, stage + (lane << p.lognloc) * 8);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   } else if (PENCIL) {
     // axis 0 of the slab partition: rows of D f go to the part[0] array of the rank that owns the plane
     const int nloc = 1 << p.lognloc;
@@ -400,14 +425,16 @@ constexpr int persist_maxreg(int nwarps, bool slab_a) {
 }
 
 template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
-__global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_kernel(PersistParams p) {
+__global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_kernel(PersistParams p, const __grid_constant__ SlabMaps maps) {
   using E = EO<P>;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];
   double* Ae = sm;
   double* Bo = sm + E::H * E::LDM;
   constexpr int BEMAX = E::BLOCK_ELEMS_RIGHT > E::BLOCK_ELEMS_LEFT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Xw = sm + E::MAT_ELEMS + warp * (NT * BEMAX);
+  // slab phase A: a staging block per warp for the pencil items' TMA stores (never touched by the loaders)
+  double* stage = (SLAB && !LASTPHASE) ? sm + E::MAT_ELEMS + NWARPS * (NT * BEMAX) + warp * (P * 8) : nullptr;
   unsigned* sync = p.sync + (LASTPHASE ? 4 : 0);  // [0] ticket, [1] exited warps
 
   const unsigned items_per_axis = (unsigned)(p.nlines / (8 * NT));
@@ -488,6 +515,11 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
   unsigned pencil_done = 0;  // pencil items this warp has finished and not yet reported
   auto report_pencils = [&]() {
     // all pushes of this warp are out; the rank whose last pencil item this was raises DONE everywhere
+    if (p.bulk) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this lane's tensor stores have completed (writes performed)
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncwarp();
+    }
     __threadfence_system();
     if (lane == 0) {
       const unsigned before = atomicAdd(sync + 2, pencil_done);
@@ -505,7 +537,7 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
       if (pencil_done) report_pencils();  // before this warp may block on the other ranks' DONE
       run_item<P, NT, true, DEEP, false, true>(p, p.d - 1, (long long)(tk - nlocal - items0) * (8 * NT), Ae, Bo, Xw, lane);
     } else if (SLAB && !LASTPHASE && tk >= nlocal) {
-      run_item<P, NT, false, DEEP, true>(p, 0, (long long)(tk - nlocal) * (8 * NT), Ae, Bo, Xw, lane);
+      run_item<P, NT, false, DEEP, true>(p, 0, (long long)(tk - nlocal) * (8 * NT), Ae, Bo, Xw, lane, &maps, stage);
       pencil_done++;
     } else {
       const unsigned tl = tk;
@@ -539,10 +571,12 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
 template <int P, int NWARPS, int NT, bool LASTPHASE, bool SLAB>
 int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
   auto kern = persist_kernel<P, NWARPS, NT, LASTPHASE, SLAB>;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};  // the opt-in above 48 KB of dynamic shared memory is per device
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (!attr[cur & 63]) {
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr[cur & 63] = true;
   }
   long long items = p.nlines / (8 * NT) * (LASTPHASE ? 1 : p.d - 1 - p.first_axis);
   if (SLAB && !LASTPHASE) items += p.Rp / (8 * NT) + (p.merged ? p.nlines / (8 * NT) : 0);
@@ -567,7 +601,8 @@ int launch_phase(const PersistParams& p, size_t smem, int sms, cudaStream_t s) {
   cfg.attrs = at;
   // phase B may start while phase A drains; slab phase A may start while the stage kernel pushes
   cfg.numAttrs = (LASTPHASE || SLAB) ? 1 : 0;
-  SB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  static const SlabMaps no_maps = {};
+  SB_CUDA(cudaLaunchKernelEx(&cfg, kern, p, (SLAB && p.maps) ? *p.maps : no_maps));
   count_launch();
   return 0;
 }
@@ -577,6 +612,7 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
   using E = EO<P>;
   constexpr int BEMAX = E::BLOCK_ELEMS_RIGHT > E::BLOCK_ELEMS_LEFT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
   const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * NT * BEMAX) * sizeof(double);
+  const size_t smem_slab_a = smem + (size_t)NWARPS * P * 8 * sizeof(double);  // + the pencil items' staging blocks
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -589,7 +625,8 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
       SB_CUDA(cudaGetLastError());
     }
     p.nlocal_items = (unsigned)(p.nlines / (8 * NT) * (p.d - 1 - p.first_axis));
-    SB_TRY((launch_phase<P, NWARPS, NT, false, true>(p, smem, sms, s)));
+    if (NT != 1) p.bulk = 0;
+    SB_TRY((launch_phase<P, NWARPS, NT, false, true>(p, smem_slab_a, sms, s)));
     if (!p.merged) SB_TRY((launch_phase<P, NWARPS, NT, true, true>(p, smem, sms, s)));
     return 0;
   }

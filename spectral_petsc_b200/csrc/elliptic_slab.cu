@@ -35,6 +35,38 @@ __global__ void slab_to_pencil_kernel(PeerPtrs pp, double* __restrict__ xp, int 
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// One descriptor per rank: its part[0] field as a 2-D fp64 tensor [nloc planes][R0 lines], box = 8 lines x nloc planes (the rows
+// of one pencil item that land on that rank).  Returns false when the driver offers no TMA descriptor API (the kernel then keeps
+// its per-thread stores).
+bool encode_part0_maps(double* const* part0peer, int G, long long R0, int nloc, SlabMaps* out) {
+  static EncodeTiledFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      encode = (EncodeTiledFn)fn;
+    else
+      cudaGetLastError();
+  }
+  if (!encode || nloc > 256) return false;
+  for (int q = 0; q < G; q++) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)R0, (cuuint64_t)nloc};
+    const cuuint64_t gstr[1] = {(cuuint64_t)R0 * sizeof(double)};
+    const cuuint32_t box[2] = {8u, (cuuint32_t)nloc};
+    const cuuint32_t es[2] = {1u, 1u};
+    if (encode(&out->m[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)part0peer[q], gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
 int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) l++;
@@ -65,6 +97,8 @@ int EllipticCtx::refresh_pencils(cudaStream_t s) {
   pencil_valid = true;
   return 0;
 }
+
+void free_slab_maps(SlabMaps* m) { delete m; }
 
 bool elliptic_slab_fused_supported(const EllipticCtx& e) {
   const int d = e.gd.d, G = e.arena.nranks;
@@ -127,6 +161,24 @@ int elliptic_matmult_slab_fused(EllipticCtx& e, const double* U, double* V, cuda
   p.Rp = p.R0 / G;
   p.sf = sf;
   p.epoch = epoch;
+  {
+    // pencil results through TMA tensor stores (SB200_SLAB_BULK = 0 keeps the per-thread 16-byte peer stores of round 1)
+    static int bulk = -1;
+    if (bulk < 0) {
+      const char* c = getenv("SB200_SLAB_BULK");
+      bulk = c ? atoi(c) : 1;
+    }
+    if (bulk && !e.tmaps_tried) {
+      e.tmaps_tried = true;
+      e.tmaps = new SlabMaps();
+      if (!encode_part0_maps(p.part0peer, G, p.R0, nloc, e.tmaps)) {
+        delete e.tmaps;
+        e.tmaps = nullptr;
+      }
+    }
+    p.maps = bulk ? e.tmaps : nullptr;
+    p.bulk = p.maps ? 1 : 0;
+  }
   {
     // one launch for all axes (the last axis waits for the local items by a counter and for the peers by DONE) or the
     // two PDL-chained phases of the single-GPU kernel: SB200_SLAB_MERGED = 0 / 1, default merged

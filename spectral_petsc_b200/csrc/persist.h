@@ -1,6 +1,7 @@
 // Internal: parameters of the persistent chain kernels (elliptic_persist.cu), shared with the slab
 // (multi-GPU) driver in elliptic_slab.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "elliptic.h"
@@ -41,12 +42,21 @@ struct PersistParams {
   long long R0, Rp;                     // lines per plane; lines per pencil (R0 / nranks)
   SymmFlags sf;
   unsigned long long epoch;             // READY / DONE flag value of this application
+  int bulk;                             // slab: pencil results leave through TMA tensor stores (maps != nullptr) instead of per-thread stores
+  const SlabMaps* maps;                 // host pointer (copied into the kernel's __grid_constant__ parameter at launch)
   int merged;                           // slab: the last-axis items run in the same launch as phase A (no phase B launch)
   unsigned nlocal_items;                // merged: local (non-pencil, non-last-axis) items whose partials the last axis reads
   unsigned long long tl_epoch;          // debug timeline: the application to stamp (SB200_TL_EPOCH)
   int stagger;       // start delay per warp group, in clocks
   int xflags;        // experiment switches (0 in production): 1 = no flux loads, 2 = no epilogue traffic
   long long* trace;  // optional (SB200_TRACE builds): per-item phase time stamps
+};
+
+// TMA descriptors of every rank's part[0] field viewed as [nloc planes][R0 lines] (fp64), box = 8 lines x nloc planes: the pencil
+// epilogue stages an item's result rows in shared memory and ONE cp.async.bulk.tensor store per destination rank carries the rows
+// that rank owns over NVLink - the issuing warp does not wait for the wire.  Passed to the kernel as a __grid_constant__ parameter.
+struct alignas(64) SlabMaps {
+  CUtensorMap m[SB200_MAX_RANKS];
 };
 
 // Runs phase A (axes first_axis..d-2; in slab mode also the axis-0 pencil items) and phase B (last

@@ -712,7 +712,7 @@ int StokesCtx::crop(int nc, const double* local, double* dst, int dstride, int d
 // y_vel[interior] (=|+=) -sum_j D_j V_j   with V from the pointwise step; shared tail of VV and Function
 int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) {
   const int d = gd.d;
-  if (fusable()) {
+  if (fusable() && gd.m <= SB200_FUSE_CROP_MAX_NODES) {
     // one launch: axes 1..d-1 store their terms D_i V_i, then axis 0 - whose 8-line blocks are contiguous in the AoS fields, so its
     // epilogue reads the terms with 16-byte loads - applies the "-=" chain (stokes.C:668-671) in AXIS order, its own value first,
     // and scatters into the global vector (:673): the arithmetic of crop_sum_kernel, no separate crop pass
@@ -731,7 +731,7 @@ int StokesCtx::viscous_tail(double* dst, int dstride, int doff, cudaStream_t s) 
     f.sign = -1.0;
     return run_jobs(jobs, d, s);
   }
-  if (batchable()) {
+  if (fusable() || batchable()) {
     // one launch for the d terms D_i V_i, the "-=" chain (stokes.C:668-671) is applied by the crop in axis order
     double* terms[3] = {workV[0], workV[1], workV[2 + d]};
     DerivParams jobs[3];
@@ -800,7 +800,7 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
                                int doff, cudaStream_t s) {
   const int d = gd.d;
   double* xL = workV[0];
-  if (fusable()) {
+  if (fusable() && gd.m <= SB200_FUSE_CROP_MAX_NODES) {
     // one launch: D_i v_i for i < d-1 stored as terms, the last axis' epilogue applies the "+=" chain (:584-590) and scatters (:592);
     // with zero boundary rows the loaders read the global vector directly, with Dirichlet data the padded copy is made first
     const bool fuse_pad = !with_dirichlet && gd.m <= SB200_FUSE_PAD_MAX_NODES;
@@ -828,7 +828,7 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
     return run_jobs(jobs, d, s);
   }
   SB_TRY(pad_vel(x, xstride, xoff, with_dirichlet, xL, s));  // :574-581
-  if (batchable()) {
+  if (fusable() || batchable()) {
     // one launch for the d terms D_i v_i; the "+=" chain (stokes.C:584-590) is applied by the crop in axis order
     double* terms[3] = {workP[0], workP[1], workP[2]};
     DerivParams jobs[3];
