@@ -571,6 +571,10 @@ class KSP:
     def set_tolerances(self, rtol=1e-5, atol=1e-50, dtol=1e5, maxits=10000):
         _ck(lib().sb200_ksp_set_tolerances(self._h, ctypes.c_double(rtol), ctypes.c_double(atol), ctypes.c_double(dtol), ctypes.c_int(maxits)))
 
+    def set_lookahead(self, depth):
+        """1: enqueue Arnoldi step k+1 before reading the norm of step k (sb200_ksp_set_lookahead; same iterates and counts)."""
+        _ck(lib().sb200_ksp_set_lookahead(self._h, ctypes.c_int(int(depth))))
+
     def solve(self, b, x=None, guess_nonzero=False):
         import torch
 

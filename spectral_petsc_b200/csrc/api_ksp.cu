@@ -45,6 +45,13 @@ int sb200_ksp_set_tolerances(sb200_ksp* k, double rtol, double atol, double dtol
   return 0;
 }
 
+int sb200_ksp_set_lookahead(sb200_ksp* k, int depth) {
+  SB_CHECK(k, SB200_ERR_ARG, "null context");
+  SB_CHECK(depth == 0 || depth == 1, SB200_ERR_USER, "KSP lookahead: 0 (read each iteration's norm before the next is enqueued) or 1");
+  k->c->lookahead = depth;
+  return 0;
+}
+
 int sb200_ksp_solve(sb200_ksp* k, const double* d_b, double* d_x, int guess_nonzero, void* stream) {
   SB_CHECK(k, SB200_ERR_ARG, "null context");
   SB_CHECK(!k->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier (a peer never arrived or the ranks' calls went out of step); the context refuses further work");

@@ -620,6 +620,15 @@ int run_cfg(PersistParams& p, cudaStream_t s) {
     if (!XF(p, 32)) {
       int blocks = sms;
       if (const char* mc = getenv("SB200_MAX_CTAS")) blocks = atoi(mc) > 0 ? atoi(mc) : blocks;
+      {
+        // same shared-memory carve-out as the chain kernel that shares the SMs with it: an SM whose carve-out has to change
+        // first drains, which delayed the chain kernel's CTAs behind the stage blocks (CTA starts spread over 12 us at 2 GPUs)
+        static bool carve[64] = {};
+        if (!carve[dev & 63]) {
+          cudaFuncSetAttribute(stage_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          carve[dev & 63] = true;
+        }
+      }
       stage_kernel<P><<<blocks, 128, 0, s>>>(p);
       count_launch();
       SB_CUDA(cudaGetLastError());

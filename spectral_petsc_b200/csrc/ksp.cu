@@ -95,10 +95,38 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
   }
 }
 
+// Layout of the small-work array (doubles), m = restart:
+//   H[(m+1)*m] | cs[m] | sn[m] | g[m+1] | y[m] | hcol[m+2] | scr[8]
+struct SmallPtrs {
+  double *H, *cs, *sn, *g, *y, *hcol, *scr;
+  int m;
+  __host__ __device__ static SmallPtrs make(double* base, int m) {
+    SmallPtrs p;
+    p.m = m;
+    p.H = base;
+    p.cs = p.H + (size_t)(m + 1) * m;
+    p.sn = p.cs + m;
+    p.g = p.sn + m;
+    p.y = p.g + (m + 1);
+    p.hcol = p.y + m;
+    p.scr = p.hcol + (m + 2);
+    return p;
+  }
+  static size_t count(int m) { return (size_t)(m + 1) * m + 2 * m + (m + 1) + m + (m + 2) + 8; }
+};
+
+struct HessArgs {  // on != 0: the block that finishes the norm also runs the Hessenberg / Givens update of column k
+  SmallPtrs sp;
+  int on, k;
+  double* rnorm_dev;
+  double* rnorm_host;
+};
+__device__ void hess_update(const SmallPtrs& p, int k, double* rnorm_dev, double* rnorm_host);
+
 // y[i] += sign * sum_j c[j] * Y[j*ldy + i];  optionally out_nrm2 = sum_i y[i]^2 (of the updated y).
 __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, const double* __restrict__ Y, long long ldy, int nv,
                                                     const double* __restrict__ c, double sign, long long n, double* __restrict__ partial,
-                                                    unsigned* counter, double* __restrict__ out_nrm2, int vec2) {
+                                                    unsigned* counter, double* __restrict__ out_nrm2, int vec2, HessArgs ha) {
   __shared__ double sm[TPB / 32];
   __shared__ double cs[64];
   __shared__ bool last;
@@ -151,6 +179,7 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
     if (threadIdx.x == 0) {
       *out_nrm2 = tot;
       *counter = 0;
+      if (ha.on) hess_update(ha.sp, ha.k, ha.rnorm_dev, ha.rnorm_host);
     }
   }
 }
@@ -168,26 +197,6 @@ __global__ void residual_kernel(double* __restrict__ r, const double* __restrict
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) r[i] = b[i] - w[i];
 }
 
-// Layout of the small-work array (doubles), m = restart:
-//   H[(m+1)*m] | cs[m] | sn[m] | g[m+1] | y[m] | hcol[m+2] | scr[8]
-struct SmallPtrs {
-  double *H, *cs, *sn, *g, *y, *hcol, *scr;
-  int m;
-  __host__ __device__ static SmallPtrs make(double* base, int m) {
-    SmallPtrs p;
-    p.m = m;
-    p.H = base;
-    p.cs = p.H + (size_t)(m + 1) * m;
-    p.sn = p.cs + m;
-    p.g = p.sn + m;
-    p.y = p.g + (m + 1);
-    p.hcol = p.y + m;
-    p.scr = p.hcol + (m + 2);
-    return p;
-  }
-  static size_t count(int m) { return (size_t)(m + 1) * m + 2 * m + (m + 1) + m + (m + 2) + 8; }
-};
-
 // beta^2 in scr[0]  ->  g = beta e_1, scr[1] = 1/beta, report beta
 __global__ void init_cycle_kernel(SmallPtrs p, double* rnorm_dev, double* rnorm_host) {
   const double beta = sqrt(p.scr[0]);
@@ -200,7 +209,7 @@ __global__ void init_cycle_kernel(SmallPtrs p, double* rnorm_dev, double* rnorm_
 }
 
 // Column k of the Hessenberg matrix: hcol[0..k] = V_j . w, hcol[k+1] = ||w||^2 after orthogonalisation.
-__global__ void hess_kernel(SmallPtrs p, int k, double* rnorm_dev, double* rnorm_host) {
+__device__ void hess_update(const SmallPtrs& p, int k, double* rnorm_dev, double* rnorm_host) {
   const int ld = p.m + 1;
   double* col = p.H + (size_t)k * ld;
   const double hn = sqrt(p.hcol[k + 1]);
@@ -232,6 +241,8 @@ __global__ void hess_kernel(SmallPtrs p, int k, double* rnorm_dev, double* rnorm
   *rnorm_host = rn;
   __threadfence_system();
 }
+
+__global__ void hess_kernel(SmallPtrs p, int k, double* rnorm_dev, double* rnorm_host) { hess_update(p, k, rnorm_dev, rnorm_host); }
 
 // y = R^{-1} g for the first kk columns
 __global__ void backsolve_kernel(SmallPtrs p, int kk) {
@@ -308,7 +319,8 @@ int KspCtx::init(long long n_, int restart_, int rank, int nranks) {
   SB_CUDA(cudaMemset(counters, 0, 64 * sizeof(unsigned)));
   SB_CUDA(cudaHostAlloc((void**)&h_rnorm, 64, cudaHostAllocMapped));
   SB_CUDA(cudaHostGetDevicePointer((void**)&d_rnorm, h_rnorm, 0));
-  for (auto& e : ev) SB_CUDA(cudaEventCreate(&e));
+  for (auto& r : evr)
+    for (auto& e : r) SB_CUDA(cudaEventCreate(&e));
   SB_TRY(arena.init(2 * SB200_MAX_RANKS * SLOT * sizeof(double), rank, nranks));
   SB_CHECK((slots = arena.alloc_doubles(2 * SB200_MAX_RANKS * SLOT)), SB200_ERR_CUDA, "arena exhausted");
   return 0;
@@ -322,8 +334,9 @@ KspCtx::~KspCtx() {
   if (partial) cudaFree(partial);
   if (counters) cudaFree(counters);
   if (h_rnorm) cudaFreeHost(h_rnorm);
-  for (auto& e : ev)
-    if (e) cudaEventDestroy(e);
+  for (auto& r : evr)
+    for (auto& e : r)
+      if (e) cudaEventDestroy(e);
   arena.destroy();
 }
 
@@ -405,35 +418,58 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
       reason = -9;  // KSP_DIVERGED_NANORINF
       return 0;
     }
-    int k = 0;
+    // Arnoldi steps of this cycle.  lookahead = 0: one host read per iteration before the next one is enqueued (PETSc's decision
+    // point).  lookahead = 1 (opt-in): iteration k+1 is enqueued before iteration k's norm is read, so the GPU never idles on the
+    // host; when iteration k turns out to be the last, the speculative step behind it is discarded (it touches nothing the
+    // back-substitution over k+1 columns reads) - at most one extra operator / preconditioner application per solve.
+    int k_enq = 0, k = 0;  // enqueued / accounted iterations of this cycle
     bool done = false;
-    for (; k < restart && !done; k++) {
-      double* vk = V + (size_t)k * ld;
-      double* zk = Zb + (size_t)k * ld;
-      SB_CUDA(cudaEventRecord(ev[0], s));
+    auto enqueue = [&](int kq) -> int {
+      double* vk = V + (size_t)kq * ld;
+      double* zk = Zb + (size_t)kq * ld;
+      cudaEvent_t* e = evr[kq % NRING];
+      SB_CUDA(cudaEventRecord(e[0], s));
       if (pc) SB_TRY(pc(pc_ctx, vk, zk, (void*)s));
-      SB_CUDA(cudaEventRecord(ev[1], s));
+      SB_CUDA(cudaEventRecord(e[1], s));
       SB_TRY(op(op_ctx, zk, w, (void*)s));
-      SB_CUDA(cudaEventRecord(ev[2], s));
-      SB_TRY(dots(w, V, ld, k + 1, sp.hcol, s));  // classical Gram-Schmidt: all projections at once
-      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, k + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (k + 1), 1);
+      SB_CUDA(cudaEventRecord(e[2], s));
+      SB_TRY(dots(w, V, ld, kq + 1, sp.hcol, s));  // classical Gram-Schmidt: all projections at once
+      HessArgs ha;
+      ha.sp = sp;
+      ha.on = arena.nranks == 1 ? 1 : 0;  // single rank: the norm's last block also updates the Hessenberg column (one launch fewer)
+      ha.k = kq;
+      ha.rnorm_dev = sp.scr + 3;
+      ha.rnorm_host = d_rnorm + (kq % NRING);
+      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, kq + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (kq + 1), 1, ha);
       count_launch();
-      SB_TRY(allreduce(sp.hcol + (k + 1), 1, s));
-      hess_kernel<<<1, 1, 0, s>>>(sp, k, sp.scr + 3, d_rnorm);
+      if (!ha.on) {
+        SB_TRY(allreduce(sp.hcol + (kq + 1), 1, s));
+        hess_kernel<<<1, 1, 0, s>>>(sp, kq, sp.scr + 3, d_rnorm + (kq % NRING));
+        count_launch();
+      }
+      scale_kernel2<<<g1, TPB, 0, s>>>(V + (size_t)(kq + 1) * ld, w, sp.scr + 1, n);
       count_launch();
-      scale_kernel2<<<g1, TPB, 0, s>>>(V + (size_t)(k + 1) * ld, w, sp.scr + 1, n);
-      count_launch();
-      SB_CUDA(cudaEventRecord(ev[3], s));
+      SB_CUDA(cudaEventRecord(e[3], s));
       SB_CUDA(cudaGetLastError());
-      SB_CUDA(cudaStreamSynchronize(s));  // the one host read per iteration (as in PETSc: the norm decides)
+      return 0;
+    };
+    while (!done) {
+      while (k_enq < restart && k_enq - k <= lookahead && its + (k_enq - k) < maxits) {
+        SB_TRY(enqueue(k_enq));
+        k_enq++;
+      }
+      if (k == k_enq) break;  // the cycle is complete
+      cudaEvent_t* e = evr[k % NRING];
+      SB_CUDA(cudaEventSynchronize(e[3]));  // the one host read per iteration (as in PETSc: the norm decides)
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      cudaEventElapsedTime(&ms, e[0], e[1]);
       t_pc += ms;
-      cudaEventElapsedTime(&ms, ev[1], ev[2]);
+      cudaEventElapsedTime(&ms, e[1], e[2]);
       t_op += ms;
-      cudaEventElapsedTime(&ms, ev[2], ev[3]);
+      cudaEventElapsedTime(&ms, e[2], e[3]);
       t_orth += ms;
-      rnorm = *h_rnorm;
+      rnorm = reinterpret_cast<volatile double*>(h_rnorm)[k % NRING];
+      k++;
       its++;
       history.push_back(rnorm);
       if (rnorm <= ttol) {
@@ -453,7 +489,8 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
     // x += Z y with R y = g
     backsolve_kernel<<<1, 1, 0, s>>>(sp, k);
     count_launch();
-    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr, vx);
+    HessArgs nohess = {};
+    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr, vx, nohess);
     count_launch();
     SB_CUDA(cudaGetLastError());
     if (done) break;

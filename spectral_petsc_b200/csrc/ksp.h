@@ -46,7 +46,9 @@ struct KspCtx {
   double rnorm = 0.0, bnorm = 0.0;
   std::vector<double> history;
   double t_op = 0.0, t_pc = 0.0, t_orth = 0.0;  // milliseconds (CUDA events), accumulated over the last solve
-  cudaEvent_t ev[4] = {};
+  static constexpr int NRING = 4;  // per-iteration event sets / residual-norm slots in flight (lookahead + 2 at most)
+  cudaEvent_t evr[NRING][4] = {};
+  int lookahead = 0;  // 1: iteration k+1 is enqueued before iteration k's norm is read (sb200_ksp_set_lookahead)
 
   static int create(long long n, int restart, int rank, int nranks, KspCtx** out);
   ~KspCtx();

@@ -472,6 +472,7 @@ int sb200_ksp_set_tolerances(sb200_ksp* k, double rtol, double atol, double dtol
   k->maxits = maxits;
   return 0;
 }
+int sb200_ksp_set_lookahead(sb200_ksp*, int depth) { return (depth == 0 || depth == 1) ? 0 : 83; }  // a scheduling choice of the CUDA path; same iterates
 int sb200_ksp_solve(sb200_ksp* K, const double* b, double* x, int guess_nonzero, void* stream) {
   const long long n = K->n;
   const int m = K->restart;

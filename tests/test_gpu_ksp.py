@@ -129,3 +129,37 @@ def test_slab_ksp_two_ranks_in_process(cuda):
         assert all(c.slab_timeouts() == 0 for c in ctx)
     finally:
         del os.environ["SB200_MAX_CTAS"]
+
+
+@pytest.mark.parametrize("restart,maxits", [(30, 10000), (7, 10000), (30, 17)])
+def test_lookahead_gives_the_same_solve(cuda, restart, maxits):
+    """sb200_ksp_set_lookahead(1): step k+1 is enqueued before the norm of step k is read.  Same iterates bit for bit, same
+    iteration count, history and reason - whether the solve ends by convergence (a speculative step is discarded), at a restart
+    boundary or at the iteration cap; the operator is applied at most once more."""
+    rng = np.random.default_rng(0)
+    n = 400
+    A = rng.standard_normal((n, n)) + 2.0 * n ** 0.5 * np.eye(n)
+    Ad = torch.from_numpy(A).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(n)).to(cuda)
+    out = []
+    for la in (0, 1):
+        calls = [0]
+
+        def op(v):
+            calls[0] += 1
+            return Ad @ v
+
+        K = sp.KSP(n, restart=restart)
+        K.set_operators(op, pc=lambda r: 0.5 * r)
+        K.set_tolerances(rtol=1e-10, maxits=maxits)
+        K.set_lookahead(la)
+        x = K.solve(b).clone()
+        out.append((x, dict(K.result), list(K.history), calls[0]))
+        K.destroy()
+    (x0, r0, h0, c0), (x1, r1, h1, c1) = out
+    assert torch.equal(x0, x1)
+    assert r0["its"] == r1["its"] and r0["reason"] == r1["reason"] and h0 == h1
+    assert c0 <= c1 <= c0 + 1
+    with pytest.raises(sp.SB200Error):
+        K2 = sp.KSP(8)
+        K2.set_lookahead(2)
