@@ -652,7 +652,7 @@ bool elliptic_persist_supported(const EllipticCtx& e) {
   const int P = e.gd.dim[0];
   for (int j = 1; j < d; j++)
     if (e.gd.dim[j] != P) return false;
-  return (P == 32 || P == 64 || P == 128) && (e.gd.m / P) % 16 == 0;
+  return (P == 32 || P == 64 || P == 96 || P == 128) && (e.gd.m / P) % 16 == 0;
 }
 
 int persist_run(int P, PersistParams& p, cudaStream_t s) {
@@ -674,6 +674,9 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
   switch (P) {
     case 32: return run_cfg<32, 16, 1>(p, s);
     case 64: return run_cfg<64, 16, 1>(p, s);
+    case 96:
+      SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: extent 96 is a single-GPU instantiation");
+      return run_cfg<96, 12, 1>(p, s);
     case 128:
       switch (cfg) {
         case 0: return run_cfg<128, 16, 1>(p, s);

@@ -16,7 +16,7 @@ namespace sb200 {
 
 namespace {
 
-constexpr int CH = 8;        // vectors per dot-product pass
+constexpr int CHMAX = 32;    // vectors per dot-product pass (template parameter CH: 8, 16 or 32, the smallest that takes them all)
 constexpr int TPB = 256;
 constexpr int SLOT = 64;     // doubles per all-reduce slot
 
@@ -32,7 +32,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid on thread 0
 }
 
-// out[j] = sum_i x[i] * Y[j*ldy + i],  j in [0, nv).  grid = (nblocks, ceil(nv / CH)).
+// out[j] = sum_i x[i] * Y[j*ldy + i],  j in [0, nv).  grid = (nblocks, ceil(nv / CH)): x is read once per group of CH vectors.
+template <int CH>
 __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x, const double* __restrict__ Y, long long ldy, int nv,
                                                    long long n, double* __restrict__ partial, unsigned* counters, double* __restrict__ out,
                                                    int vec2) {
@@ -85,11 +86,11 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
     // warp jj adds the per-block partials of vector j0+jj: lane-strided loads, then a shuffle tree (fixed order)
     __threadfence();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < cnt) {
+    for (int jj = warp; jj < cnt; jj += TPB / 32) {
       double t = 0.0;
-      for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (long long)(j0 + warp) * gridDim.x + b);
+      for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (long long)(j0 + jj) * gridDim.x + b);
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) out[j0 + warp] = t;
+      if (lane == 0) out[j0 + jj] = t;
     }
     if (threadIdx.x == 0) counters[blockIdx.y] = 0;
   }
@@ -135,9 +136,13 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * TPB;
   if (vec2) {
+    // DESCENDING through the vectors: the multi-dot that ran just before walked them upwards, so the last ~100 MB it touched (the
+    // high end of every vector) are still in the 126 MB L2 when this kernel starts there
     const long long n2 = n >> 1;
     double2* __restrict__ y2 = reinterpret_cast<double2*>(y);
-    for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n2; i += stride) {
+    const long long first = (long long)blockIdx.x * TPB + threadIdx.x;
+    const long long steps = first < n2 ? (n2 - 1 - first) / stride : -1;
+    for (long long i = first + steps * stride; steps >= 0 && i >= first; i -= stride) {
       double2 v = y2[i];
 #pragma unroll 4
       for (int j = 0; j < nv; j++) {
@@ -359,9 +364,14 @@ int KspCtx::allreduce(double* vals, int k, cudaStream_t s) {
 }
 
 int KspCtx::dots(const double* x, const double* Y, long long ldy, int nv, double* out, cudaStream_t s) {
-  dim3 grid(nblocks, (nv + CH - 1) / CH);
   const int vec2 = (reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(Y) % 16 == 0 && ldy % 2 == 0) ? 1 : 0;
-  mdot_kernel<<<grid, TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  if (nv <= 8) {
+    mdot_kernel<8><<<dim3(nblocks, 1), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  } else if (nv <= 16) {
+    mdot_kernel<16><<<dim3(nblocks, 1), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  } else {
+    mdot_kernel<CHMAX><<<dim3(nblocks, (nv + CHMAX - 1) / CHMAX), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  }
   count_launch();
   SB_CUDA(cudaGetLastError());
   return allreduce(out, nv, s);

@@ -107,15 +107,36 @@ struct TermPtrs {
 
 // dst[gid*dstride + doff + k] = ((0 +- T_0) +- T_1) +- T_2 at interior nodes: the VecAXPY chain of stokes.C:584-590 /
 // 668-671 (w0 = 0; w0 -= D_i V_i in axis order) applied while cropping, same operation order as the reference.
-__global__ void crop_sum_kernel(GridDesc gd, int nc, int nterms, TermPtrs tp, double sign, double* __restrict__ dst, int dstride, int doff) {
+// Two nodes per thread and pass, every load issued before the first use.
+template <int NC, int NT>
+__global__ void crop_sum_kernel(GridDesc gd, TermPtrs tp, double sign, double* __restrict__ dst, int dstride, int doff) {
+  constexpr int U = 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < gd.m; idx += stride) {
-    const NodeInfo n = decode_node(gd, idx);
-    if (!n.interior) continue;
-    for (int k = 0; k < nc; k++) {
-      double v = 0.0;
-      for (int t = 0; t < nterms; t++) v = __dadd_rn(v, __dmul_rn(sign, tp.t[t][idx * nc + k]));
-      dst[n.gid * dstride + doff + k] = v;
+  for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < gd.m; idx0 += U * stride) {
+    double v[U][NT][NC];
+    NodeInfo nd[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long idx = idx0 + u * stride;
+      nd[u].interior = false;
+      if (idx >= gd.m) continue;
+      nd[u] = decode_node(gd, idx);
+      if (!nd[u].interior) continue;
+#pragma unroll
+      for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int k = 0; k < NC; k++) v[u][t][k] = tp.t[t][idx * NC + k];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!nd[u].interior) continue;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        double a = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) a = __dadd_rn(a, __dmul_rn(sign, v[u][t][k]));
+        dst[nd[u].gid * dstride + doff + k] = a;
+      }
     }
   }
 }
@@ -386,6 +407,45 @@ __global__ void reduce_order_lastaxis_kernel(ReduceArgs a, const double* __restr
   if (lane == 0) {
     pres[base] = f0;
     pres[base + (a.P - 1)] = f1;
+  }
+}
+
+// The pressure pad (VecScatter global -> local, stokes.C:606-608) and the LAST-axis pass of the extrapolation in one kernel (single
+// GPU): one warp per interior line reads the line's interior values from the global vector, forms the two end-point sums with the
+// arithmetic of reduce_order_lastaxis_kernel (lane-strided fma chains, xor-shuffle tree) and writes the complete padded line.
+// Lines on the boundary of another axis are left alone: the later passes write every one of their nodes before anything reads them.
+__global__ void pad_reduce_lastaxis_kernel(GridDesc gd, const double* __restrict__ src, int sstride, int soff, const double* __restrict__ w0,
+                                           const double* __restrict__ w1, double* __restrict__ pres) {
+  const long long line = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int d = gd.d, P = gd.dim[d - 1];
+  if (line >= gd.m / P) return;
+  long long rem = line, gbase = 0;
+  bool inter = true;
+  for (int j = d - 2; j >= 0; j--) {
+    const int dj = gd.dim[j];
+    const int ij = (int)(rem % dj);
+    rem /= dj;
+    inter = inter && ij >= 1 && ij <= dj - 2;
+    gbase += (long long)(ij - 1) * gd.istride[j];
+  }
+  if (!inter) return;
+  const double* __restrict__ sl = src + gbase * sstride + soff;  // interior node k (1 <= k <= P-2) at sl[(k-1)*sstride]
+  double* __restrict__ pl = pres + line * P;
+  double f0 = 0.0, f1 = 0.0;
+  for (int k = 1 + lane; k < P - 1; k += 32) {
+    const double v = sl[(long long)(k - 1) * sstride];
+    pl[k] = v;
+    f0 = fma(w0[k], v, f0);
+    f1 = fma(w1[k], v, f1);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+    f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+  }
+  if (lane == 0) {
+    pl[0] = f0;
+    pl[P - 1] = f1;
   }
 }
 
@@ -672,7 +732,15 @@ int StokesCtx::run_jobs(DerivParams* jobs, int d, cudaStream_t s) {
 int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s) {
   TermPtrs tp;
   for (int t = 0; t < 3; t++) tp.t[t] = t < nterms ? terms[t] : nullptr;
-  crop_sum_kernel<<<grid_for(gd.m), 256, 0, s>>>(gd, nc, nterms, tp, sign, dst, dstride, doff);
+  const int g = grid_for(gd.m);
+  if (nc == 3 && nterms == 3) crop_sum_kernel<3, 3><<<g, 256, 0, s>>>(gd, tp, sign, dst, dstride, doff);
+  else if (nc == 1 && nterms == 3) crop_sum_kernel<1, 3><<<g, 256, 0, s>>>(gd, tp, sign, dst, dstride, doff);
+  else if (nc == 2 && nterms == 2) crop_sum_kernel<2, 2><<<g, 256, 0, s>>>(gd, tp, sign, dst, dstride, doff);
+  else if (nc == 1 && nterms == 2) crop_sum_kernel<1, 2><<<g, 256, 0, s>>>(gd, tp, sign, dst, dstride, doff);
+  else {
+    set_last_error("crop_sum: unsupported component / term count");
+    return SB200_ERR_SUP;
+  }
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;
@@ -842,11 +910,25 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
   return crop(1, acc, dst, dstride, doff, false, nullptr, s);  // :592
 }
 
-int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s) {
+// pL = the padded, boundary-extrapolated pressure of a global vector (stokes.C:606-609): pad + StokesPressureReduceOrder.
+int StokesCtx::pad_pres_reduced(const double* src, int sstride, int soff, double* pL, cudaStream_t s) {
+  const int d = gd.d;
+  if (arena.nranks == 1 && gd.stride[d - 1] == 1 && gdim[d - 1] >= 3 && gd.m < (1ll << 31)) {
+    const long long nlines = gd.m / gd.dim[d - 1];
+    pad_reduce_lastaxis_kernel<<<(unsigned)((nlines * 32 + 255) / 256), 256, 0, s>>>(gd, src, sstride, soff, w0[d - 1], w1[d - 1], pL);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+    return pressure_reduce_order(pL, s, 1);  // the remaining passes
+  }
+  SB_TRY(pad_pres(src, sstride, soff, pL, s));
+  return pressure_reduce_order(pL, s);
+}
+
+int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s, int first_pass) {
   // stokes.C:1029-1080: z lines, then y lines, then x lines; later passes consume earlier results
   const int d = gd.d;
   const bool slab = arena.nranks > 1;
-  for (int pass = 0; pass < d; pass++) {
+  for (int pass = first_pass; pass < d; pass++) {
     const int axis = d - 1 - pass;
     if (gdim[axis] < 3) continue;
     if (axis == 0 && slab) {
@@ -912,8 +994,7 @@ int StokesCtx::matmult_vp_into(const double* x, int xstride, int xoff, double* d
                                const double* sub, cudaStream_t s) {
   const int d = gd.d;
   double* pL = workP[0];
-  SB_TRY(pad_pres(x, xstride, xoff, pL, s));  // :606-608
-  SB_TRY(pressure_reduce_order(pL, s));       // :609
+  SB_TRY(pad_pres_reduced(x, xstride, xoff, pL, s));  // :606-609
   double* vL = workV[0];
   if (fusable()) {
     // D_i p goes straight into component i of the global velocity rows (:611-617), with the caller's "+=" / "- force" applied there
@@ -945,8 +1026,7 @@ int StokesCtx::matmult(const double* xG, double* yG, cudaStream_t s) {
   const int d = gd.d;
   const double* pfold = nullptr;
   if (fold_pressure) {  // opt-in: the padded, boundary-extrapolated pressure (:606-609) enters the viscous flux as -p I
-    SB_TRY(pad_pres(xG, d + 1, d, workP[0], s));
-    SB_TRY(pressure_reduce_order(workP[0], s));
+    SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], s));
     pfold = workP[0];
   }
   if (trace_divergence) {
@@ -976,8 +1056,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   else if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));
   const double* pfold = nullptr;
   if (fold_pressure) {  // opt-in, as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750)
-    SB_TRY(pad_pres(xG, d + 1, d, workP[0], s));
-    SB_TRY(pressure_reduce_order(workP[0], s));
+    SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], s));
     pfold = workP[0];
   }
   init_minmax_kernel<<<1, 1, 0, s>>>(minmax);

@@ -77,7 +77,8 @@ struct StokesCtx {
   bool fold_pressure = true;
   int divergence_into(const double* x, int xstride, int xoff, bool with_dirichlet, double* dst, int dstride, int doff,
                       cudaStream_t s);
-  int pressure_reduce_order(double* pL, cudaStream_t s);
+  int pressure_reduce_order(double* pL, cudaStream_t s, int first_pass = 0);
+  int pad_pres_reduced(const double* src, int sstride, int soff, double* pL, cudaStream_t s);
   int matmult_vp_into(const double* x, int xstride, int xoff, double* dst, int dstride, int doff, bool add,
                       const double* sub, cudaStream_t s);
   int matmult(const double* xG, double* yG, cudaStream_t s);

@@ -114,6 +114,25 @@ def test_fused_chain_path_matches_generic_and_oracle(cuda, dim):
     assert np.array_equal(V3, V3b)
 
 
+@pytest.mark.parametrize("dim", [[96, 96], [96, 96, 96]], ids=str)
+def test_persistent_chain_at_96(cuda, dim):
+    """P = 96 (H = 48, 6 pair tiles): the persistent chain kernel is the default path there too; against the oracle and the generic path."""
+    O, G, u, u2 = make_pair(dim, 4.0, 2.0, cuda)
+    Us = 0.1 * np.random.default_rng(1).standard_normal(O.g)
+    O.form_function(Us)
+    G.form_function(torch.from_numpy(Us).to(cuda))
+    U = np.random.default_rng(0).standard_normal(O.g)
+    Vo = O.mat_mult(U)
+    Ud = torch.from_numpy(U).to(cuda)
+    V0 = G.mat_mult(Ud).cpu().numpy()
+    assert "persist" in G.kernel_name()
+    V0b = G.mat_mult(Ud).cpu().numpy()
+    G.set_path(1)
+    V1 = G.mat_mult(Ud).cpu().numpy()
+    assert rel_max(V0, Vo) < TOL and rel_max(V1, Vo) < TOL and rel_max(V0, V1) < 1e-13
+    assert np.array_equal(V0, V0b)
+
+
 def test_fused_path_rejects_unsupported_extents(cuda):
     G = sp.Elliptic([16, 16, 16])
     G.set_path(2)
