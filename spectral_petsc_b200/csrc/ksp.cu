@@ -6,6 +6,7 @@
 #include "ksp.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/spectral_b200.h"
@@ -16,7 +17,7 @@ namespace sb200 {
 
 namespace {
 
-constexpr int CHMAX = 32;    // vectors per dot-product pass (template parameter CH: 8, 16 or 32, the smallest that takes them all)
+constexpr int CHMAX = 32;    // vectors per dot-product pass: template parameter CH in {8, 16, 32}; 8 is the default (measured), SB200_KSP_MDOT_CH raises it
 constexpr int TPB = 256;
 constexpr int SLOT = 64;     // doubles per all-reduce slot
 
@@ -127,7 +128,7 @@ __device__ void hess_update(const SmallPtrs& p, int k, double* rnorm_dev, double
 // y[i] += sign * sum_j c[j] * Y[j*ldy + i];  optionally out_nrm2 = sum_i y[i]^2 (of the updated y).
 __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, const double* __restrict__ Y, long long ldy, int nv,
                                                     const double* __restrict__ c, double sign, long long n, double* __restrict__ partial,
-                                                    unsigned* counter, double* __restrict__ out_nrm2, int vec2, HessArgs ha) {
+                                                    unsigned* counter, double* __restrict__ out_nrm2, int vec2, HessArgs ha, int desc) {
   __shared__ double sm[TPB / 32];
   __shared__ double cs[64];
   __shared__ bool last;
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
     double2* __restrict__ y2 = reinterpret_cast<double2*>(y);
     const long long first = (long long)blockIdx.x * TPB + threadIdx.x;
     const long long steps = first < n2 ? (n2 - 1 - first) / stride : -1;
-    for (long long i = first + steps * stride; steps >= 0 && i >= first; i -= stride) {
+    const long long istart = desc ? first + steps * stride : first, istep = desc ? -stride : stride;
+    for (long long i = istart, c = 0; c <= steps; c++, i += istep) {
       double2 v = y2[i];
 #pragma unroll 4
       for (int j = 0; j < nv; j++) {
@@ -345,6 +347,15 @@ KspCtx::~KspCtx() {
   arena.destroy();
 }
 
+static int maxpy_desc() {
+  static int d = -1;
+  if (d < 0) {
+    const char* c = getenv("SB200_KSP_DESC");  // tuning hook: MAXPY walks the vectors downwards (L2 reuse after the multi-dot)
+    d = c ? atoi(c) : 1;
+  }
+  return d;
+}
+
 int KspCtx::allreduce(double* vals, int k, cudaStream_t s) {
   if (arena.nranks == 1) return 0;
   SB_CHECK(arena.attached(), SB200_ERR_USER, "KSP on a slab partition: peers are not attached");
@@ -365,10 +376,15 @@ int KspCtx::allreduce(double* vals, int k, cudaStream_t s) {
 
 int KspCtx::dots(const double* x, const double* Y, long long ldy, int nv, double* out, cudaStream_t s) {
   const int vec2 = (reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(Y) % 16 == 0 && ldy % 2 == 0) ? 1 : 0;
-  if (nv <= 8) {
-    mdot_kernel<8><<<dim3(nblocks, 1), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
-  } else if (nv <= 16) {
-    mdot_kernel<16><<<dim3(nblocks, 1), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  static int chcap = -1;
+  if (chcap < 0) {
+    const char* c = getenv("SB200_KSP_MDOT_CH");  // tuning hook: largest group (8, 16 or 32 vectors per pass)
+    chcap = c ? atoi(c) : 8;  // measured on B200 (profiles/r02_notes.md): 8 vectors per pass beat 16 and 32 (registers, concurrent DRAM streams)
+  }
+  if (nv <= 8 || chcap <= 8) {
+    mdot_kernel<8><<<dim3(nblocks, (nv + 7) / 8), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+  } else if (nv <= 16 || chcap <= 16) {
+    mdot_kernel<16><<<dim3(nblocks, (nv + 15) / 16), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
   } else {
     mdot_kernel<CHMAX><<<dim3(nblocks, (nv + CHMAX - 1) / CHMAX), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
   }
@@ -450,7 +466,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
       ha.k = kq;
       ha.rnorm_dev = sp.scr + 3;
       ha.rnorm_host = d_rnorm + (kq % NRING);
-      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, kq + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (kq + 1), 1, ha);
+      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, kq + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (kq + 1), 1, ha, maxpy_desc());
       count_launch();
       if (!ha.on) {
         SB_TRY(allreduce(sp.hcol + (kq + 1), 1, s));
@@ -500,7 +516,7 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
     backsolve_kernel<<<1, 1, 0, s>>>(sp, k);
     count_launch();
     HessArgs nohess = {};
-    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr, vx, nohess);
+    maxpy_kernel<<<g1, TPB, 0, s>>>(x, Zb, ld, k, sp.y, 1.0, n, partial, counters + 32, nullptr, vx, nohess, 0);
     count_launch();
     SB_CUDA(cudaGetLastError());
     if (done) break;
