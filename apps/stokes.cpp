@@ -153,7 +153,8 @@ struct Flow {
   HostPc vel, svel;
   bool svel_is_vel = true, svel_preonly = false;
   int saddle = 0, vel_max_it = 10000, schur_max_it = 10000;
-  double vel_rtol = 1e-5, schur_rtol = 1e-5;
+  double vel_rtol = 1e-5, schur_rtol = 1e-5, svel_rtol = 1e-5;
+  int svel_max_it = 10000;
   Vecd diag;  // StokesMatGetDiagonalSchur: 1/eta at the pressure nodes
   // StokesPCApply{saddle} on the device (sb200_saddle_*, host/saddle.cpp): the default; -saddle_on_host 1 runs the same
   // composition in this file on host copies instead (kept as the cross-check of the device-resident one)
@@ -167,6 +168,7 @@ struct Flow {
     if (saddle_on_host) return 0;
     if (!dev_saddle) CHK(sb200_saddle_create(StokesGetHandle(ctx), saddle, &dev_saddle));
     CHK(sb200_saddle_set_inner(dev_saddle, vel_rtol, vel_max_it, schur_rtol, schur_max_it, svel_preonly ? 1 : 0));
+    CHK(sb200_saddle_set_svel(dev_saddle, svel_rtol, svel_max_it));
     sb200_apply_fn fv = vel.type == "none" ? nullptr : pc_device;
     HostPc& sp = svel_is_vel ? vel : svel;
     sb200_apply_fn fs = sp.type == "none" ? nullptr : pc_device;
@@ -234,7 +236,7 @@ struct Flow {
   int solve_schur_velocity(const Vecd& rhs, Vecd& x) {  // KSPSchurVelocity (stokes.C:338-341); -svel_ksp_type preonly = one PC application
     HostPc& pc = svel_is_vel ? vel : svel;
     if (svel_preonly) return pc_op(pc)(rhs, x);
-    return left_gmres(gv, shell_op(MatVV), pc_op(pc), rhs, x, vel_rtol, vel_max_it, false);
+    return left_gmres(gv, shell_op(MatVV), pc_op(pc), rhs, x, svel_rtol, svel_max_it, false);
   }
   int schur(const Vecd& p, Vecd& y) {  // StokesMatMultSchur (stokes.C:523-535)
     Vecd v0, v1;
@@ -364,6 +366,8 @@ int main(int argc, char** argv) {
   F.schur_max_it = o.integer("schur_ksp_max_it", 10000);
   F.schur_rtol = o.real("schur_ksp_rtol", 1e-5);
   F.svel_preonly = o.str("svel_ksp_type", "gmres") == "preonly";
+  F.svel_rtol = o.real("svel_ksp_rtol", 1e-5);  // KSPSchurVelocity's own prefix (stokes.C:338-341)
+  F.svel_max_it = o.integer("svel_ksp_max_it", 10000);
   F.saddle_on_host = o.integer("saddle_on_host", 0) != 0;
   F.vel.type = o.str("vel_pc_type", "ilu");  // PETSc's default PC for the SeqAIJ matrix MatVVPC is ILU(0); README:44 overrides it with hypre
   F.svel.type = o.str("svel_pc_type", "ilu");

@@ -106,6 +106,8 @@ PetscErrorCode StokesPCSetUp0(PC pc);
  * -schur_ksp_max_it, -svel_ksp_type preonly). */
 PetscErrorCode StokesSetVelocityPC(StokesCtxB200* ctx, StokesVelocitySolve vel_pc, void* vel_pc_ctx, StokesVelocitySolve svel_pc, void* svel_pc_ctx);
 PetscErrorCode StokesSetInnerSolves(StokesCtxB200* ctx, PetscReal vel_rtol, PetscInt vel_max_it, PetscReal schur_rtol, PetscInt schur_max_it, PetscTruth svel_preonly);
+/* -svel_ksp_rtol / -svel_ksp_max_it (KSPSchurVelocity's own prefix, stokes.C:338-341; defaults 1e-5 / 10000) */
+PetscErrorCode StokesSetSchurVelocityTolerances(StokesCtxB200* ctx, PetscReal svel_rtol, PetscInt svel_max_it);
 PetscErrorCode StokesPCApply0(PC pc, Vec x, Vec y);
 PetscErrorCode StokesPCApply1(PC pc, Vec x, Vec y);
 PetscErrorCode StokesPCApply2(PC pc, Vec x, Vec y);

@@ -289,6 +289,9 @@ int sb200_saddle_create(sb200_stokes* s, int type, sb200_saddle** out);
 int sb200_saddle_set_velocity_pc(sb200_saddle* p, sb200_apply_fn vel_pc, void* vel_ctx, sb200_apply_fn svel_pc, void* svel_ctx, int svel_same);
 /* -vel_ksp_rtol / -vel_ksp_max_it, -schur_ksp_rtol / -schur_ksp_max_it, -svel_ksp_type preonly (PETSc defaults: 1e-5, 10000, gmres) */
 int sb200_saddle_set_inner(sb200_saddle* p, double vel_rtol, int vel_maxits, double schur_rtol, int schur_maxits, int svel_preonly);
+/* -svel_ksp_rtol / -svel_ksp_max_it: KSPSchurVelocity has its own options prefix (stokes.C:338-341); PETSc defaults 1e-5, 10000.
+ * Only read when -svel_ksp_type is not preonly. */
+int sb200_saddle_set_svel(sb200_saddle* p, double svel_rtol, int svel_maxits);
 int sb200_saddle_apply(sb200_saddle* p, const double* d_x, double* d_y, void* stream); /* y = StokesPCApply{type}(x), g doubles */
 /* StokesRemoveConstantPressure's null space (stokes.C:1006-1025) applied to a global vector in place */
 int sb200_saddle_remove_constant_pressure(sb200_saddle* p, double* d_x, void* stream);

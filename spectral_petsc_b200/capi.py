@@ -634,12 +634,13 @@ class StokesSaddle:
     velocity_pc / svel_pc: callables z = M^-1 r on torch tensors of gv doubles (None = PCNONE); svel_pc defaults to velocity_pc."""
 
     def __init__(self, stokes, saddle_type=0, velocity_pc=None, svel_pc="same", vel_rtol=1e-5, vel_max_it=10000, schur_rtol=1e-5, schur_max_it=10000,
-                 svel_preonly=False):
+                 svel_preonly=False, svel_rtol=1e-5, svel_max_it=10000):
         self._h = ctypes.c_void_p()
         self.stokes = stokes
         _ck(lib().sb200_saddle_create(stokes._h, ctypes.c_int(saddle_type), ctypes.byref(self._h)))
         _ck(lib().sb200_saddle_set_inner(self._h, ctypes.c_double(vel_rtol), ctypes.c_int(vel_max_it), ctypes.c_double(schur_rtol), ctypes.c_int(schur_max_it),
                                          ctypes.c_int(int(svel_preonly))))
+        _ck(lib().sb200_saddle_set_svel(self._h, ctypes.c_double(svel_rtol), ctypes.c_int(svel_max_it)))
         self._keep = []
         fv = self._as_fn(velocity_pc)
         fs = fv if svel_pc == "same" else self._as_fn(svel_pc)

@@ -414,6 +414,7 @@ def stokes_main(argv, out=print, make_problem=GpuStokes):
     vel_max_it, vel_rtol = o.int("vel_ksp_max_it", 10000), o.real("vel_ksp_rtol", 1e-5)
     schur_max_it, schur_rtol = o.int("schur_ksp_max_it", 10000), o.real("schur_ksp_rtol", 1e-5)
     svel_preonly = o.string("svel_ksp_type", "gmres") == "preonly"
+    svel_max_it, svel_rtol = o.int("svel_ksp_max_it", 10000), o.real("svel_ksp_rtol", 1e-5)  # KSPSchurVelocity's own prefix (stokes.C:338-341)
     # PETSc's default PC for the SeqAIJ matrix MatVVPC is ILU(0); README:44 overrides it with hypre
     vel_pc, svel_pc = o.string("vel_pc_type", "ilu"), o.string("svel_pc_type", "ilu")
     vel_levels, svel_levels = o.int("vel_pc_factor_levels", 0), o.int("svel_pc_factor_levels", 0)
@@ -458,13 +459,13 @@ def stokes_main(argv, out=print, make_problem=GpuStokes):
             pcs["svel"] = pcs["svel"].update(P) if "svel" in pcs else HostPC(P, svel_pc, svel_levels)
         on_dev = lambda pc: (lambda v: prob.from_host(pc.apply(prob.to_host(v))))
         spc = solvers.StokesSaddlePC(prob, d, prob.krylov, on_dev(pcs["vel"]), saddle_type=saddle, vel_max_it=vel_max_it, schur_max_it=schur_max_it,
-                                     vel_rtol=vel_rtol, schur_rtol=schur_rtol, svel_preonly=svel_preonly)
+                                     vel_rtol=vel_rtol, schur_rtol=schur_rtol, svel_preonly=svel_preonly, svel_rtol=svel_rtol, svel_max_it=svel_max_it)
         if pcs["svel"] is not pcs["vel"]:
             svel = on_dev(pcs["svel"])
             if svel_preonly:
                 spc.solve_schur_velocity = svel
             else:
-                spc.solve_schur_velocity = lambda rhs: solvers.left_gmres(prob.krylov, prob.mat_mult_vv, svel, rhs, vel_rtol, vel_max_it)[0]
+                spc.solve_schur_velocity = lambda rhs: solvers.left_gmres(prob.krylov, prob.mat_mult_vv, svel, rhs, svel_rtol, svel_max_it)[0]
         return spc
 
     x = prob.from_host(np.zeros(prob.g))  # VecSet(x, 0.0), :215

@@ -202,8 +202,8 @@ struct StokesCtxB200 {
   void* vel_pc_ctx = nullptr;
   void* svel_pc_ctx = nullptr;
   std::vector<double> h_force;  // host copy of c->force (stokes.C:1001), what StokesStateView writes as vel_force / div_force
-  double vel_rtol = 1e-5, schur_rtol = 1e-5;  // KSP defaults
-  int vel_max_it = 10000, schur_max_it = 10000, svel_preonly = 0;
+  double vel_rtol = 1e-5, schur_rtol = 1e-5, svel_rtol = 1e-5;  // KSP defaults
+  int vel_max_it = 10000, schur_max_it = 10000, svel_max_it = 10000, svel_preonly = 0;
 };
 
 static PetscErrorCode stokes_fill(StokesCtxB200* c, std::vector<double>* U, std::vector<double>* U2, std::vector<double>* D) {
@@ -473,6 +473,13 @@ PetscErrorCode StokesSetInnerSolves(StokesCtxB200* c, PetscReal vel_rtol, PetscI
   return 0;
 }
 
+PetscErrorCode StokesSetSchurVelocityTolerances(StokesCtxB200* c, PetscReal svel_rtol, PetscInt svel_max_it) {
+  if (svel_rtol < 0 || svel_max_it < 0) return SB200_ERR_USER;
+  c->svel_rtol = svel_rtol;
+  c->svel_max_it = svel_max_it;
+  return 0;
+}
+
 // the C ABI hands a preconditioner raw device pointers; wrap them as Vecs for the PETSc-side PCApply
 static int vec_trampoline(StokesCtxB200* c, StokesVelocitySolve f, void* fctx, const double* d_r, double* d_z) {
   Vec r = nullptr, z = nullptr;
@@ -497,6 +504,7 @@ static PetscErrorCode stokes_saddle(StokesCtxB200* c, int type, sb200_saddle** o
   sb200_saddle* p = c->saddle[type];
   CHK(sb200_saddle_set_velocity_pc(p, c->vel_pc ? vel_pc_trampoline : nullptr, c, c->svel_pc ? svel_pc_trampoline : nullptr, c, 0));
   CHK(sb200_saddle_set_inner(p, c->vel_rtol, c->vel_max_it, c->schur_rtol, c->schur_max_it, c->svel_preonly));
+  CHK(sb200_saddle_set_svel(p, c->svel_rtol, c->svel_max_it));
   *out = p;
   return 0;
 }

@@ -28,8 +28,8 @@ struct sb200_saddle {
   sb200_apply_fn vel_pc = nullptr, svel_pc = nullptr;
   void* vel_ctx = nullptr;
   void* svel_ctx = nullptr;
-  double vel_rtol = 1e-5, schur_rtol = 1e-5;
-  int vel_maxits = 10000, schur_maxits = 10000;
+  double vel_rtol = 1e-5, schur_rtol = 1e-5, svel_rtol = 1e-5;       // PETSc's KSP defaults; KSPSchurVelocity has its own
+  int vel_maxits = 10000, schur_maxits = 10000, svel_maxits = 10000;  // "svel_" options prefix (stokes.C:338-341)
   bool svel_preonly = false;
   sb200_ksp* kvel = nullptr;    // KSPVelocity      (stokes.C:334-337)
   sb200_ksp* kschur = nullptr;  // KSPSchur         (stokes.C:328-333)
@@ -100,7 +100,7 @@ int solve_velocity(sb200_saddle* P, const double* rhs, double* x, void* stream) 
 int solve_schur_velocity(sb200_saddle* P, const double* rhs, double* x, void* stream) {
   if (P->svel_preonly) return pc_or_copy(P->svel_pc, P->svel_ctx, P->gv, rhs, x, stream);  // -svel_ksp_type preonly: one PC application
   CHK(pc_or_copy(P->svel_pc, P->svel_ctx, P->gv, rhs, P->v[UV], stream));
-  return left_gmres(P->ksvel, op_schur_velocity, P, P->v[UV], x, P->vel_rtol, P->vel_maxits, nullptr, stream);
+  return left_gmres(P->ksvel, op_schur_velocity, P, P->v[UV], x, P->svel_rtol, P->svel_maxits, nullptr, stream);
 }
 
 // StokesMatMultSchur (stokes.C:523-535): y = -PV * KSPSolve(KSPSchurVelocity, VP * x)
@@ -188,6 +188,17 @@ int sb200_saddle_set_inner(sb200_saddle* P, double vel_rtol, int vel_maxits, dou
   return 0;
 }
 
+int sb200_saddle_set_svel(sb200_saddle* P, double svel_rtol, int svel_maxits) {
+  if (!P) return SB200_ERR_ARG;
+  if (svel_rtol < 0 || svel_maxits < 0) {
+    sb200::set_last_error("sb200_saddle_set_svel: negative tolerance");
+    return SB200_ERR_USER;
+  }
+  P->svel_rtol = svel_rtol;
+  P->svel_maxits = svel_maxits;
+  return 0;
+}
+
 int sb200_saddle_apply(sb200_saddle* P, const double* d_x, double* d_y, void* stream) {
   if (!P || !d_x || !d_y || d_x == d_y) {
     sb200::set_last_error("StokesPCApply: x and y must be distinct non-null vectors");
@@ -195,7 +206,7 @@ int sb200_saddle_apply(sb200_saddle* P, const double* d_x, double* d_y, void* st
   }
   CHK(ensure_ksp(&P->kvel, &P->r_vel, P->gv, P->vel_maxits));
   CHK(ensure_ksp(&P->kschur, &P->r_schur, P->gp, P->schur_maxits));
-  if (!P->svel_preonly) CHK(ensure_ksp(&P->ksvel, &P->r_svel, P->gv, P->vel_maxits));
+  if (!P->svel_preonly) CHK(ensure_ksp(&P->ksvel, &P->r_svel, P->gv, P->svel_maxits));
   double *xv = P->v[XV], *xp = P->p[XP], *v1 = P->v[V1], *p1 = P->p[P1], *tp = P->p[TP];
   CHK(sb200_vec_split(P->gp, P->d, d_x, xv, xp, stream));              // scatterGV / scatterGP
   CHK(sb200_stokes_get_diagonal_schur(P->s, P->diag, stream));         // PCJacobi's MatGetDiagonal (1 / eta of the current state)

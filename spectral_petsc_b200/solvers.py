@@ -57,10 +57,11 @@ class StokesSaddlePC:
     velocity block (stands for -vel_pc_type / -svel_pc_type hypre on MatVVPC)."""
 
     def __init__(self, shells, d, krylov, velocity_pc, saddle_type=0, vel_max_it=4, schur_max_it=3, vel_rtol=1e-5, schur_rtol=1e-5,
-                 svel_preonly=True):
+                 svel_preonly=True, svel_rtol=1e-5, svel_max_it=10000):
         self.s, self.d, self.krylov, self.vpc = shells, d, krylov, velocity_pc
         self.type, self.vel_max_it, self.schur_max_it = saddle_type, vel_max_it, schur_max_it
         self.vel_rtol, self.schur_rtol, self.svel_preonly = vel_rtol, schur_rtol, svel_preonly
+        self.svel_rtol, self.svel_max_it = svel_rtol, svel_max_it  # KSPSchurVelocity's own "svel_" prefix (stokes.C:338-341)
         self.inner_its = {"velocity": 0, "schur": 0}
 
     # KSPVelocity: -vel_ksp_max_it 4, PC on MatVVPC (stokes.C:334-337)
@@ -73,7 +74,7 @@ class StokesSaddlePC:
     def solve_schur_velocity(self, rhs):
         if self.svel_preonly:
             return self.vpc(rhs)
-        x, _, _ = left_gmres(self.krylov, self.s.mat_mult_vv, self.vpc, rhs, self.vel_rtol, self.vel_max_it)
+        x, _, _ = left_gmres(self.krylov, self.s.mat_mult_vv, self.vpc, rhs, self.svel_rtol, self.svel_max_it)
         return x
 
     # StokesMatMultSchur (stokes.C:523-535): S p = -PV (A^-1 (VP p))

@@ -199,6 +199,7 @@ static int test_saddle(int n0) {
   // inner solves to 1e-12, no preconditioner on the velocity block (PCNONE), KSPSchurVelocity a full GMRES
   CHK(StokesSetVelocityPC(ctx, PETSC_NULL, PETSC_NULL, PETSC_NULL, PETSC_NULL));
   CHK(StokesSetInnerSolves(ctx, 1e-12, 2000, 1e-12, 500, PETSC_FALSE));
+  CHK(StokesSetSchurVelocityTolerances(ctx, 1e-12, 2000));  // -svel_ksp_rtol / -svel_ksp_max_it: KSPSchurVelocity has its own prefix
   std::vector<double> hx(g), hz(g);
   srand(11);
   for (PetscInt i = 0; i < g; i++) hx[i] = rand() / (double)RAND_MAX - 0.5;

@@ -60,8 +60,8 @@ def test_device_saddle_equals_torch_composition(cuda, saddle, dim, rheology, pre
 
     dinv = torch.from_numpy(1.0 / sps.csr_matrix((vals, colidx, rowptr), shape=(S.gv, S.gv)).diagonal()).to(cuda)
     vpc = lambda r: dinv * r  # Jacobi on MatVVPC stands for PETSc's PC (stays on the device: no host round trip in this test)
-    ref = solvers.StokesSaddlePC(S, d, solvers.make_gpu_krylov(), vpc, saddle_type=saddle, vel_max_it=4, schur_max_it=3, svel_preonly=preonly)
-    dev = sp.StokesSaddle(S, saddle, velocity_pc=vpc, vel_max_it=4, schur_max_it=3, svel_preonly=preonly)
+    ref = solvers.StokesSaddlePC(S, d, solvers.make_gpu_krylov(), vpc, saddle_type=saddle, vel_max_it=4, schur_max_it=3, svel_preonly=preonly, svel_max_it=4)
+    dev = sp.StokesSaddle(S, saddle, velocity_pc=vpc, vel_max_it=4, schur_max_it=3, svel_preonly=preonly, svel_max_it=4)  # (-svel_ksp_max_it 4)
     x = torch.from_numpy(np.random.default_rng(saddle).standard_normal(S.g)).to(cuda)
     y_ref = ref.apply(x)
     y = dev.apply(x)
@@ -79,7 +79,7 @@ def test_device_saddle_equals_torch_composition(cuda, saddle, dim, rheology, pre
 def test_block_lu_with_exact_inner_solves_inverts_the_operator(cuda):
     """stokes.C:1712-1713: "If applied exactly, this is a direct method." """
     S = _state(cuda, [7, 7, 7], 1)
-    dev = sp.StokesSaddle(S, 0, velocity_pc=None, vel_rtol=1e-12, vel_max_it=2000, schur_rtol=1e-12, schur_max_it=500, svel_preonly=False)
+    dev = sp.StokesSaddle(S, 0, velocity_pc=None, vel_rtol=1e-12, vel_max_it=2000, schur_rtol=1e-12, schur_max_it=500, svel_preonly=False, svel_rtol=1e-12, svel_max_it=2000)
     x = torch.from_numpy(np.random.default_rng(5).standard_normal(S.g)).to(cuda)
     sp.vec_remove_mean(x, stride=4, offset=3)
     y = dev.apply(S.mat_mult(x), remove_constant_pressure=True)
