@@ -51,6 +51,11 @@ struct sb200_elliptic {
   HostSlot q[SB200_HOST_QUEUE_DEPTH];
   cudaStream_t q_in = nullptr, q_op = nullptr, q_out = nullptr;
   long long q_submitted = 0, q_waited = 0;
+  // Ordering between FormFunction (any stream; it rewrites eta / deta / gradu) and the queue's applications (which read them):
+  // state_ev is recorded behind every FormFunction and waited for by every submission; a FormFunction waits for the last
+  // submitted application's op_done before it touches the state.
+  cudaEvent_t state_ev = nullptr;
+  bool state_recorded = false;
   FdAssembler* fd = nullptr;  // FormJacobian's matrix (built on first use)
 };
 
@@ -324,7 +329,13 @@ const char* sb200_elliptic_last_kernel(const sb200_elliptic* e) { return e ? e->
 int sb200_elliptic_function(sb200_elliptic* e, const double* d_U, double* d_F, void* stream) {
   SB_CHECK(e, SB200_ERR_ARG, "null context");
   SB_CHECK(!e->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier; the context refuses further work");
-  return e->c->function(d_U, d_F, (cudaStream_t)stream);
+  if (e->q_in && e->q_submitted > 0)  // queued applications still reading the old state finish first
+    SB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e->q[(e->q_submitted - 1) % SB200_HOST_QUEUE_DEPTH].op_done, 0));
+  SB_TRY(e->c->function(d_U, d_F, (cudaStream_t)stream));
+  if (!e->state_ev) SB_CUDA(cudaEventCreateWithFlags(&e->state_ev, cudaEventDisableTiming));
+  SB_CUDA(cudaEventRecord(e->state_ev, (cudaStream_t)stream));
+  e->state_recorded = true;
+  return 0;
 }
 
 static int elliptic_host_staging(sb200_elliptic* e) {
@@ -369,9 +380,11 @@ int sb200_elliptic_matmult_host_submit(sb200_elliptic* e, const double* h_U, dou
   SB_TRY(elliptic_host_queue(e));
   const size_t bytes = (size_t)e->c->gd.g * sizeof(double);
   auto& s = e->q[e->q_submitted % SB200_HOST_QUEUE_DEPTH];
+  // every application runs behind the last FormFunction, whatever stream that was issued on and whether or not the queue is idle
+  // (the non-blocking queue streams see no other stream's work by themselves)
+  if (e->state_recorded) SB_CUDA(cudaStreamWaitEvent(e->q_op, e->state_ev, 0));
   if (e->q_submitted == e->q_waited) {
-    // queue idle: order the first application behind whatever the caller enqueued before on the default stream
-    // (FormFunction refreshing eta / deta / gradu), which the non-blocking queue streams would otherwise not see
+    // queue idle: also behind whatever else the caller enqueued on the legacy default stream (set_rhs / set_dirichlet copies)
     SB_CUDA(cudaEventRecord(s.op_done, 0));
     SB_CUDA(cudaStreamWaitEvent(e->q_op, s.op_done, 0));
   }
@@ -483,10 +496,13 @@ int sb200_elliptic_debug_timeline(sb200_elliptic* e, unsigned long long* h_out20
 
 int sb200_elliptic_destroy(sb200_elliptic* e) {
   if (!e) return 0;
+  // applications still in flight use the context's scratch and write into the slots freed below: drain the queue first
+  if (e->q_op) cudaStreamSynchronize(e->q_op);
+  if (e->q_out) cudaStreamSynchronize(e->q_out);
   delete e->c;
   if (e->d_in) cudaFree(e->d_in);
   if (e->d_out) cudaFree(e->d_out);
-  if (e->q_out) cudaStreamSynchronize(e->q_out);  // applications still in flight write into the slots freed below
+  if (e->state_ev) cudaEventDestroy(e->state_ev);
   for (auto& s : e->q) {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
