@@ -250,6 +250,9 @@ int sb200_ksp_get_result(const sb200_ksp* k, int* its, double* rnorm, double* bn
 int sb200_ksp_get_history(const sb200_ksp* k, double* h_hist, int cap, int* n);   /* KSPGetResidualHistory */
 /* CUDA-event times of the last solve, split the way the north star asks: operator / PC ("timed separately") / KSP vector work. */
 int sb200_ksp_get_times(const sb200_ksp* k, double* ms_operator, double* ms_pc, double* ms_orthogonalisation);
+/* Sum of count <= 64 device doubles over the ranks of a slab-partitioned solver, in rank order (same bits on every rank), in place;
+ * collective, no-op on one rank.  (The all-reduce FGMRES uses for its dot products: peer memory + epoch flags, no NCCL.) */
+int sb200_ksp_allreduce_sum(sb200_ksp* k, double* d_vals, int count, void* stream);
 int sb200_ksp_ipc_export(sb200_ksp* k, void* handle);
 int sb200_ksp_ipc_attach(sb200_ksp* k, int peer_rank, const void* handle);
 int sb200_ksp_attach_local(sb200_ksp* k, int peer_rank, sb200_ksp* peer);
@@ -276,6 +279,10 @@ int sb200_csr_diagonal(long long nrows, const int* d_rowptr, const int* d_colidx
  * the global vector are stride d+1, offset d).  d_scratch: SB200_REDUCE_SCRATCH_DOUBLES doubles of device memory. */
 #define SB200_REDUCE_SCRATCH_DOUBLES 1024
 int sb200_vec_remove_mean(long long n, int stride, int offset, double* d_x, double* d_scratch, void* stream);
+/* The same in two steps for vectors that are slab-partitioned over several ranks: d_out2 = {sum of the local entries, local count}
+ * (fixed summation order); after the ranks have added their pairs (sb200_ksp_allreduce_sum), x -= d_sums2[0] / d_sums2[1]. */
+int sb200_vec_sum_count(long long n, int stride, int offset, const double* d_x, double* d_scratch, double* d_out2, void* stream);
+int sb200_vec_shift_mean(long long n, int stride, int offset, double* d_x, const double* d_sums2, void* stream);
 
 /* ---- StokesPCApply0..3 (stokes.C:1714-1817): the saddle-point preconditioners, device resident -----------------------------
  * Composition of the PV / VP / VV shells with the three inner Krylov solves of stokes.C:328-341 - KSPVelocity, KSPSchur (on the
@@ -292,6 +299,16 @@ int sb200_saddle_set_inner(sb200_saddle* p, double vel_rtol, int vel_maxits, dou
 /* -svel_ksp_rtol / -svel_ksp_max_it: KSPSchurVelocity has its own options prefix (stokes.C:338-341); PETSc defaults 1e-5, 10000.
  * Only read when -svel_ksp_type is not preonly. */
 int sb200_saddle_set_svel(sb200_saddle* p, double svel_rtol, int svel_maxits);
+/* Slab-partitioned Stokes context (config 5 as a SOLVE over 2/4/8 GPUs): the three inner Krylov solvers are slab solvers whose dot products
+ * cross the ranks, and the constant-pressure null space is removed with a cross-rank mean.  After sb200_saddle_set_inner / _set_svel call
+ * sb200_saddle_prepare (creates the inner solvers), exchange the SB200_SADDLE_HANDLE_BYTES-byte handle of sb200_saddle_ipc_export between
+ * the ranks (MPI_Allgather / torch.distributed.all_gather) and attach every peer's; sb200_saddle_attach_local maps a peer context that lives
+ * in the same process (tests).  Every sb200_saddle_apply is then a collective.  On one rank none of this is needed. */
+#define SB200_SADDLE_HANDLE_BYTES 192
+int sb200_saddle_prepare(sb200_saddle* p);
+int sb200_saddle_ipc_export(sb200_saddle* p, void* handle192);
+int sb200_saddle_ipc_attach(sb200_saddle* p, int peer_rank, const void* handle192);
+int sb200_saddle_attach_local(sb200_saddle* p, int peer_rank, sb200_saddle* peer);
 int sb200_saddle_apply(sb200_saddle* p, const double* d_x, double* d_y, void* stream); /* y = StokesPCApply{type}(x), g doubles */
 /* StokesRemoveConstantPressure's null space (stokes.C:1006-1025) applied to a global vector in place */
 int sb200_saddle_remove_constant_pressure(sb200_saddle* p, double* d_x, void* stream);

@@ -645,6 +645,24 @@ class StokesSaddle:
         fv = self._as_fn(velocity_pc)
         fs = fv if svel_pc == "same" else self._as_fn(svel_pc)
         _ck(lib().sb200_saddle_set_velocity_pc(self._h, fv, None, fs, None, ctypes.c_int(0)))
+        # slab-partitioned Stokes context: the inner solvers are slab solvers; create them now so that their arenas can be exchanged
+        # (spectral_petsc_b200.dist.attach_peers(pc) / attach_in_process([...])) before the first - collective - apply
+        self.rank, self.nranks = getattr(stokes, "rank", 0), getattr(stokes, "nranks", 1)
+        if self.nranks > 1:
+            _ck(lib().sb200_saddle_prepare(self._h))
+
+    HANDLE_BYTES = 192
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        _ck(lib().sb200_saddle_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, peer_rank, handle):
+        _ck(lib().sb200_saddle_ipc_attach(self._h, ctypes.c_int(peer_rank), ctypes.c_char_p(handle)))
+
+    def attach_local(self, peer_rank, peer):
+        _ck(lib().sb200_saddle_attach_local(self._h, ctypes.c_int(peer_rank), peer._h))
 
     def _as_fn(self, f):
         if f is None:

@@ -83,6 +83,12 @@ int sb200_ksp_get_times(const sb200_ksp* k, double* ms_operator, double* ms_pc, 
   return 0;
 }
 
+int sb200_ksp_allreduce_sum(sb200_ksp* k, double* d_vals, int count, void* stream) {
+  SB_CHECK(k && d_vals && count >= 1, SB200_ERR_ARG, "sb200_ksp_allreduce_sum: bad arguments");
+  SB_CHECK(!k->c->arena.failed(), SB200_ERR_CUDA, "slab partition: a device-side flag wait timed out earlier; the context refuses further work");
+  return k->c->allreduce(d_vals, count, (cudaStream_t)stream);
+}
+
 int sb200_ksp_ipc_export(sb200_ksp* k, void* handle) {
   SB_CHECK(k, SB200_ERR_ARG, "null context");
   return k->c->arena.export_handle(handle);

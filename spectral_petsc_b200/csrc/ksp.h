@@ -53,10 +53,10 @@ struct KspCtx {
   static int create(long long n, int restart, int rank, int nranks, KspCtx** out);
   ~KspCtx();
   int solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s);
+  int allreduce(double* vals, int k, cudaStream_t s);  // sum over the slab ranks in rank order, in place (no-op on one rank)
 
  private:
   int init(long long n, int restart, int rank, int nranks);
-  int allreduce(double* vals, int k, cudaStream_t s);
   int dots(const double* x, const double* Y, long long ldy, int nv, double* out, cudaStream_t s);
   int norm(const double* x, double* out, cudaStream_t s);
 };

@@ -112,6 +112,25 @@ __global__ void __launch_bounds__(TPB) sub_mean_kernel(long long n, int stride_x
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) x[off + i * stride_x] -= mean;
 }
 
+// out[0] = sum of the np partials (one block, fixed order), out[1] = n: what the slab ranks add up before the mean is formed
+__global__ void __launch_bounds__(TPB) sum_final_kernel(const double* __restrict__ partial, int np, long long n, double* __restrict__ out) {
+  __shared__ double sm[TPB / 32];
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < np; b += TPB) acc += partial[b];
+  const double t = block_sum_all(acc, sm);
+  if (threadIdx.x == 0) {
+    out[0] = t;
+    out[1] = (double)n;
+  }
+}
+
+// x[off + i*stride] -= sums[0] / sums[1]
+__global__ void __launch_bounds__(TPB) shift_kernel(long long n, int stride_x, int off, double* __restrict__ x, const double* __restrict__ sums) {
+  const double mean = sums[0] / sums[1];
+  const long long stride = (long long)gridDim.x * TPB;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) x[off + i * stride_x] -= mean;
+}
+
 }  // namespace
 }  // namespace sb200
 
@@ -162,6 +181,25 @@ int sb200_csr_diagonal(long long nrows, const int* d_rowptr, const int* d_colidx
   SB_CHECK(nrows >= 0 && d_rowptr && d_colidx && d_vals && d_diag, SB200_ERR_ARG, "sb200_csr_diagonal: bad arguments");
   if (nrows == 0) return 0;
   csr_diagonal_kernel<<<blocks_for(nrows, 148 * 16), TPB, 0, (cudaStream_t)stream>>>(nrows, d_rowptr, d_colidx, d_vals, d_diag);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sb200_vec_sum_count(long long n, int stride, int offset, const double* d_x, double* d_scratch, double* d_out2, void* stream) {
+  SB_CHECK(n >= 0 && stride >= 1 && offset >= 0 && offset < stride && d_scratch && d_out2 && (d_x || n == 0), SB200_ERR_ARG, "sb200_vec_sum_count: bad arguments");
+  const int np = n > 0 ? blocks_for(n, MAX_PARTIALS) : 0;
+  if (np > 0) sum_partial_kernel<<<np, TPB, 0, (cudaStream_t)stream>>>(n, stride, offset, d_x, d_scratch);
+  sum_final_kernel<<<1, TPB, 0, (cudaStream_t)stream>>>(d_scratch, np, n, d_out2);
+  count_launch(np > 0 ? 2 : 1);
+  SB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sb200_vec_shift_mean(long long n, int stride, int offset, double* d_x, const double* d_sums2, void* stream) {
+  SB_CHECK(n >= 0 && stride >= 1 && offset >= 0 && offset < stride && d_sums2 && (d_x || n == 0), SB200_ERR_ARG, "sb200_vec_shift_mean: bad arguments");
+  if (n == 0) return 0;
+  shift_kernel<<<blocks_for(n, 148 * 16), TPB, 0, (cudaStream_t)stream>>>(n, stride, offset, d_x, d_sums2);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return 0;

@@ -41,6 +41,8 @@ struct sb200_saddle {
   double* p[5] = {};
   double* diag = nullptr;
   double* scratch = nullptr;
+  double* sums = nullptr;  // {sum, count} of a mean removal (summed over the ranks on a slab partition)
+  int rank = 0, nranks = 1;  // slab partition of the Stokes context (1 = single GPU)
 };
 
 namespace {
@@ -68,14 +70,36 @@ int op_schur_velocity(void* ctx, const double* x, double* y, void* stream) {  //
 
 // GMRES(30) that may take at most maxits < 30 iterations never restarts, so it only needs maxits + 1 basis vectors: the solver is
 // (re)created with restart = min(30, maxits) - identical iterates, a sixth of the memory for the usual -vel_ksp_max_it 4.
-int ensure_ksp(sb200_ksp** k, int* have, long long n, int maxits) {
+// On a slab partition the solvers are created by sb200_saddle_prepare (their arenas are exchanged between the ranks afterwards) and
+// may not be re-created behind the peers' backs.
+int ensure_ksp(sb200_saddle* P, sb200_ksp** k, int* have, long long n, int maxits, bool may_create) {
   const int want = maxits < 1 ? 1 : (maxits < 30 ? maxits : 30);
   if (*k && *have == want) return 0;
+  if (!may_create) {
+    sb200::set_last_error("slab-partitioned saddle PC: call sb200_saddle_prepare and attach the peers after changing the inner solvers' settings");
+    return SB200_ERR_USER;
+  }
   if (*k) sb200_ksp_destroy(*k);
   *k = nullptr;
-  CHK(sb200_ksp_create(n, want, k));
+  CHK(sb200_ksp_create_slab(n, want, P->rank, P->nranks, k));
   *have = want;
   return 0;
+}
+
+int ensure_all(sb200_saddle* P, bool may_create) {
+  CHK(ensure_ksp(P, &P->kvel, &P->r_vel, P->gv, P->vel_maxits, may_create));
+  CHK(ensure_ksp(P, &P->kschur, &P->r_schur, P->gp, P->schur_maxits, may_create));
+  if (!P->svel_preonly) CHK(ensure_ksp(P, &P->ksvel, &P->r_svel, P->gv, P->svel_maxits, may_create));
+  return 0;
+}
+
+// VecAXPY with the mean / MatNullSpaceRemove of the constant vector (stokes.C:1006-1025); on a slab partition the mean is global:
+// local {sum, count} pairs are added over the ranks through the Schur solver's peer-memory all-reduce (rank order, same bits everywhere)
+int remove_mean(sb200_saddle* P, long long n, int stride, int offset, double* x, void* stream) {
+  if (P->nranks == 1) return sb200_vec_remove_mean(n, stride, offset, x, P->scratch, stream);
+  CHK(sb200_vec_sum_count(n, stride, offset, x, P->scratch, P->sums, stream));
+  CHK(sb200_ksp_allreduce_sum(P->kschur, P->sums, 2, stream));
+  return sb200_vec_shift_mean(n, stride, offset, x, P->sums, stream);
 }
 
 // left-preconditioned GMRES: x = KSPSolve(b), Minv(b) staged in pb
@@ -113,7 +137,7 @@ int schur_mult(sb200_saddle* P, const double* p, double* y, void* stream) {
 
 int jacobi_project(sb200_saddle* P, const double* r, double* z, void* stream) {  // PCJacobi with 1/eta, then the constant null space
   CHK(sb200_vec_pointwise_divide(P->gp, r, P->diag, z, stream));
-  return sb200_vec_remove_mean(P->gp, 1, 0, z, P->scratch, stream);
+  return remove_mean(P, P->gp, 1, 0, z, stream);
 }
 
 int op_schur(void* ctx, const double* x, double* y, void* stream) {  // KSPSchur: A = the Schur shell, M = Jacobi
@@ -145,18 +169,14 @@ int sb200_saddle_create(sb200_stokes* s, int type, sb200_saddle** out) {
   P->s = s;
   P->type = type;
   int rc = sb200_stokes_sizes(s, &P->m, &P->g, &P->gp, &P->gv, &P->dv);
-  int nranks = 1;
-  if (!rc) rc = sb200_stokes_slab_info(s, nullptr, &nranks, nullptr, nullptr, nullptr);
-  if (!rc && nranks != 1) {  // the inner KSPs and the null-space projection here reduce over one rank's vectors only
-    sb200::set_last_error("sb200_saddle_create: the saddle-point preconditioners are single-GPU (the context is slab-partitioned)");
-    rc = SB200_ERR_SUP;
-  }
+  if (!rc) rc = sb200_stokes_slab_info(s, &P->rank, &P->nranks, nullptr, nullptr, nullptr);
   if (!rc && P->gp <= 0) rc = SB200_ERR_USER;
   if (!rc) P->d = (int)(P->gv / P->gp);
   for (int i = 0; i < 8 && !rc; i++) rc = sb200_malloc((void**)&P->v[i], (size_t)P->gv * sizeof(double) + 16);
   for (int i = 0; i < 5 && !rc; i++) rc = sb200_malloc((void**)&P->p[i], (size_t)P->gp * sizeof(double) + 16);
   if (!rc) rc = sb200_malloc((void**)&P->diag, (size_t)P->gp * sizeof(double) + 16);
   if (!rc) rc = sb200_malloc((void**)&P->scratch, SB200_REDUCE_SCRATCH_DOUBLES * sizeof(double));
+  if (!rc) rc = sb200_malloc((void**)&P->sums, 64 * sizeof(double));
   if (rc) {
     sb200_saddle_destroy(P);
     return rc;
@@ -204,9 +224,7 @@ int sb200_saddle_apply(sb200_saddle* P, const double* d_x, double* d_y, void* st
     sb200::set_last_error("StokesPCApply: x and y must be distinct non-null vectors");
     return SB200_ERR_ARG;
   }
-  CHK(ensure_ksp(&P->kvel, &P->r_vel, P->gv, P->vel_maxits));
-  CHK(ensure_ksp(&P->kschur, &P->r_schur, P->gp, P->schur_maxits));
-  if (!P->svel_preonly) CHK(ensure_ksp(&P->ksvel, &P->r_svel, P->gv, P->svel_maxits));
+  CHK(ensure_all(P, P->nranks == 1));
   double *xv = P->v[XV], *xp = P->p[XP], *v1 = P->v[V1], *p1 = P->p[P1], *tp = P->p[TP];
   CHK(sb200_vec_split(P->gp, P->d, d_x, xv, xp, stream));              // scatterGV / scatterGP
   CHK(sb200_stokes_get_diagonal_schur(P->s, P->diag, stream));         // PCJacobi's MatGetDiagonal (1 / eta of the current state)
@@ -243,7 +261,45 @@ int sb200_saddle_apply(sb200_saddle* P, const double* d_x, double* d_y, void* st
 
 int sb200_saddle_remove_constant_pressure(sb200_saddle* P, double* d_x, void* stream) {
   if (!P || !d_x) return SB200_ERR_ARG;
-  return sb200_vec_remove_mean(P->gp, P->d + 1, P->d, d_x, P->scratch, stream);
+  if (P->nranks > 1) CHK(ensure_all(P, false));
+  return remove_mean(P, P->gp, P->d + 1, P->d, d_x, stream);
+}
+
+// ---- slab partition: the inner solvers' peer-mapped arenas -------------------------------------------------------------------
+int sb200_saddle_prepare(sb200_saddle* P) {
+  if (!P) return SB200_ERR_ARG;
+  return ensure_all(P, true);
+}
+
+int sb200_saddle_ipc_export(sb200_saddle* P, void* handle192) {
+  if (!P || !handle192) return SB200_ERR_ARG;
+  CHK(ensure_all(P, false));
+  char* h = (char*)handle192;
+  for (int i = 0; i < SB200_SADDLE_HANDLE_BYTES; i++) h[i] = 0;
+  CHK(sb200_ksp_ipc_export(P->kvel, h));
+  CHK(sb200_ksp_ipc_export(P->kschur, h + 64));
+  if (P->ksvel) CHK(sb200_ksp_ipc_export(P->ksvel, h + 128));
+  return 0;
+}
+
+int sb200_saddle_ipc_attach(sb200_saddle* P, int peer_rank, const void* handle192) {
+  if (!P || !handle192) return SB200_ERR_ARG;
+  CHK(ensure_all(P, false));
+  const char* h = (const char*)handle192;
+  CHK(sb200_ksp_ipc_attach(P->kvel, peer_rank, h));
+  CHK(sb200_ksp_ipc_attach(P->kschur, peer_rank, h + 64));
+  if (P->ksvel) CHK(sb200_ksp_ipc_attach(P->ksvel, peer_rank, h + 128));
+  return 0;
+}
+
+int sb200_saddle_attach_local(sb200_saddle* P, int peer_rank, sb200_saddle* peer) {
+  if (!P || !peer) return SB200_ERR_ARG;
+  CHK(ensure_all(P, false));
+  CHK(ensure_all(peer, false));
+  CHK(sb200_ksp_attach_local(P->kvel, peer_rank, peer->kvel));
+  CHK(sb200_ksp_attach_local(P->kschur, peer_rank, peer->kschur));
+  if (P->ksvel && peer->ksvel) CHK(sb200_ksp_attach_local(P->ksvel, peer_rank, peer->ksvel));
+  return 0;
 }
 
 int sb200_apply_saddle(void* ctx, const double* d_x, double* d_y, void* stream) {
@@ -267,6 +323,7 @@ int sb200_saddle_destroy(sb200_saddle* P) {
     if (a) sb200_free(a);
   if (P->diag) sb200_free(P->diag);
   if (P->scratch) sb200_free(P->scratch);
+  if (P->sums) sb200_free(P->sums);
   if (P->kvel) sb200_ksp_destroy(P->kvel);
   if (P->kschur) sb200_ksp_destroy(P->kschur);
   if (P->ksvel) sb200_ksp_destroy(P->ksvel);

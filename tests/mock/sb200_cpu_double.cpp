@@ -278,6 +278,24 @@ int sb200_vec_remove_mean(long long n, int stride, int offset, double* x, double
   for (long long i = 0; i < n; i++) x[offset + i * stride] -= s;
   return 0;
 }
+int sb200_vec_sum_count(long long n, int stride, int offset, const double* x, double* scratch, double* out2, void*) {
+  if (n < 0 || stride < 1 || offset < 0 || offset >= stride || !scratch || !out2) FAIL(SB200_ERR_ARG, "sb200_vec_sum_count: bad arguments");
+  double s = 0;
+  for (long long i = 0; i < n; i++) s += x[offset + i * stride];
+  out2[0] = s;
+  out2[1] = (double)n;
+  return 0;
+}
+int sb200_vec_shift_mean(long long n, int stride, int offset, double* x, const double* sums2, void*) {
+  if (n < 0 || stride < 1 || offset < 0 || offset >= stride || !sums2) FAIL(SB200_ERR_ARG, "sb200_vec_shift_mean: bad arguments");
+  const double mean = sums2[0] / sums2[1];
+  for (long long i = 0; i < n; i++) x[offset + i * stride] -= mean;
+  return 0;
+}
+int sb200_ksp_allreduce_sum(sb200_ksp*, double*, int, void*) { return 0; }  // single rank: the sum over the ranks is the value itself
+int sb200_ksp_ipc_export(sb200_ksp*, void*) { FAIL(SB200_ERR_SUP, "test double: single rank only"); }
+int sb200_ksp_ipc_attach(sb200_ksp*, int, const void*) { FAIL(SB200_ERR_SUP, "test double: single rank only"); }
+int sb200_ksp_attach_local(sb200_ksp*, int, sb200_ksp*) { FAIL(SB200_ERR_SUP, "test double: single rank only"); }
 int sb200_stream_sync(void*) { return 0; }
 // measurement helper: the double has no tensor pipe; a nominal figure keeps bench.py's dry run going
 int sb200_fp64_dmma_peak(double, double* tflops, double* measured_ms) {

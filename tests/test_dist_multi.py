@@ -40,3 +40,16 @@ def test_stokes_slab_multi_process(world):
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
     assert out.returncode == 0, out.stderr[-2000:]
     assert len(lines) == 1 and lines[0]["ok"] and lines[0]["ranks"] == world
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_slab_saddle_solve_multi_process(world):
+    """Config 5 as a SOLVE on the slab partition: outer FGMRES + block-LU saddle PC with slab inner solvers (tests/dist/dist_saddle.py)."""
+    if _ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "dist", "dist_saddle.py"), "16" if world == 8 else "32"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"check"')]
+    assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+    assert len(lines) == 1 and lines[0]["ok"] and lines[0]["ranks"] == world
