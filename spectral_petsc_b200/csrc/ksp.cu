@@ -19,6 +19,26 @@ namespace {
 
 constexpr int CHMAX = 32;    // vectors per dot-product pass: template parameter CH in {8, 16, 32}; 8 is the default (measured), SB200_KSP_MDOT_CH raises it
 constexpr int TPB = 256;
+
+// The vector kernels of an Arnoldi step follow each other on one stream, each a few tens of microseconds long: launched as programmatic
+// dependents, a kernel's blocks are set up while its predecessor drains and wait (griddepcontrol.wait) before their first global access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 constexpr int SLOT = 64;     // doubles per all-reduce slot
 
 __device__ __forceinline__ double block_sum(double v, double* sm) {
@@ -40,6 +60,8 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(const double* __restrict__ x,
                                                    int vec2) {
   __shared__ double sm[TPB / 32];
   __shared__ bool last;
+  pdl_go();
+  pdl_wait();
   const int j0 = blockIdx.y * CH, cnt = min(CH, nv - j0);
   double acc[CH];
 #pragma unroll
@@ -132,6 +154,8 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
   __shared__ double sm[TPB / 32];
   __shared__ double cs[64];
   __shared__ bool last;
+  pdl_go();
+  pdl_wait();
   if (threadIdx.x < nv) cs[threadIdx.x] = sign * c[threadIdx.x];
   __syncthreads();
   double acc = 0.0;
@@ -193,6 +217,8 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(double* __restrict__ y, cons
 
 // y = a*x (+ b*z)   with a read from device memory as  a = *pa  (or 1/sqrt-free: the caller prepares it)
 __global__ void scale_kernel2(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ pa, long long n) {
+  pdl_go();
+  pdl_wait();
   const double a = *pa;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * x[i];
@@ -382,7 +408,7 @@ int KspCtx::dots(const double* x, const double* Y, long long ldy, int nv, double
     chcap = c ? atoi(c) : 8;  // measured on B200 (profiles/r02_notes.md): 8 vectors per pass beat 16 and 32 (registers, concurrent DRAM streams)
   }
   if (nv <= 8 || chcap <= 8) {
-    mdot_kernel<8><<<dim3(nblocks, (nv + 7) / 8), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
+    SB_CUDA(launch_pdl(mdot_kernel<8>, dim3(nblocks, (nv + 7) / 8), dim3(TPB), s, x, Y, ldy, nv, n, partial, counters, out, vec2));
   } else if (nv <= 16 || chcap <= 16) {
     mdot_kernel<16><<<dim3(nblocks, (nv + 15) / 16), TPB, 0, s>>>(x, Y, ldy, nv, n, partial, counters, out, vec2);
   } else {
@@ -466,14 +492,15 @@ int KspCtx::solve(const double* b, double* x, bool guess_nonzero, cudaStream_t s
       ha.k = kq;
       ha.rnorm_dev = sp.scr + 3;
       ha.rnorm_host = d_rnorm + (kq % NRING);
-      maxpy_kernel<<<g1, TPB, 0, s>>>(w, V, ld, kq + 1, sp.hcol, -1.0, n, partial, counters + 32, sp.hcol + (kq + 1), 1, ha, maxpy_desc());
+      SB_CUDA(launch_pdl(maxpy_kernel, dim3(g1), dim3(TPB), s, w, (const double*)V, ld, kq + 1, (const double*)sp.hcol, -1.0, n, partial, counters + 32,
+                         sp.hcol + (kq + 1), 1, ha, maxpy_desc()));
       count_launch();
       if (!ha.on) {
         SB_TRY(allreduce(sp.hcol + (kq + 1), 1, s));
         hess_kernel<<<1, 1, 0, s>>>(sp, kq, sp.scr + 3, d_rnorm + (kq % NRING));
         count_launch();
       }
-      scale_kernel2<<<g1, TPB, 0, s>>>(V + (size_t)(kq + 1) * ld, w, sp.scr + 1, n);
+      SB_CUDA(launch_pdl(scale_kernel2, dim3(g1), dim3(TPB), s, V + (size_t)(kq + 1) * ld, (const double*)w, (const double*)(sp.scr + 1), n));
       count_launch();
       SB_CUDA(cudaEventRecord(e[3], s));
       SB_CUDA(cudaGetLastError());

@@ -273,7 +273,7 @@ int sb200_saddle_prepare(sb200_saddle* P) {
 
 int sb200_saddle_ipc_export(sb200_saddle* P, void* handle192) {
   if (!P || !handle192) return SB200_ERR_ARG;
-  CHK(ensure_all(P, false));
+  CHK(ensure_all(P, P->nranks == 1));
   char* h = (char*)handle192;
   for (int i = 0; i < SB200_SADDLE_HANDLE_BYTES; i++) h[i] = 0;
   CHK(sb200_ksp_ipc_export(P->kvel, h));
@@ -284,7 +284,7 @@ int sb200_saddle_ipc_export(sb200_saddle* P, void* handle192) {
 
 int sb200_saddle_ipc_attach(sb200_saddle* P, int peer_rank, const void* handle192) {
   if (!P || !handle192) return SB200_ERR_ARG;
-  CHK(ensure_all(P, false));
+  CHK(ensure_all(P, P->nranks == 1));
   const char* h = (const char*)handle192;
   CHK(sb200_ksp_ipc_attach(P->kvel, peer_rank, h));
   CHK(sb200_ksp_ipc_attach(P->kschur, peer_rank, h + 64));
