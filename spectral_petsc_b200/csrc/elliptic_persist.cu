@@ -116,9 +116,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(s) : "memory");
 }
 
-template <int P, int NT, bool RIGHT, bool DEEP, bool PENCIL = false, bool WAITDONE = false>
+struct NoEarly {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// after_gemm2: called once the second GEMM has read the block for the last time (the block is free): the single-GPU kernel grabs its
+// next ticket and issues that item's load there, so the load flies during the epilogue instead of after it.
+template <int P, int NT, bool RIGHT, bool DEEP, bool PENCIL = false, bool WAITDONE = false, typename F = NoEarly>
 __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long long n0, const double* Ae,
-                                         const double* Bo, double* Xw, int lane, const SlabMaps* maps = nullptr, double* stage = nullptr) {
+                                         const double* Bo, double* Xw, int lane, const SlabMaps* maps = nullptr, double* stage = nullptr,
+                                         F after_gemm2 = F()) {
   using E = EO<P>;
   static_assert(!(PENCIL && RIGHT), "pencil items are strided-axis items");
   constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
@@ -154,6 +161,10 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
     prefetch_block<P, RIGHT>(eta_a, base0[j], lg.R, lane);
     prefetch_block<P, RIGHT>(deta_a, base0[j], lg.R, lane);
     prefetch_block<P, RIGHT>(g0, base0[j], lg.R, lane);
+    if (RIGHT && !PENCIL) {
+      // last axis: the partial sums its epilogue adds (4 dependent batches of loads) are pulled into L2 now, a whole chain ahead
+      for (int k = 0; k < p.d - 1; k++) prefetch_block<P, true>(p.part[k], base0[j], 1, lane);
+    }
   }
   cp_async_wait<0>();
   __syncwarp();
@@ -188,6 +199,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
   STAMP(3);
   eo_gemm_nt<P, NT, RIGHT>(Ae, Bo, Xw, a, b, g, t);
   __syncwarp();  // block free again (the caller refills it while the epilogue drains)
+  after_gemm2();
   STAMP(4);
 
   if (XF(p, 2)) {
@@ -532,6 +544,7 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
     }
     pencil_done = 0;
   };
+  unsigned nxt = 0;
   while (tk < total) {
     if (SLAB && !LASTPHASE && tk >= nlocal + items0) {
       if (pencil_done) report_pencils();  // before this warp may block on the other ranks' DONE
@@ -544,15 +557,27 @@ __global__ void __maxnreg__(persist_maxreg(NWARPS, SLAB && !LASTPHASE)) persist_
       const int arel = LASTPHASE ? 0 : tl / items_per_axis;
       const int axis = LASTPHASE ? p.d - 1 : p.first_axis + arel;
       const long long n0 = (long long)(tl - arel * items_per_axis) * (8 * NT);
-      run_item<P, NT, LASTPHASE, DEEP, false, SLAB && LASTPHASE>(p, axis, n0, Ae, Bo, Xw, lane);
+      if (SLAB) {
+        run_item<P, NT, LASTPHASE, DEEP, false, SLAB && LASTPHASE>(p, axis, n0, Ae, Bo, Xw, lane);
+      } else {
+        auto early = [&]() {
+          nxt = grab();
+          issue_load(nxt);
+        };
+        run_item<P, NT, LASTPHASE, DEEP, false, false>(p, axis, n0, Ae, Bo, Xw, lane, nullptr, nullptr, early);
+      }
       if (merged) {
         __threadfence();  // this item's partial rows are visible device-wide before it checks in
         __syncwarp();
         if (lane == 0) atomicAdd(sync + 6, 1u);
       }
     }
-    tk = grab();
-    issue_load(tk);  // run_item waits for it at its top
+    if (SLAB) {
+      tk = grab();
+      issue_load(tk);  // run_item waits for it at its top
+    } else {
+      tk = nxt;  // grabbed and loading since the end of GEMM2
+    }
   }
   cp_async_wait<0>();
   if (SLAB && !LASTPHASE && pencil_done) report_pencils();
@@ -659,7 +684,8 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
   static int cfg = -1, stg = -1;
   if (cfg < 0) {
     const char* c = getenv("SB200_PERSIST_CFG");
-    cfg = c ? atoi(c) : 2;  // 8 warps x 255 registers measured best on B200 (profiles/r01_notes.md)
+    cfg = c ? atoi(c) : -1;  // default: 12 warps x 168 registers on one GPU (0.0993 ms against 0.1014 ms for 8 x 255, profiles/r02_notes.md),
+                             // 8 x 255 on a slab partition (its staging blocks need the shared memory of the extra warps' blocks)
     const char* g = getenv("SB200_STAGGER");
     stg = g ? atoi(g) : 6000;
   }
@@ -678,9 +704,11 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
       SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: extent 96 is a single-GPU instantiation");
       return run_cfg<96, 12, 1>(p, s);
     case 128:
-      switch (cfg) {
+      switch (cfg >= 0 ? cfg : (p.nranks > 1 ? 2 : 1)) {
         case 0: return run_cfg<128, 16, 1>(p, s);
-        case 1: return run_cfg<128, 12, 1>(p, s);
+        case 1:
+          if (p.nranks > 1) return run_cfg<128, 8, 1>(p, s);  // (12 warps + staging blocks exceed the shared memory of an SM)
+          return run_cfg<128, 12, 1>(p, s);
         case 3: return run_cfg<128, 8, 2>(p, s);
         default: return run_cfg<128, 8, 1>(p, s);
       }
