@@ -41,49 +41,34 @@ __device__ __forceinline__ int xaddr(int m, int c) {
 // LEFT  (!RIGHT): matrices are the A operand.  acc[i][h] <-> pair index i*8+g, line 2t+h.
 // RIGHT:          the field is the A operand.   acc[i][h] <-> line g, pair index i*8+2t+h.
 // Either way a thread's two values are adjacent in global memory (16-byte accesses).
+// (Defined after eo_gemm_nt, which it wraps, so that every fused path shares one summation order.)
 template <int P, bool RIGHT>
 __device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const double* __restrict__ Bo,
                                         const double* __restrict__ Xw, double (&a)[EO<P>::MT][2],
-                                        double (&b)[EO<P>::MT][2], int g, int t) {
-  using E = EO<P>;
-#pragma unroll
-  for (int i = 0; i < E::MT; i++) a[i][0] = a[i][1] = b[i][0] = b[i][1] = 0.0;
-#pragma unroll 4
-  for (int ks = 0; ks < E::KS; ks++) {
-    const int kk = ks * 4 + t;
-    const double p = Xw[xaddr<P, RIGHT>(kk, g)];
-    const double q = Xw[xaddr<P, RIGHT>(P - 1 - kk, g)];
-    const double s = p + q, d = p - q;
-    double fa[E::MT], fb[E::MT];
-#pragma unroll
-    for (int i = 0; i < E::MT; i++) {
-      fa[i] = Ae[(i * 8 + g) * E::LDM + kk];
-      fb[i] = Bo[(i * 8 + g) * E::LDM + kk];
-    }
-#pragma unroll
-    for (int i = 0; i < E::MT; i++) {
-      if (RIGHT) {
-        dmma884(a[i][0], a[i][1], s, fa[i]);
-        dmma884(b[i][0], b[i][1], d, fb[i]);
-      } else {
-        dmma884(a[i][0], a[i][1], fa[i], s);
-        dmma884(b[i][0], b[i][1], fb[i], d);
-      }
-    }
-  }
-}
+                                        double (&b)[EO<P>::MT][2], int g, int t);
 
 // NT-block variant: one set of matrix fragments feeds NT line-blocks (block j at Xw + j*BE).
+// SB200_KSPLIT == 2: even and odd k-steps accumulate into two independent register sets that are added at the end - 2 x 2 x MT x NT
+// independent DMMAs between dependent ones, enough for ONE warp to keep the FP64 tensor pipe busy (the dependent-issue latency of a
+// DMMA is ~370 clk = 23 issue slots, profiles/r02_notes.md); costs 4*MT*NT more registers and changes the summation order.
+#ifndef SB200_KSPLIT
+#define SB200_KSPLIT 1
+#endif
 template <int P, int NT, bool RIGHT>
 __device__ __forceinline__ void eo_gemm_nt(const double* __restrict__ Ae, const double* __restrict__ Bo,
                                            const double* __restrict__ Xw, double (&a)[NT][EO<P>::MT][2],
                                            double (&b)[NT][EO<P>::MT][2], int g, int t) {
   using E = EO<P>;
   constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
+  constexpr int KSP = (SB200_KSPLIT == 2 && E::KS % 2 == 0) ? 2 : 1;
+  double a1[KSP == 2 ? NT : 1][E::MT][2], b1[KSP == 2 ? NT : 1][E::MT][2];
 #pragma unroll
   for (int j = 0; j < NT; j++)
 #pragma unroll
-    for (int i = 0; i < E::MT; i++) a[j][i][0] = a[j][i][1] = b[j][i][0] = b[j][i][1] = 0.0;
+    for (int i = 0; i < E::MT; i++) {
+      a[j][i][0] = a[j][i][1] = b[j][i][0] = b[j][i][1] = 0.0;
+      if (KSP == 2) a1[j][i][0] = a1[j][i][1] = b1[j][i][0] = b1[j][i][1] = 0.0;
+    }
 #pragma unroll 2
   for (int ks = 0; ks < E::KS; ks++) {
     const int kk = ks * 4 + t;
@@ -101,20 +86,43 @@ __device__ __forceinline__ void eo_gemm_nt(const double* __restrict__ Ae, const 
       fa[i] = Ae[(i * 8 + g) * E::LDM + kk];
       fb[i] = Bo[(i * 8 + g) * E::LDM + kk];
     }
+    const bool odd = KSP == 2 && (ks & 1);
 #pragma unroll
     for (int i = 0; i < E::MT; i++) {
 #pragma unroll
       for (int j = 0; j < NT; j++) {
+        double& a0r = odd ? a1[KSP == 2 ? j : 0][i][0] : a[j][i][0];
+        double& a1r = odd ? a1[KSP == 2 ? j : 0][i][1] : a[j][i][1];
+        double& b0r = odd ? b1[KSP == 2 ? j : 0][i][0] : b[j][i][0];
+        double& b1r = odd ? b1[KSP == 2 ? j : 0][i][1] : b[j][i][1];
         if (RIGHT) {
-          dmma884(a[j][i][0], a[j][i][1], s[j], fa[i]);
-          dmma884(b[j][i][0], b[j][i][1], d[j], fb[i]);
+          dmma884(a0r, a1r, s[j], fa[i]);
+          dmma884(b0r, b1r, d[j], fb[i]);
         } else {
-          dmma884(a[j][i][0], a[j][i][1], fa[i], s[j]);
-          dmma884(b[j][i][0], b[j][i][1], fb[i], d[j]);
+          dmma884(a0r, a1r, fa[i], s[j]);
+          dmma884(b0r, b1r, fb[i], d[j]);
         }
       }
     }
   }
+  if (KSP == 2) {
+#pragma unroll
+    for (int j = 0; j < NT; j++)
+#pragma unroll
+      for (int i = 0; i < E::MT; i++) {
+        a[j][i][0] += a1[j][i][0];
+        a[j][i][1] += a1[j][i][1];
+        b[j][i][0] += b1[j][i][0];
+        b[j][i][1] += b1[j][i][1];
+      }
+  }
+}
+
+template <int P, bool RIGHT>
+__device__ __forceinline__ void eo_gemm(const double* __restrict__ Ae, const double* __restrict__ Bo,
+                                        const double* __restrict__ Xw, double (&a)[EO<P>::MT][2],
+                                        double (&b)[EO<P>::MT][2], int g, int t) {
+  eo_gemm_nt<P, 1, RIGHT>(Ae, Bo, Xw, reinterpret_cast<double (&)[1][EO<P>::MT][2]>(a), reinterpret_cast<double (&)[1][EO<P>::MT][2]>(b), g, t);
 }
 
 // Thread-owned element geometry shared by every epilogue.  For tile i the thread owns a "top" pair
