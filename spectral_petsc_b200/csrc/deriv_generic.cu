@@ -189,11 +189,13 @@ template <int TM, int WM, int WN, bool LEFT>
 int launch_cfg(const DerivParams& p, cudaStream_t stream) {
   constexpr int TN = WN * 32;
   using Cfg = TileCfg<TM, TN, LEFT>;
-  static bool attr_set = false;
+  static bool attr_set[64] = {};  // the opt-in above 48 KB of dynamic shared memory is per device
   auto kern = deriv_kernel<TM, WM, WN, LEFT>;
-  if (!attr_set) {
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (!attr_set[cur_dev & 63]) {
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[cur_dev & 63] = true;
   }
   dim3 grid;
   if (LEFT) {

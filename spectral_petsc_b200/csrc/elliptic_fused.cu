@@ -170,13 +170,13 @@ int launch_chain(const ChainParams& p, cudaStream_t s) {
   constexpr int BE = RIGHT ? E::BLOCK_ELEMS_RIGHT : E::BLOCK_ELEMS_LEFT;
   const size_t smem = (size_t)(E::MAT_ELEMS + NWARPS * BE) * sizeof(double);
   auto kern = chain_kernel<P, RIGHT, POS>;
-  static bool attr = false;
-  if (!attr) {
-    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool attr[64] = {};  // the opt-in above 48 KB of dynamic shared memory is per device
+  if (!attr[dev & 63]) {
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[dev & 63] = true;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long nblocks = p.lg.nlines / 8;
   // one persistent CTA per SM; fewer when there is not a block per warp to hand out
