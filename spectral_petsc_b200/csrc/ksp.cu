@@ -346,7 +346,9 @@ int KspCtx::init(long long n_, int restart_, int rank, int nranks) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  nblocks = (int)std::min<long long>((n + TPB - 1) / TPB > 0 ? (n + TPB - 1) / TPB : 1, (long long)sms * 8);
+  int per_sm = 8;
+  if (const char* c = getenv("SB200_KSP_BLOCKS_PER_SM")) per_sm = atoi(c) > 0 ? atoi(c) : 8;  // tuning hook (8 measured best, profiles/r02_notes.md)
+  nblocks = (int)std::min<long long>((n + TPB - 1) / TPB > 0 ? (n + TPB - 1) / TPB : 1, (long long)sms * per_sm);
   SB_CUDA(cudaMalloc((void**)&partial, (size_t)nblocks * 64 * sizeof(double)));
   SB_CUDA(cudaMalloc((void**)&counters, 64 * sizeof(unsigned)));
   SB_CUDA(cudaMemset(counters, 0, 64 * sizeof(unsigned)));

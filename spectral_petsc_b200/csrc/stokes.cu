@@ -420,13 +420,14 @@ __global__ void pad_reduce_lastaxis_kernel(GridDesc gd, const double* __restrict
   const int lane = threadIdx.x & 31;
   const int d = gd.d, P = gd.dim[d - 1];
   if (line >= gd.m / P) return;
-  long long rem = line, gbase = 0;
+  long long rem = line, gbase = -gd.goff;  // slab view: axis-0 indices are global, ordinals local to this rank
   bool inter = true;
   for (int j = d - 2; j >= 0; j--) {
     const int dj = gd.dim[j];
-    const int ij = (int)(rem % dj);
+    const int il = (int)(rem % dj);
     rem /= dj;
-    inter = inter && ij >= 1 && ij <= dj - 2;
+    const int ij = gd.gidx(j, il), ext = gd.gext(j);
+    inter = inter && ij >= 1 && ij <= ext - 2;
     gbase += (long long)(ij - 1) * gd.istride[j];
   }
   if (!inter) return;
@@ -553,6 +554,14 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   SB_CUDA(cudaMalloc((void**)&vG1, std::max<size_t>(8, (size_t)gv * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&minmax, 2 * sizeof(double)));
   SB_CUDA(cudaMalloc((void**)&sync, 64));
+  if (nranks > 1) {
+    const char* c = getenv("SB200_STOKES_SIDE_STREAM");  // 0: everything on the caller's stream (round 1's order)
+    if (!c || atoi(c)) {
+      SB_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+      SB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+  }
   SB_CUDA(cudaMemset(sync, 0, 64));
   for (int k = 0; k < d; k++) {
     Dax[k] = nullptr;
@@ -581,6 +590,12 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
 }
 
 StokesCtx::~StokesCtx() {
+  if (aux_stream) {
+    cudaStreamSynchronize(aux_stream);
+    cudaStreamDestroy(aux_stream);
+  }
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   arena.destroy();
   if (dirichlet) cudaFree(dirichlet);
   if (force) cudaFree(force);
@@ -723,10 +738,20 @@ int StokesCtx::run_jobs(DerivParams* jobs, int d, cudaStream_t s) {
     if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
     return 0;
   }
-  // push the operand planes, do the local axes while they cross NVLink, then differentiate the pencil and push back
+  // The axis-0 chain (push the operand planes into the pencils, barrier, differentiate the pencil, push the rows back, barrier) runs on
+  // the caller's stream; the local axes run CONCURRENTLY on the context's side stream (their own ticket counters): the two pushes and the
+  // two cross-GPU barriers no longer sit in front of / behind 40 us of local work (profiles/r02_stokes_slab_profile_n2.txt).
+  if (d > 1 && aux_stream) {
+    SB_CUDA(cudaEventRecord(ev_fork, s));
+    SB_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+    SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync + 4, aux_stream));
+    SB_CUDA(cudaEventRecord(ev_join, aux_stream));
+  }
   SB_TRY(slab_deriv0_pencil_begin(arena, jobs[0], gd.dim[0], gd.i0, Xp, s));
-  if (d > 1) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
-  return slab_deriv0_pencil_finish(arena, jobs[0], gd.dim[0], Xp, Yp, s);
+  if (d > 1 && !aux_stream) SB_TRY(deriv_eo_batch(jobs + 1, d - 1, sync, s));
+  SB_TRY(slab_deriv0_pencil_finish(arena, jobs[0], gd.dim[0], Xp, Yp, s));
+  if (d > 1 && aux_stream) SB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+  return 0;
 }
 
 int StokesCtx::crop_sum(int nc, int nterms, double* const* terms, double sign, double* dst, int dstride, int doff, cudaStream_t s) {
@@ -845,9 +870,10 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   }
   // the divergence rows: inside the flux kernel (from the gradient in its registers) on the fused path, else a pass of their own
   // before the flux overwrites the gradient - the same arithmetic either way
+  // the divergence rows: written by the flux kernel from the gradient in its registers (the arithmetic of crop_trace_kernel; decode_node
+  // knows the slab view, so this holds on a partition too)
   DivDst dv{nullptr, 0, 0};
-  if (div_dst && fused) dv = DivDst{div_dst, div_stride, div_off};
-  else if (div_dst) SB_TRY(crop_trace(&workV[2], div_dst, div_stride, div_off, s));
+  if (div_dst) dv = DivDst{div_dst, div_stride, div_off};
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
@@ -913,7 +939,7 @@ int StokesCtx::divergence_into(const double* x, int xstride, int xoff, bool with
 // pL = the padded, boundary-extrapolated pressure of a global vector (stokes.C:606-609): pad + StokesPressureReduceOrder.
 int StokesCtx::pad_pres_reduced(const double* src, int sstride, int soff, double* pL, cudaStream_t s) {
   const int d = gd.d;
-  if (arena.nranks == 1 && gd.stride[d - 1] == 1 && gdim[d - 1] >= 3 && gd.m < (1ll << 31)) {
+  if (d >= 2 && gd.stride[d - 1] == 1 && gdim[d - 1] >= 3 && gd.m < (1ll << 31)) {
     const long long nlines = gd.m / gd.dim[d - 1];
     pad_reduce_lastaxis_kernel<<<(unsigned)((nlines * 32 + 255) / 256), 256, 0, s>>>(gd, src, sstride, soff, w0[d - 1], w1[d - 1], pL);
     count_launch();
@@ -1052,8 +1078,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
     for (int i = 0; i < d; i++) SB_TRY(deriv_v(i, xL, strain[i], nullptr, DERIV_STORE, s));   // :701
   }
   DivDst dv{nullptr, 0, 0};  // :746 from the gradient above (same Dirichlet-padded input): inside the rheology kernel on the fused path
-  if (trace_divergence && fusable()) dv = DivDst{yG, d + 1, d};
-  else if (trace_divergence) SB_TRY(crop_trace(strain, yG, d + 1, d, s));
+  if (trace_divergence) dv = DivDst{yG, d + 1, d};
   const double* pfold = nullptr;
   if (fold_pressure) {  // opt-in, as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750)
     SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], s));

@@ -37,6 +37,8 @@ struct StokesCtx {
   unsigned* sync = nullptr;  // counters of the even-odd derivative kernel
   double* Xp = nullptr;   // pencil operand / result buffers of the axis-0 derivative (m*d doubles each)
   double* Yp = nullptr;
+  cudaStream_t aux_stream = nullptr;  // slab: the local-axis derivative batch runs here, beside the axis-0 pencil chain on the caller's stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double* red = nullptr;  // [nranks][2][lines per plane]: partial end-point sums of the axis-0 extrapolation pass
 
   static int create(int d, const int* dim, int rank, int nranks, StokesCtx** out);
