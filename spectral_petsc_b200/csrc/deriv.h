@@ -13,6 +13,25 @@ enum DerivMode { DERIV_STORE = 0, DERIV_SUB = 1, DERIV_ADD = 2 };
 // Likewise the fused crop-sum epilogue (its term loads are dependent L2 round trips of the finishing job's warps): 180 us against
 // 100 + 55 us at 128^3 for the Stokes viscous tail; small grids gain the launch
 #define SB200_FUSE_CROP_MAX_NODES (1ll << 18)
+// Forward all-to-all of the slab partition folded into the kernel that PRODUCES the operand of an axis-0 derivative: element e of the
+// local field (planes x R elements, unit stride) also goes to the pencil of the rank that owns its column - Xp_q[(i0 + ml)*Rp + (c - q*Rp)]
+// with ml = e / R, c = e % R, q = c / Rp - so no separate push kernel reads the field again.
+#ifndef SB200_MAX_RANKS
+#define SB200_MAX_RANKS 8
+#endif
+struct SlabPush {
+  double* dst[SB200_MAX_RANKS] = {};
+  int on = 0, i0 = 0;
+  long long R = 1, Rp = 1;
+#ifdef __CUDACC__
+  __device__ __forceinline__ void store(long long e, double v) const {
+    const long long ml = e / R, c = e - ml * R;
+    const int q = (int)(c / Rp);
+    dst[q][(i0 + ml) * Rp + (c - (long long)q * Rp)] = v;
+  }
+#endif
+};
+
 // Grid geometry behind the lines of a job of the even-odd kernel (only needed by its fused pad / crop modes).
 struct EoLineMap {
   int d = 0, nc = 1, axis = 0;
@@ -62,6 +81,12 @@ struct DerivParams {
   const double* term[SB200_EO_MAX_JOBS - 1] = {};
   const double* sub = nullptr;
   double sign = 1.0;
+  // Backward all-to-all of the slab partition folded into the epilogue of the PENCIL derivative (O == 1, R = Rp columns, unit strides,
+  // DERIV_STORE or "0 - D x"): row m of the result belongs to rank m / peer_nloc and is stored straight into that rank's field,
+  // ypeer[q][(m - q*peer_nloc) * peer_R + peer_col0 + column]  (16-byte stores over NVLink), so no push kernel re-reads a pencil buffer.
+  double* ypeer[SB200_MAX_RANKS] = {};
+  int peer_on = 0, peer_nloc = 0, peer_negate = 0;
+  long long peer_R = 0, peer_col0 = 0;
 };
 enum { EO_FIN_NONE = 0, EO_FIN_SUM = 1, EO_FIN_RAW = 2 };
 
@@ -82,5 +107,7 @@ bool slab_deriv0_pencil_supported(const SymmArena& a, const DerivParams& p);
 int slab_deriv0_pencil(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, double* Yp, cudaStream_t s);
 int slab_deriv0_pencil_begin(SymmArena& a, const DerivParams& p, int nloc, int i0, double* Xp, cudaStream_t s);
 int slab_deriv0_pencil_finish(SymmArena& a, const DerivParams& p, int nloc, double* Xp, double* Yp, cudaStream_t s);
+// The push descriptor a producer kernel needs to fill the pencils of an axis-0 derivative of the field it writes (R elements per plane).
+SlabPush slab_make_push(const SymmArena& a, double* Xp, int i0, long long R);
 
 }  // namespace sb200

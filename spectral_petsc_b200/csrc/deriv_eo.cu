@@ -50,6 +50,10 @@ struct EoJob {
   const double* term[SB200_EO_MAX_JOBS - 1];
   const double* sub;
   double sign;
+  // pencil derivative of a slab partition: result rows go straight to their owners (see deriv.h)
+  double* ypeer[SB200_MAX_RANKS];
+  int peer_on, peer_nloc, peer_negate;
+  long long peer_R, peer_col0;
 };
 struct EoParams {
   EoJob job[SB200_EO_MAX_JOBS];
@@ -346,6 +350,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) eo_deriv_kernel(EoParams q) {
         }
       }
       }
+    } else if (FUSED && p.peer_on) {
+      // O == 1, unit strides, R % 8 == 0: columns n0 + 2t, +1 of row m -> the owner of plane m (16-byte peer stores)
+      const long long col = p.peer_col0 + n0 + 2 * t;
+#pragma unroll
+      for (int i = 0; i < MT; i++) {
+        const int mt = i * 8 + g, mb = n - mt;
+        if (!EXACT && mt >= hh) continue;
+        const int qt = mt / p.peer_nloc, qb = mb / p.peer_nloc;
+        double2 vt = make_double2(a[i][0] + b[i][0], a[i][1] + b[i][1]);
+        double2 vb = make_double2(b[i][0] - a[i][0], b[i][1] - a[i][1]);
+        if (p.peer_negate) {
+          vt = make_double2(0.0 - vt.x, 0.0 - vt.y);
+          vb = make_double2(0.0 - vb.x, 0.0 - vb.y);
+        }
+        st2(p.ypeer[qt] + (long long)(mt - qt * p.peer_nloc) * p.peer_R + col, vt.x, vt.y);
+        if (EXACT || mb != mt) st2(p.ypeer[qb] + (long long)(mb - qb * p.peer_nloc) * p.peer_R + col, vb.x, vb.y);
+      }
     } else if (p.vec) {
       const long long base = line_base(n0, R) + 2 * t;
 #pragma unroll
@@ -444,7 +465,7 @@ int launch_eo(const EoParams& q, cudaStream_t s) {
 template <int MT, int NWARPS>
 int launch_mt(const EoParams& q, cudaStream_t s) {
   bool fused = false;
-  for (int j = 0; j < q.njobs; j++) fused = fused || q.job[j].gsrc || q.job[j].gdst;
+  for (int j = 0; j < q.njobs; j++) fused = fused || q.job[j].gsrc || q.job[j].gdst || q.job[j].peer_on;
   if (q.P == 16 * MT) return fused ? launch_eo<MT, NWARPS, true, true>(q, s) : launch_eo<MT, NWARPS, true, false>(q, s);
   return fused ? launch_eo<MT, NWARPS, false, true>(q, s) : launch_eo<MT, NWARPS, false, false>(q, s);
 }
@@ -470,7 +491,7 @@ int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t 
   for (int j = 0; j < n; j++) {
     const DerivParams& p = jobs[j];
     SB_CHECK(deriv_eo_supported(p) && p.P == jobs[0].P && p.Ae == q.Ae, SB200_ERR_USER, "even-odd derivative: jobs must share the matrix");
-    SB_CHECK(p.gsrc || p.gdst || p.inplace_ok || p.x != p.y, SB200_ERR_ARG, "deriv: x and y must not alias (chebyshev.c:127)");
+    SB_CHECK(p.gsrc || p.gdst || p.inplace_ok || p.peer_on || p.x != p.y, SB200_ERR_ARG, "deriv: x and y must not alias (chebyshev.c:127)");
     SB_CHECK((!p.gsrc && !p.gdst) || (p.lm.d >= 1 && p.lm.d <= SB200_EO_MAX_JOBS && p.lm.nc >= 1), SB200_ERR_USER, "even-odd derivative: fused scatter without a line map");
     EoJob& e = q.job[j];
     e.x = p.x;
@@ -496,6 +517,14 @@ int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t 
     for (int t = 0; t < SB200_EO_MAX_JOBS - 1; t++) e.term[t] = p.term[t];
     e.sub = p.sub;
     e.sign = p.sign;
+    for (int r = 0; r < SB200_MAX_RANKS; r++) e.ypeer[r] = p.ypeer[r];
+    e.peer_on = p.peer_on;
+    e.peer_nloc = p.peer_nloc;
+    e.peer_negate = p.peer_negate;
+    e.peer_R = p.peer_R;
+    e.peer_col0 = p.peer_col0;
+    SB_CHECK(!p.peer_on || (!p.gdst && p.O == 1 && p.R % 8 == 0 && p.xs == 1 && p.peer_nloc >= 1 && p.peer_R % 2 == 0 && p.peer_col0 % 2 == 0), SB200_ERR_USER,
+             "even-odd derivative: the peer epilogue needs a unit-stride pencil with an even column range");
     e.self_pos = (p.gdst && p.fin == EO_FIN_SUM) ? (p.self_pos < 0 ? e.nterms : p.self_pos) : 0;
     SB_CHECK(e.self_pos >= 0 && e.self_pos <= e.nterms, SB200_ERR_USER, "even-odd derivative: bad chain position");
     e.fvec = p.gdst && p.fin == EO_FIN_SUM && e.nterms >= 1 && e.nterms <= 2 && !p.sub && (p.R % 8 == 0) && p.ys == 1 && p.yoff == 0 &&
@@ -507,8 +536,9 @@ int deriv_eo_batch(const DerivParams* jobs, int n, unsigned* sync, cudaStream_t 
       if (!q.count_done) q.wait_items = total;
       q.count_done = 1;
     }
-    e.vec = !p.gsrc && !p.gdst && (p.R % 8 == 0) && p.xs == 1 && p.ys == 1 && p.xoff == 0 && p.yoff == 0 &&
-            ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.yin)) % 16 == 0);
+    e.vec = !p.gsrc && !p.gdst && (p.R % 8 == 0) && p.xs == 1 && (p.peer_on || (p.ys == 1 && p.yoff == 0)) && p.xoff == 0 &&
+            ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.peer_on ? nullptr : p.y) | reinterpret_cast<uintptr_t>(p.yin)) % 16 == 0);
+    SB_CHECK(!p.peer_on || e.vec, SB200_ERR_USER, "even-odd derivative: the peer epilogue needs the 16-byte block loader (aligned pencil)");
     total += (unsigned)((e.nlines + 7) / 8);
     e.end = total;
   }

@@ -6,6 +6,8 @@
 // (G-1)/G of the WHOLE field per rank for the operand-pull scheme (deriv_generic.cu slab mode), which this replaces
 // whenever the column count divides by the number of ranks.  The "field" is the scalar view (P planes x R columns,
 // element stride / offset for AoS components) that DerivParams describes.
+#include <cstdlib>
+
 #include "../../include/spectral_b200.h"
 #include "common.cuh"
 #include "deriv.h"
@@ -92,6 +94,16 @@ int slab_deriv0_pencil_begin(SymmArena& a, const DerivParams& p, int nloc, int i
   return 0;
 }
 
+SlabPush slab_make_push(const SymmArena& a, double* Xp, int i0, long long R) {
+  SlabPush sp;
+  for (int q = 0; q < SB200_MAX_RANKS; q++) sp.dst[q] = q < a.nranks ? a.on(q, Xp) : nullptr;
+  sp.on = 1;
+  sp.i0 = i0;
+  sp.R = R;
+  sp.Rp = R / a.nranks;
+  return sp;
+}
+
 int slab_deriv0_pencil_finish(SymmArena& a, const DerivParams& p, int nloc, double* Xp, double* Yp, cudaStream_t s) {
   const int G = a.nranks;
   const long long R = p.R, Rp = R / G;
@@ -107,6 +119,25 @@ int slab_deriv0_pencil_finish(SymmArena& a, const DerivParams& p, int nloc, doub
   lp.xs = lp.ys = 1;
   lp.xoff = lp.yoff = 0;
   lp.npeer = 0;
+  // unit-stride result in an aligned even column range: the derivative's epilogue stores the rows straight into the plane owners'
+  // fields over NVLink (no pencil result buffer, no second push kernel)
+  static int peer_epi = -1;
+  if (peer_epi < 0) {
+    const char* c = getenv("SB200_SLAB_PEER_EPILOGUE");
+    peer_epi = c ? atoi(c) : 1;
+  }
+  if (peer_epi && p.ys == 1 && p.yoff == 0 && p.sync && Rp % 8 == 0 && R % 2 == 0 && deriv_eo_supported(lp) &&
+      reinterpret_cast<uintptr_t>(Xp) % 16 == 0 && reinterpret_cast<uintptr_t>(p.y) % 16 == 0) {
+    lp.y = nullptr;
+    lp.peer_on = 1;
+    lp.peer_nloc = nloc;
+    lp.peer_negate = p.mode == DERIV_SUB ? 1 : 0;
+    lp.peer_R = R;
+    lp.peer_col0 = (long long)a.rank * Rp;
+    for (int q = 0; q < G; q++) lp.ypeer[q] = py.dst[q];
+    SB_TRY(deriv_eo_apply(lp, p.sync, s));
+    return a.barrier(s);
+  }
   SB_TRY(deriv_apply(lp, s));
   push_to_slabs_kernel<<<blocks_for((long long)p.P * Rp), 256, 0, s>>>(Yp, py, p.ys, p.yoff, p.P, nloc, a.rank, R, Rp, p.mode == DERIV_SUB ? 1 : 0);
   count_launch();
