@@ -559,12 +559,15 @@ int StokesCtx::init(int d, const int* dim, int rank, int nranks) {
   SB_CUDA(cudaMalloc((void**)&vG1, std::max<size_t>(8, (size_t)gv * sizeof(double))));
   SB_CUDA(cudaMalloc((void**)&minmax, 2 * sizeof(double)));
   SB_CUDA(cudaMalloc((void**)&sync, 64));
-  if (nranks > 1) {
+  {
+    // side stream: on a slab partition the local-axis derivative batch runs there beside the axis-0 pencil chain; on one GPU the pressure
+    // pad + boundary extrapolation (small latency-bound kernels) run there beside the velocity pad and the gradient batch
     const char* c = getenv("SB200_STOKES_SIDE_STREAM");  // 0: everything on the caller's stream (round 1's order)
     if (!c || atoi(c)) {
       SB_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
       SB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&ev_pjoin, cudaEventDisableTiming));
     }
   }
   SB_CUDA(cudaMemset(sync, 0, 64));
@@ -601,6 +604,7 @@ StokesCtx::~StokesCtx() {
   }
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (ev_pjoin) cudaEventDestroy(ev_pjoin);
   arena.destroy();
   if (dirichlet) cudaFree(dirichlet);
   if (force) cudaFree(force);
@@ -905,6 +909,7 @@ int StokesCtx::matmult_vv_into(const double* x, int xstride, int xoff, double* d
   if (div_dst) dv = DivDst{div_dst, div_stride, div_off};
   const SlabPush push = push_for(workV[2]);  // slab: the flux kernel fills the pencils of the tail's axis-0 term itself
   if (push.on) prefilled = workV[2];
+  SB_TRY(join_pressure(s));  // the folded pressure prepared on the side stream
   if (d == 2) {
     VPtrs<2> p;
     for (int j = 0; j < 2; j++) { p.v[j] = workV[2 + j]; p.s[j] = strain[j]; }
@@ -979,6 +984,30 @@ int StokesCtx::pad_pres_reduced(const double* src, int sstride, int soff, double
   }
   SB_TRY(pad_pres(src, sstride, soff, pL, s));
   return pressure_reduce_order(pL, s);
+}
+
+// The folded pressure of StokesMatMult / StokesFunction (workP[0]): on one GPU prepared on the side stream while the caller's stream pads
+// and differentiates the velocity; the consumer (flux / rheology kernel) joins through join_pressure().  On a slab partition the
+// extrapolation contains cross-rank barriers, which must stay in the one stream order every rank shares: serial there.
+int StokesCtx::fold_pressure_begin(const double* xG, cudaStream_t s) {
+  const int d = gd.d;
+  if (arena.nranks == 1 && aux_stream) {
+    SB_CUDA(cudaEventRecord(ev_fork, s));
+    SB_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+    SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], aux_stream));
+    SB_CUDA(cudaEventRecord(ev_pjoin, aux_stream));
+    pressure_pending = true;
+    return 0;
+  }
+  return pad_pres_reduced(xG, d + 1, d, workP[0], s);
+}
+
+int StokesCtx::join_pressure(cudaStream_t s) {
+  if (pressure_pending) {
+    SB_CUDA(cudaStreamWaitEvent(s, ev_pjoin, 0));
+    pressure_pending = false;
+  }
+  return 0;
 }
 
 int StokesCtx::pressure_reduce_order(double* pL, cudaStream_t s, int first_pass) {
@@ -1083,7 +1112,7 @@ int StokesCtx::matmult(const double* xG, double* yG, cudaStream_t s) {
   const int d = gd.d;
   const double* pfold = nullptr;
   if (fold_pressure) {  // opt-in: the padded, boundary-extrapolated pressure (:606-609) enters the viscous flux as -p I
-    SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], s));
+    SB_TRY(fold_pressure_begin(xG, s));
     pfold = workP[0];
   }
   if (trace_divergence) {
@@ -1100,6 +1129,11 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   SB_CHECK(xG && yG && xG != yG, SB200_ERR_ARG, "StokesFunction: x and y must be distinct non-null vectors");
   const int d = gd.d;
   double* xL = workV[0];
+  const double* pfold = nullptr;
+  if (fold_pressure) {  // as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750); prepared
+    SB_TRY(fold_pressure_begin(xG, s));  // first (on one GPU on the side stream, beside the velocity pad and the gradient batch)
+    pfold = workP[0];
+  }
   SB_TRY(pad_vel(xG, d + 1, 0, true, xL, s, true));                                           // :691-699
   if (fusable() || batchable()) {
     DerivParams jobs[3];
@@ -1110,11 +1144,7 @@ int StokesCtx::function(const double* xG, double* yG, cudaStream_t s) {
   }
   DivDst dv{nullptr, 0, 0};  // :746 from the gradient above (same Dirichlet-padded input): inside the rheology kernel on the fused path
   if (trace_divergence) dv = DivDst{yG, d + 1, d};
-  const double* pfold = nullptr;
-  if (fold_pressure) {  // opt-in, as in matmult(): V = eta*eps - p I, so the viscous tail also yields the pressure gradient (:747-750)
-    SB_TRY(pad_pres_reduced(xG, d + 1, d, workP[0], s));
-    pfold = workP[0];
-  }
+  SB_TRY(join_pressure(s));
   init_minmax_kernel<<<1, 1, 0, s>>>(minmax);
   count_launch();
   Rheo r{rheology, hardness, exponent, regularization, gamma0};

@@ -38,7 +38,10 @@ struct StokesCtx {
   double* Xp = nullptr;   // pencil operand / result buffers of the axis-0 derivative (m*d doubles each)
   double* Yp = nullptr;
   cudaStream_t aux_stream = nullptr;  // slab: the local-axis derivative batch runs here, beside the axis-0 pencil chain on the caller's stream
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pjoin = nullptr;
+  bool pressure_pending = false;  // the folded pressure is being prepared on the side stream (join_pressure before its consumer)
+  int fold_pressure_begin(const double* xG, cudaStream_t s);
+  int join_pressure(cudaStream_t s);
   double* red = nullptr;  // [nranks][2][lines per plane]: partial end-point sums of the axis-0 extrapolation pass
 
   static int create(int d, const int* dim, int rank, int nranks, StokesCtx** out);
