@@ -66,6 +66,11 @@ int sb200_cheb_apply_host(sb200_cheb* c, const double* h_x, double* h_y);
 int sb200_cheb_destroy(sb200_cheb* c);
 /* The P x P differentiation matrix the kernels apply (row-major, host buffer of P*P doubles). */
 int sb200_cheb_matrix(int P, double* h_D);
+/* The two half-size matrices the even-odd kernels apply instead (any P >= 2; D is centro-antisymmetric): pair j couples nodes j and P-1-j
+ * (for odd P the middle node with itself), Ae = (D[i][j] + D[i][P-1-j]) / 2, Bo = (D[i][j] - D[i][P-1-j]) / 2, zero padded to HP x HP with
+ * HP = 8 * ceil(ceil(P/2) / 8); with s_j = u_j + u_{P-1-j}, d_j = u_j - u_{P-1-j}:  (D u)_i = (Ae s)_i + (Bo d)_i,  (D u)_{P-1-i} = (Bo d)_i - (Ae s)_i.
+ * *HP receives the padded size; h_Ae / h_Bo (HP*HP doubles each, row-major) may be NULL to query it. */
+int sb200_cheb_even_odd(int P, int* HP, double* h_Ae, double* h_Bo);
 
 /* ---- elliptic.C: MatCreate_Elliptic / MatMult_Elliptic / FormFunction ---------------------- */
 /* MatCreate_Elliptic(comm, d, dim, flag, bf, &vG, &A) (elliptic.C:250-293) with the all-Dirichlet

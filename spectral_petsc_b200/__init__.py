@@ -26,6 +26,7 @@ from .capi import (  # noqa: F401
     vec_pointwise_divide,
     vec_remove_mean,
     csr_diagonal,
+    cheb_even_odd,
 )
 
-__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution", "HostILU", "StokesSaddle", "vec_split", "vec_merge", "vec_axpby", "vec_pointwise_divide", "vec_remove_mean", "csr_diagonal"]
+__all__ = ["SB200Error", "lib", "lib_path", "launch_count", "Cheb", "Elliptic", "Stokes", "KSP", "cheb_matrix", "elliptic_exact_solution", "stokes_exact_solution", "HostILU", "StokesSaddle", "vec_split", "vec_merge", "vec_axpby", "vec_pointwise_divide", "vec_remove_mean", "csr_diagonal", "cheb_even_odd"]

@@ -75,6 +75,15 @@ def cheb_matrix(P):
     return D
 
 
+def cheb_even_odd(P):
+    """The zero-padded half-size matrices (Ae, Bo) of the even-odd kernels (host, numpy; sb200_cheb_even_odd)."""
+    hp = ctypes.c_int(0)
+    _ck(lib().sb200_cheb_even_odd(ctypes.c_int(P), ctypes.byref(hp), None, None))
+    Ae, Bo = np.empty((hp.value, hp.value)), np.empty((hp.value, hp.value))
+    _ck(lib().sb200_cheb_even_odd(ctypes.c_int(P), ctypes.byref(hp), _hptr(Ae), _hptr(Bo)))
+    return Ae, Bo
+
+
 def elliptic_exact_solution(dim, exact, cos_scale=0.0, gamma=0.0, exponent=2.0):
     """CreateExactSolution (elliptic.C:594-677) on the host: (u, u2, dirichlet) as numpy arrays in the reference's Vec order."""
     dim = [int(v) for v in dim]

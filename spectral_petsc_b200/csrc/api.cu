@@ -213,6 +213,19 @@ int sb200_cheb_matrix(int P, double* h_D) {
   return 0;
 }
 
+int sb200_cheb_even_odd(int P, int* HP, double* h_Ae, double* h_Bo) {
+  SB_CHECK(P >= 2 && HP, SB200_ERR_ARG, "bad arguments");
+  const int hp = ((P + 1) / 2 + 7) / 8 * 8;
+  *HP = hp;
+  if (!h_Ae && !h_Bo) return 0;
+  SB_CHECK(h_Ae && h_Bo, SB200_ERR_ARG, "bad arguments");
+  std::vector<double> Ae, Bo;
+  cgl_even_odd_padded(P, hp, Ae, Bo);
+  std::memcpy(h_Ae, Ae.data(), Ae.size() * sizeof(double));
+  std::memcpy(h_Bo, Bo.data(), Bo.size() * sizeof(double));
+  return 0;
+}
+
 // ---- elliptic ----------------------------------------------------------------------------
 int sb200_elliptic_create(int d, const int* dim, sb200_elliptic** out) {
   SB_CHECK(out && dim, SB200_ERR_ARG, "null pointer");

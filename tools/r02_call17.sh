@@ -9,4 +9,4 @@ for f in n8 n4; do python -c "import json; d=json.loads(open('$O/r02_bench_$f.js
 timeout 300 $TR --nproc-per-node 8 --master-port 29514 tests/dist/dist_check.py 32 64 128 > $O/r02_dist_check_n8.jsonl 2> $O/r02_dist_check_n8.err; echo "dist_check n8 exit $?"; cat $O/r02_dist_check_n8.jsonl
 timeout 300 $TR --nproc-per-node 8 --master-port 29515 tests/dist/dist_saddle.py 16 > $O/r02_dist_saddle_n8.jsonl 2> $O/r02_dist_saddle_n8.err; echo "dist_saddle n8 exit $?"; cat $O/r02_dist_saddle_n8.jsonl
 CUDA_VISIBLE_DEVICES=0,1 timeout 300 $TR --nproc-per-node 2 --master-port 29516 tests/dist/dist_saddle.py 32 > $O/r02_dist_saddle_n2.jsonl 2> $O/r02_dist_saddle_n2.err; echo "dist_saddle n2 exit $?"; cat $O/r02_dist_saddle_n2.jsonl
-tail -3 $O/r02_bench_n8.err $O/r02_dist_saddle_n8.err
+tail -n 3 $O/r02_bench_n8.err
