@@ -410,7 +410,7 @@ class Stokes:
                                             ctypes.c_double(regularization), ctypes.c_double(gamma0)))
 
     def set_trace_divergence(self, on):
-        """Opt-in: pressure rows of mat_mult / function from the trace of the gradient the viscous part computes (same bits)."""
+        """Evaluation switch (on by default): pressure rows of mat_mult / function from the trace of the gradient the viscous part computes (same bits)."""
         _ck(lib().sb200_stokes_set_trace_divergence(self._h, ctypes.c_int(int(on))))
 
     def set_graph(self, on):
@@ -418,7 +418,7 @@ class Stokes:
         _ck(lib().sb200_stokes_set_graph(self._h, ctypes.c_int(int(on))))
 
     def set_fold_pressure(self, on):
-        """Opt-in: the pressure gradient of mat_mult / function comes out of the viscous divergence (flux = eta*eps - p I)."""
+        """Evaluation switch (on by default): the pressure gradient of mat_mult / function comes out of the viscous divergence (flux = eta*eps - p I)."""
         _ck(lib().sb200_stokes_set_fold_pressure(self._h, ctypes.c_int(int(on))))
 
     def set_dirichlet(self, values):
