@@ -265,10 +265,12 @@ __device__ __forceinline__ void load_block_from_U(double* Xw, const double* __re
   }
   const int fast_hi = (fast == 0 ? sg.n0g : P) - 2;
   if (RIGHT) {
-    // lanes run along the line (contiguous in U); 8 lines, P/32 passes each
+    // lanes run along the line (contiguous in U); 8 lines, ceil(P/32) passes each
+    constexpr int PASSES = (P + 31) / 32;
 #pragma unroll 4
-    for (int i = 0; i < 8 * (P / 32); i++) {
-      const int c = i / (P / 32), m = lane + 32 * (i % (P / 32));
+    for (int i = 0; i < 8 * PASSES; i++) {
+      const int c = i / PASSES, m = lane + 32 * (i % PASSES);
+      if (m >= P) continue;
       const bool ok = inter && (dig_fast + c >= 1) && (dig_fast + c <= fast_hi) && m >= 1 && m <= P - 2;
       cp_async8(Xw + c * E::LDR + m, U + (ok ? gb + c * ist_fast + (m - 1) : 0), ok);
     }

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) chain_kernel(ChainParams p) {
       if (POS != POS_FIRST) {
 #pragma unroll
         for (int ii = 0; ii < 4; ii++) {
+          if (ib + ii >= E::MT) continue;  // (MT % 4 != 0: the last batch is short)
           ot[ii] = ld2(p.out + own.top(ib + ii));
           ob[ii] = ld2(p.out + own.bot(ib + ii));
         }
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) chain_kernel(ChainParams p) {
 #pragma unroll
       for (int ii = 0; ii < 4; ii++) {
         const int i = ib + ii;
+        if (i >= E::MT) continue;
         const double yt0 = a[i][0] + b[i][0], yt1 = a[i][1] + b[i][1];
         const double yb0 = RIGHT ? b[i][1] - a[i][1] : b[i][0] - a[i][0];
         const double yb1 = RIGHT ? b[i][0] - a[i][0] : b[i][1] - a[i][1];

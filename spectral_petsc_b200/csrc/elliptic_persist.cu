@@ -70,6 +70,7 @@ __device__ __forceinline__ void flux_load(FluxBuf& f, const Own<P, RIGHT>& own, 
                                           const double* __restrict__ deta, const double* __restrict__ g0) {
 #pragma unroll
   for (int ii = 0; ii < 2; ii++) {
+    if (ib + ii >= EO<P>::MT) continue;  // (odd MT: the last pair of tiles is a single tile)
     if (eta == nullptr) {
       f.e[ii][0] = f.e[ii][1] = make_double2(1.5, 1.5);
       f.de[ii][0] = f.de[ii][1] = f.gg[ii][0] = f.gg[ii][1] = make_double2(0.25, 0.25);
@@ -92,6 +93,7 @@ __device__ __forceinline__ void flux_apply(const FluxBuf& f, const Own<P, RIGHT>
 #pragma unroll
   for (int ii = 0; ii < 2; ii++) {
     const int i = ib + ii;
+    if (i >= EO<P>::MT) continue;
     const int st = own.stop(i), sb = own.sbot(i);
     const double2 wt = ld2(Xj + st), wb = ld2(Xj + sb);
     const double yt0 = a[i][0] + b[i][0], yt1 = a[i][1] + b[i][1];
@@ -181,11 +183,11 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
       // software pipeline: batch k+1 is in flight while batch k is applied
       if (j > 0) flux_load<P, RIGHT>(f0, own[j], 0, etap, deta_a, g0);
 #pragma unroll
-      for (int ib = 0; ib < E::MT; ib += 4) {
-        flux_load<P, RIGHT>(f1, own[j], ib + 2, etap, deta_a, g0);
+      for (int ib = 0; ib < E::MT; ib += 4) {  // (MT is even: tiles ib, ib+1 always exist; ib+2, ib+3 only when MT % 4 == 0 or ib + 4 <= MT)
+        if (ib + 2 < E::MT) flux_load<P, RIGHT>(f1, own[j], ib + 2, etap, deta_a, g0);
         flux_apply<P, RIGHT>(f0, own[j], ib, Xj, a[j], b[j]);
         if (ib + 4 < E::MT) flux_load<P, RIGHT>(f0, own[j], ib + 4, etap, deta_a, g0);
-        flux_apply<P, RIGHT>(f1, own[j], ib + 2, Xj, a[j], b[j]);
+        if (ib + 2 < E::MT) flux_apply<P, RIGHT>(f1, own[j], ib + 2, Xj, a[j], b[j]);
       }
     } else {
 #pragma unroll
@@ -305,6 +307,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
             const double* __restrict__ pk = p.part[k];
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {
+              if (ib + ii >= E::MT) continue;  // (MT % 4 != 0: the last batch is short)
               lt[k][ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].top(ib + ii)));
               lb[k][ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].bot(ib + ii)));
             }
@@ -313,6 +316,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
           for (int k = 0; k < 2; k++) {
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {
+              if (ib + ii >= E::MT) continue;
               ot[ii].x -= lt[k][ii].x;
               ot[ii].y -= lt[k][ii].y;
               ob[ii].x -= lb[k][ii].x;
@@ -325,11 +329,13 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
             double2 lt[4], lb[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {
+              if (ib + ii >= E::MT) continue;
               lt[ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].top(ib + ii)));
               lb[ii] = __ldcg(reinterpret_cast<const double2*>(pk + own[j].bot(ib + ii)));
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {
+              if (ib + ii >= E::MT) continue;
               ot[ii].x -= lt[ii].x;
               ot[ii].y -= lt[ii].y;
               ob[ii].x -= lb[ii].x;
@@ -341,6 +347,7 @@ __device__ __forceinline__ void run_item(const PersistParams& p, int axis, long 
 #pragma unroll
           for (int ii = 0; ii < 4; ii++) {
             const int i = ib + ii;
+            if (i >= E::MT) continue;
             const double yt0 = a[j][i][0] + b[j][i][0], yt1 = a[j][i][1] + b[j][i][1];
             const double yb0 = b[j][i][1] - a[j][i][1], yb1 = b[j][i][0] - a[j][i][0];
             const int mt = i * 8 + 2 * t, mb = P - 2 - i * 8 - 2 * t;  // first row of each pair
@@ -677,7 +684,7 @@ bool elliptic_persist_supported(const EllipticCtx& e) {
   const int P = e.gd.dim[0];
   for (int j = 1; j < d; j++)
     if (e.gd.dim[j] != P) return false;
-  return (P == 32 || P == 64 || P == 96 || P == 128) && (e.gd.m / P) % 16 == 0;
+  return P % 16 == 0 && P >= 32 && P <= 160 && (e.gd.m / P) % 16 == 0;
 }
 
 int persist_run(int P, PersistParams& p, cudaStream_t s) {
@@ -700,9 +707,13 @@ int persist_run(int P, PersistParams& p, cudaStream_t s) {
   switch (P) {
     case 32: return run_cfg<32, 16, 1>(p, s);
     case 64: return run_cfg<64, 16, 1>(p, s);
-    case 96:
-      SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: extent 96 is a single-GPU instantiation");
-      return run_cfg<96, 12, 1>(p, s);
+    // the extents between the powers of two: single-GPU instantiations of the same kernel (no extent cliff for P % 16 == 0 up to 160)
+    case 48: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<48, 16, 1>(p, s);
+    case 80: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<80, 12, 1>(p, s);
+    case 96: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<96, 12, 1>(p, s);
+    case 112: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<112, 12, 1>(p, s);
+    case 144: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<144, 8, 1>(p, s);
+    case 160: SB_CHECK(p.nranks == 1, SB200_ERR_SUP, "persistent path: this extent is a single-GPU instantiation"); return run_cfg<160, 8, 1>(p, s);
     case 128:
       switch (cfg >= 0 ? cfg : (p.nranks > 1 ? 2 : 1)) {
         case 0: return run_cfg<128, 16, 1>(p, s);

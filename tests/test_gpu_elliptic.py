@@ -114,9 +114,10 @@ def test_fused_chain_path_matches_generic_and_oracle(cuda, dim):
     assert np.array_equal(V3, V3b)
 
 
-@pytest.mark.parametrize("dim", [[96, 96], [96, 96, 96]], ids=str)
+@pytest.mark.parametrize("dim", [[96, 96], [96, 96, 96], [48, 48, 48], [80, 80, 80], [112, 112], [112, 112, 112], [144, 144], [160, 160]], ids=str)
 def test_persistent_chain_at_96(cuda, dim):
-    """P = 96 (H = 48, 6 pair tiles): the persistent chain kernel is the default path there too; against the oracle and the generic path."""
+    """Every extent P % 16 == 0 from 32 to 160 runs the persistent chain kernel by default (P = 96: 6 pair tiles; 48 / 80 / 112 / 144: an odd
+    number of tiles; 144 / 160: 9 / 10 tiles); against the oracle and the generic path."""
     O, G, u, u2 = make_pair(dim, 4.0, 2.0, cuda)
     Us = 0.1 * np.random.default_rng(1).standard_normal(O.g)
     O.form_function(Us)

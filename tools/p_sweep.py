@@ -51,7 +51,7 @@ def rows(steps=10, Ps=(16, 32, 48, 64, 96, 128, 129), dev=None, flush=None):
         V = torch.empty_like(U)
         fl, by = 6 * 2.0 * P * m, 8.0 * (2 * E.g + 5 * m)  # 2d derivatives; U, V, eta, deta, gradu[3] once each
         for path, name in ((1, "generic"), (2, "chain per axis"), (3, "persistent chain")):
-            if (path == 2 and P not in (32, 64, 128)) or (path == 3 and P not in (32, 64, 96, 128)):
+            if (path == 2 and P not in (32, 64, 128)) or (path == 3 and not (P % 16 == 0 and 32 <= P <= 160)):
                 continue
             E.set_path(path)
             l0 = sp.launch_count()
