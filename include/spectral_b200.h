@@ -122,7 +122,7 @@ int sb200_elliptic_jacobian_csr(sb200_elliptic* e, int* d_rowptr, int* d_colidx,
 int sb200_elliptic_pad(sb200_elliptic* e, const double* d_U, int with_dirichlet, double* d_local, void* stream);
 int sb200_elliptic_crop(sb200_elliptic* e, const double* d_local, double* d_U, void* stream);
 /* Select kernel path: 0 = auto, 1 = generic per-axis kernels, 2 = one fused chain kernel per axis,
- * 3 = single persistent chain kernel (2 and 3 need equal extents P in {32, 64, 128}), 4 = the generic kernels captured once
+ * 3 = single persistent chain kernel (2 needs equal extents P in {32, 64, 128}, 3 equal extents P % 16 == 0 from 32 to 160), 4 = the generic kernels captured once
  * into a CUDA graph and replayed (opt-in for the small, launch-bound grids; single GPU; same arithmetic as path 1). */
 int sb200_elliptic_set_path(sb200_elliptic* e, int path);
 /* Debug hook (only active in SB200_TRACE builds): device buffer receiving per-item phase clocks. */
